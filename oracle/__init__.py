@@ -1,0 +1,138 @@
+"""TEST INFRASTRUCTURE -- not part of the product.
+
+ctypes doors onto
+  * ``oracle/librmoracle.so``             -- the C restatement (recometrics_oracle.c)
+  * ``oracle/_ref/librecometrics_ref.so`` -- the unmodified reference compiled by oracle/Makefile
+
+Only tests/, ``__graft_entry__.smoke()`` and bench.py's cpu_baseline / ``--impl reference`` legs may
+import this module.  ``recometrics_b200`` never does.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "librmoracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "librecometrics_ref.so")
+
+METRICS = ("p", "tp", "r", "ap", "tap", "ndcg", "hit", "rr", "roc", "pr")
+ALL_METRICS = METRICS
+_TOPK = METRICS[:8]
+
+_vp = ctypes.c_void_p
+_i32 = ctypes.c_int32
+_int = ctypes.c_int
+_sz = ctypes.c_size_t
+_u64 = ctypes.c_uint64
+
+
+def build(force=False):
+    """Compile the restatement (always possible) and, when /root/reference exists, oracle/_ref."""
+    if force or not os.path.exists(ORACLE_SO) or (os.path.isdir("/root/reference/src") and not os.path.exists(REF_SO)):
+        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+_libs = {}
+
+
+def _lib(path):
+    if path not in _libs:
+        _libs[path] = ctypes.CDLL(path)
+    return _libs[path]
+
+
+def _ptr(a):
+    return _vp(a.ctypes.data) if (a is not None and a.size) else _vp(None)
+
+
+def _prep(A, B, Xtr, Xte, dtype):
+    A = np.ascontiguousarray(A, dtype=dtype)
+    B = np.ascontiguousarray(B, dtype=dtype)
+    trp = np.ascontiguousarray(Xtr.indptr, dtype=np.int32)
+    tri = np.ascontiguousarray(Xtr.indices, dtype=np.int32)
+    tep = np.ascontiguousarray(Xte.indptr, dtype=np.int32)
+    tei = np.ascontiguousarray(Xte.indices, dtype=np.int32)
+    tev = np.ascontiguousarray(Xte.data, dtype=dtype)
+    return A, B, trp, tri, tep, tei, tev
+
+
+def _alloc_outs(metrics, m, K, cumulative, dtype):
+    outs = {}
+    for name in METRICS:
+        if name in metrics:
+            size = m * K if (cumulative and name in _TOPK) else m
+            # poison so that "left untouched" is visible
+            outs[name] = np.full(size, -12345.0, dtype=dtype)
+        else:
+            outs[name] = None
+    return outs
+
+
+def _shape_outs(outs, m, K, cumulative):
+    res = {}
+    for name, a in outs.items():
+        if a is None:
+            continue
+        res[name] = a.reshape(m, K) if (cumulative and name in _TOPK) else a
+    return res
+
+
+def ref_calc(A, B, Xtr, Xte, k, metrics=("p", "ap", "ndcg"), cumulative=False,
+             consider_cold_start=True, min_items_pool=2, min_pos_test=1, nthreads=1,
+             break_ties_with_noise=False, seed=1, dtype=np.float32):
+    """Run the UNMODIFIED reference (calc_metrics_float/_double, recometrics_signatures.hpp:46-98)."""
+    lib = _lib(REF_SO)
+    A, B, trp, tri, tep, tei, tev = _prep(A, B, Xtr, Xte, dtype)
+    m, n, p = A.shape[0], B.shape[0], A.shape[1]
+    outs = _alloc_outs(metrics, m, k, cumulative, dtype)
+    fn = lib.rmref_calc_metrics_f32 if dtype == np.float32 else lib.rmref_calc_metrics_f64
+    fn.restype = _int
+    rc = fn(_ptr(A), _sz(A.shape[1]), _ptr(B), _sz(B.shape[1]), _i32(m), _i32(n), _i32(p),
+            _ptr(trp), _ptr(tri), _ptr(tep), _ptr(tei), _ptr(tev),
+            _i32(k), _int(int(cumulative)), _int(int(break_ties_with_noise)),
+            *[_ptr(outs[q]) for q in METRICS],
+            _int(int(consider_cold_start)), _i32(min_items_pool), _i32(min_pos_test),
+            _i32(nthreads), _u64(seed))
+    if rc != 0:
+        raise RuntimeError("reference threw")
+    return _shape_outs(outs, m, k, cumulative)
+
+
+def oracle_calc(A, B, Xtr, Xte, k, metrics=("p", "ap", "ndcg"), cumulative=False,
+                consider_cold_start=True, min_items_pool=2, min_pos_test=1, nthreads=1,
+                fix_quirks=True, extras=False, dtype=np.float32):
+    """Run the C restatement.  With extras=True also returns status / top-K ids+scores / ranks."""
+    lib = _lib(ORACLE_SO)
+    A, B, trp, tri, tep, tei, tev = _prep(A, B, Xtr, Xte, dtype)
+    m, n, p = A.shape[0], B.shape[0], A.shape[1]
+    outs = _alloc_outs(metrics, m, k, cumulative, dtype)
+    status = np.zeros(m, dtype=np.int32)
+    topk_items = np.zeros(m * k, dtype=np.int32) if extras else None
+    topk_scores = np.zeros(m * k, dtype=dtype) if extras else None
+    pos_rank = np.zeros(max(int(tep[-1]), 1), dtype=np.int64) if extras else None
+    tie_flags = np.zeros(m, dtype=np.int32) if extras else None
+    fn = lib.rmo_calc_metrics_f32 if dtype == np.float32 else lib.rmo_calc_metrics_f64
+    fn.restype = _int
+    rc = fn(_ptr(A), _sz(A.shape[1]), _ptr(B), _sz(B.shape[1]), _i32(m), _i32(n), _i32(p),
+            _ptr(trp), _ptr(tri), _ptr(tep), _ptr(tei), _ptr(tev),
+            _i32(k), _int(int(cumulative)),
+            *[_ptr(outs[q]) for q in METRICS],
+            _int(int(consider_cold_start)), _i32(min_items_pool), _i32(min_pos_test),
+            _i32(nthreads), _int(int(fix_quirks)),
+            _ptr(status), _ptr(topk_items), _ptr(topk_scores), _ptr(pos_rank), _ptr(tie_flags))
+    if rc != 0:
+        raise MemoryError("oracle allocation failed")
+    res = _shape_outs(outs, m, k, cumulative)
+    if extras:
+        res["status"] = status
+        res["topk_items"] = topk_items.reshape(m, k)
+        res["topk_scores"] = topk_scores.reshape(m, k)
+        res["pos_rank"] = pos_rank[: int(tep[-1])]
+        res["tie_flags"] = tie_flags
+    return res
