@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- evaluated users/sec of the per-user evaluation path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle/_ref)
+
+A "step" is one pass of the hot path (one calc_metrics call) over one batch of synthetic input: the
+users of the configuration named in config.workload (default: BASELINE configs[3], the 1M x 1M
+catalogue the north-star quotes its target on; it fits one B200).  One process per GPU; under
+torchrun every rank evaluates its own block of `--users` users against its own replica of B
+("weak" scaling, no data-path collective: the path has no exchange step).
+
+  value     users/s with A, B, the CSR matrices and the outputs resident in HBM when the timed
+            region starts (C-ABI call with inputs_on_device=1), CUDA events, max over ranks.
+  e2e       the same call through the reference-facing API with HOST (pinned) buffers: host->device
+            copies of that step's inputs and device->host copies of its metric rows inside the timed
+            region.
+  roofline  FP32 (FP64) FMA pipe of the scoring kernel: algorithmic flops 2*p'*sum_eligible(n-ntrain)
+             / the kernel's CUDA-event time, against the FMA peak measured live.
+  cpu_baseline  the reference's own OpenMP/SIMD implementation (oracle/_ref; the C port if absent)
+            on this box's host cores, on a bounded prefix of the same users.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+from tools import synth  # noqa: E402
+
+METRIC = "evaluated_users_per_sec"
+UNIT = "users/s"
+METRIC_FLAGS = dict(p="precision", tp="trunc_precision", r="recall", ap="average_precision",
+                    tap="trunc_average_precision", ndcg="ndcg", hit="hit", rr="rr", roc="roc_auc", pr="pr_auc")
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+def workload_name(cfg, users):
+    return "%s; users/GPU=%d" % (cfg.name, users)
+
+
+# ----------------------------------------------------------------------------- CPU arms
+def cpu_arm_callable():
+    """The CPU implementation to time: the compiled reference when it travelled, else the C port."""
+    import oracle
+    oracle.build()
+    if oracle.have_ref():
+        return "reference", oracle
+    return "port", oracle
+
+
+def run_cpu(kind, oracle, d, cfg, nthreads):
+    A, B = synth.fold_biases(d["A"], d["B"], d["item_biases"])   # what the reference front-end does
+    kw = dict(metrics=cfg.metrics, cumulative=cfg.cumulative, nthreads=nthreads, min_pos_test=cfg.min_pos_test,
+              dtype=cfg.dtype)
+    t0 = time.perf_counter()
+    if kind == "reference":
+        oracle.ref_calc(A, B, d["X_train"], d["X_test"], cfg.k, **kw)
+    else:
+        oracle.oracle_calc(A, B, d["X_train"], d["X_test"], cfg.k, fix_quirks=False, **kw)
+    return time.perf_counter() - t0
+
+
+def cpu_sample_size(kind, oracle, cfg, cores, target_s, n_items):
+    """Pilot on a few users, then size the sample for ~target_s seconds of CPU work."""
+    pilot = max(2 * cores, 16)
+    d = synth.make(cfg.cfg_id, m=pilot, n=n_items)
+    dt = max(run_cpu(kind, oracle, d, cfg, cores), 1e-4)
+    users = int(min(max(pilot, target_s * pilot / dt), 200000))
+    users = max(cores, (users // cores) * cores)
+    return users
+
+
+def reference_arm(args, cfg, rank):
+    """--impl reference: the reference's CPU path, all host threads, bounded sample per step."""
+    if rank != 0:
+        return
+    kind, oracle = cpu_arm_callable()
+    cores = os.cpu_count() or 1
+    users = cpu_sample_size(kind, oracle, cfg, cores, 4.0, args.items)
+    d = synth.make(cfg.cfg_id, m=users, n=args.items)
+    for _ in range(args.warmup):
+        run_cpu(kind, oracle, d, cfg, cores)
+    t = [run_cpu(kind, oracle, d, cfg, cores) for _ in range(args.steps)]
+    sec = float(np.mean(t))
+    value = users / sec
+    sample = "first %d users of the workload per step (users are independent; OpenMP schedule(dynamic))" % users
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32" if cfg.dtype == np.float32 else "f64", "data": "synthetic",
+        "config": {"workload": workload_name(cfg, args.users), "items": args.items, "k_metrics": cfg.k,
+                   "factors": cfg.p, "metrics": list(cfg.metrics), "cpu_sample_users_per_step": users},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(prefix="rmb200_clocks_", suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            hot = [s for s, p in zip(sm, power) if p >= 0.5 * max(power)] or sm
+            out = {"sm_mhz": float(np.median(hot)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                   "samples": len(sm), "power_w_max": float(max(power))}
+        return out
+
+
+# ----------------------------------------------------------------------------- product arm
+def product_arm(args, cfg, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    import recometrics_b200 as rb
+    from recometrics_b200 import _capi
+
+    if not torch.cuda.is_available() or rb.device_count() == 0:
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path to measure")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    T = cfg.dtype
+    tdt = torch.float32 if T == np.float32 else torch.float64
+    users = args.users
+    d = synth.make(cfg.cfg_id, m=users, n=args.items, seed_shift=rank)   # every rank: its own users, same B shape
+    A, B, bias = d["A"], d["B"], d["item_biases"]
+    Xtr, Xte = d["X_train"], d["X_test"]
+    m, n, p = A.shape[0], B.shape[0], A.shape[1]
+    K = cfg.k
+    flops = synth.algorithmic_flops(cfg, Xtr, Xte, has_ndcg="ndcg" in cfg.metrics)
+    rs = K if cfg.cumulative else 1
+
+    def pinned(x):
+        t = torch.from_numpy(np.ascontiguousarray(x))
+        try:
+            return t.pin_memory()
+        except Exception:
+            return t
+
+    # host side (pinned) for e2e; device side for `value`
+    hA, hB = pinned(A), pinned(B)
+    hb = pinned(bias) if bias is not None else None
+    htrp, htri, htep, htei = pinned(Xtr.indptr), pinned(Xtr.indices), pinned(Xte.indptr), pinned(Xte.indices)
+    htev = pinned(Xte.data.astype(T))
+    houts = {q: pinned(np.empty(m * (rs if q in _capi.TOPK_METRICS else 1), dtype=T)) for q in cfg.metrics}
+    dA, dB = hA.to(dev), hB.to(dev)
+    db = hb.to(dev) if hb is not None else None
+    dtrp, dtri, dtep, dtei, dtev = (x.to(dev) for x in (htrp, htri, htep, htei, htev))
+    douts = {q: torch.empty(m * (rs if q in _capi.TOPK_METRICS else 1), dtype=tdt, device=dev) for q in cfg.metrics}
+
+    def call(on_device, timing):
+        ex = _capi.make_extra(device=local_rank, inputs_on_device=on_device, timing=timing)
+        if on_device:
+            ptr = lambda t: t.data_ptr() if t is not None else None
+            outs = {q: v.data_ptr() for q, v in douts.items()}
+            rc = _capi.calc_metrics(T, ptr(dA), p, ptr(dB), p, m, n, p, ptr(dtrp), ptr(dtri), ptr(dtep), ptr(dtei), ptr(dtev),
+                                    K, cfg.cumulative, False, outs, True, 2, cfg.min_pos_test, item_biases=ptr(db), extra=ex)
+        else:
+            npv = lambda t: t.numpy() if t is not None else None
+            outs = {q: v.numpy() for q, v in houts.items()}
+            rc = _capi.calc_metrics(T, npv(hA), p, npv(hB), p, m, n, p, npv(htrp), npv(htri), npv(htep), npv(htei), npv(htev),
+                                    K, cfg.cumulative, False, outs, True, 2, cfg.min_pos_test, item_biases=npv(hb), extra=ex)
+        _capi.raise_for_status(rc)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # measured FMA peak (roofline denominator) -- before the timed region
+    peak_tflops, _ = _capi.measure_fma_peak(local_rank, T)
+
+    # ---- device-resident timing: W warm-up steps, then exactly K timed steps
+    tm = _capi.Timing()
+    for _ in range(args.warmup):
+        call(True, tm)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    kernel_ms, launches = 0.0, 0
+    e0.record()
+    for _ in range(args.steps):
+        call(True, tm)
+        kernel_ms += tm.score_select_ms
+        launches += tm.kernel_launches
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    dev_ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms = float(t.item())
+    value = world * m * args.steps / (dev_ms * 1e-3)
+
+    # ---- end-to-end through the host-pointer C-ABI (H2D of inputs + D2H of metric rows inside)
+    call(False, tm)   # one warm-up
+    barrier()
+    t0 = time.perf_counter()
+    h2d = d2h = 0
+    for _ in range(args.steps):
+        call(False, tm)
+        h2d, d2h = tm.h2d_bytes, tm.d2h_bytes
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * m * args.steps / e2e_s
+
+    # ---- roofline of the dominant kernel (score_select): algorithmic flops / CUDA-event kernel time
+    ach = flops * args.steps / (kernel_ms * 1e-3) / 1e12
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(str(cfg.cfg_id))
+        except Exception:
+            traffic = None
+    roofline = {
+        "bound": "fp32_fma" if T == np.float32 else "fp64_fma", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": ach / peak_tflops if peak_tflops > 0 else None, "traffic": traffic,
+        "kernel": "score_select_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+        "kernel_share_of_step": kernel_ms / dev_ms if world == 1 else None,
+        "algorithmic_flops_per_step": flops, "launches_per_step": -(-m // (8 * 148 * 128)),
+        "peak_source": "FMA microbenchmark run live on this GPU (rmb200_measure_fma_peak): MEASURED_PEAKS.json holds "
+                       "HBM and bf16-tensor peaks only; nominal %s" % ("74.4 TFLOP/s FP32" if T == np.float32 else "37.2 TFLOP/s FP64"),
+    }
+    try:
+        mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        roofline["hbm_peak_gbs_measured"] = mp.get("hbm_gbs")
+    except Exception:
+        pass
+
+    # ---- CPU baseline: the reference's implementation on this box's cores (rank 0, N=1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        kind, oracle = cpu_arm_callable()
+        cores = os.cpu_count() or 1
+        cu = cpu_sample_size(kind, oracle, cfg, cores, 12.0, args.items)
+        dd = synth.make(cfg.cfg_id, m=cu, n=args.items)
+        sec = run_cpu(kind, oracle, dd, cfg, cores)
+        cpu = {"value": cu / sec, "unit": UNIT, "cores": cores, "kind": kind,
+               "sample": "first %d users of the workload, %d threads, %.1f s" % (cu, cores, sec)}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if T == np.float32 else "f64", "data": "synthetic",
+            "config": {"workload": workload_name(cfg, users), "users_per_gpu": m, "items": n, "factors": p,
+                       "k_metrics": K, "metrics": list(cfg.metrics), "cumulative": bool(cfg.cumulative),
+                       "l2": "inputs (A+B+CSR = %.0f MB) larger than the 126 MB L2; no flush" % (
+                           (A.nbytes + B.nbytes + Xtr.indices.nbytes + Xte.indices.nbytes) / 1e6),
+                       "parallelism": "users block-partitioned, B replicated, no data-path collective"},
+            "roofline": roofline, "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_s * 1e3 / args.steps},
+            "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", type=int, default=4, help="BASELINE.json configs index + 1 (default 4: 1M x 1M, K=100)")
+    ap.add_argument("--users", type=int, default=0, help="users per GPU (default: the configuration's m)")
+    ap.add_argument("--items", type=int, default=0, help="items (default: the configuration's n)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    cfg = synth.CONFIGS[args.config]
+    args.users = args.users or cfg.m
+    args.items = args.items or cfg.n
+    rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if world == 1 and args.gpus > 1 and args.impl == "b200":
+        # convenience: re-launch under torchrun, one rank per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    if args.impl == "reference":
+        reference_arm(args, cfg, rank)
+    else:
+        product_arm(args, cfg, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

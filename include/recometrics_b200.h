@@ -1,0 +1,159 @@
+/* recometrics_b200.h -- C-ABI of librecometrics_b200.so
+ *
+ * B200-native (sm_100a) implementation of the per-user evaluation path of david-cortes/recometrics.
+ * The entry points below are what the reference's own bindings bind for that path:
+ *
+ *   reference interface (replaced)                                         this library
+ *   ---------------------------------------------------------------------  ---------------------------
+ *   calc_metrics_float   src/recometrics_signatures.hpp:73-98              rmb200_calc_metrics_f32
+ *     (defined src/recometrics_instantiated.cpp:94-143,
+ *      called from recometrics/wrapper.pyx:381-403)
+ *   calc_metrics_double  src/recometrics_signatures.hpp:48-72              rmb200_calc_metrics_f64
+ *     (defined src/recometrics_instantiated.cpp:43-92,
+ *      called from recometrics/wrapper.pyx:282-304)
+ *   calc_metrics<real_t> src/recometrics.hpp:359-385                       both of the above
+ *     (called directly from src/Rwrapper.cpp:250-274)                      (via include/recometrics_b200_shim.hpp)
+ *   get_has_openmp       src/recometrics_signatures.hpp:46                 rmb200_device_count() > 0
+ *   std::runtime_error on SIGINT, src/recometrics.hpp:167-173, :964        RMB200_ERR_INTERRUPTED
+ *
+ * Parameter order, types and meaning of the first 30 arguments are those of the reference
+ * (bool -> int so that the boundary is plain C).  All pointers are HOST pointers owned by the
+ * caller unless rmb200_extra_t::inputs_on_device says otherwise; outputs may be uninitialised on
+ * entry and EVERY element of every non-NULL output is written (NaN rows included), as the
+ * reference does (np.empty outputs, recometrics/wrapper.pyx:270-280).  A NULL output pointer means
+ * "metric not requested" (wrapper.pyx:208-224).  Data problems of single users never raise:
+ * they give NaN rows (src/recometrics.hpp:193-209).
+ *
+ * There is no CPU fallback: without a CUDA device every compute entry returns RMB200_ERR_NO_DEVICE.
+ */
+#ifndef RECOMETRICS_B200_H
+#define RECOMETRICS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__) || defined(__clang__)
+#   define RMB200_API __attribute__((visibility("default")))
+#else
+#   define RMB200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMB200_VERSION 100 /* 0.1.0 */
+
+enum rmb200_status {
+    RMB200_OK = 0,
+    RMB200_ERR_BAD_ARG = 1,      /* inconsistent sizes / NULL where data is required          */
+    RMB200_ERR_NO_DEVICE = 2,    /* no usable CUDA device (no CPU fallback exists)            */
+    RMB200_ERR_CUDA = 3,         /* a CUDA call failed; see rmb200_last_error()               */
+    RMB200_ERR_OOM = 4,          /* device or host allocation failed (reference: bad_alloc)   */
+    RMB200_ERR_INTERRUPTED = 5,  /* SIGINT arrived during the call (reference: runtime_error) */
+    RMB200_ERR_UNSUPPORTED = 6   /* valid request outside what this build implements          */
+};
+
+/* Largest k_metrics the fused top-K selection handles in this build. */
+#define RMB200_MAX_K 384
+
+/* Per-call timing breakdown (milliseconds, CUDA events on the call's stream). */
+typedef struct rmb200_timing {
+    double total_ms;        /* whole call, host clock                                           */
+    double h2d_ms;          /* host->device staging (0 when inputs_on_device)                   */
+    double prep_ms;         /* layout kernels: factor transposes, held-out item scores, sorting  */
+    double score_select_ms; /* the fused score + exclude + top-K (+rank counting) kernel        */
+    double metrics_ms;      /* per-user metrics kernel                                          */
+    double d2h_ms;          /* device->host result copies                                       */
+    int64_t kernel_launches;/* kernels of this library launched by the call                     */
+    int64_t h2d_bytes, d2h_bytes;
+} rmb200_timing_t;
+
+/* Optional extension block (pass NULL for reference behaviour).  Zero-initialise, then set
+ * struct_size = sizeof(rmb200_extra_t). */
+typedef struct rmb200_extra {
+    int32_t struct_size;
+    int32_t device;             /* CUDA device ordinal; -1 = env RMB200_DEVICE or 0                    */
+    int32_t user_begin;         /* evaluate only users [user_begin, user_end) -- the unit by which a   */
+    int32_t user_end;           /* job is sharded over GPUs/processes; 0,0 = all m users.  Arrays keep */
+                                /* their full-size indexing: row u of every output is written at u.    */
+    int32_t inputs_on_device;   /* 1: A, B, item_biases, the CSR arrays AND all outputs are device     */
+                                /* pointers on `device` (HBM-resident call, no host copies)            */
+    int32_t strict_min_pos_test;/* 1: honour min_pos_test as documented; 0 (default): reproduce the    */
+                                /* reference, which clamps it to <= 1 (src/recometrics.hpp:393)        */
+    int32_t *topk_items;        /* optional out [m * k_metrics]: ranked item ids, -1 where undefined   */
+    void    *topk_scores;       /* optional out [m * k_metrics] (float or double): their scores        */
+    int64_t *pos_rank;          /* optional out [nnz_test]: 1-based rank of every held-out item among  */
+                                /* the user's candidates (0 where not computed); forces rank counting  */
+    int32_t *status;            /* optional out [m]: 0 computed, 1 not eligible (hpp:439-448),         */
+                                /* 2 NaN by the cand<=K rule (hpp:485-486), 3 NaN by score validity     */
+    rmb200_timing_t *timing;    /* optional out                                                        */
+} rmb200_extra_t;
+
+/* Drop-in for calc_metrics_float (src/recometrics_signatures.hpp:73-98).  Returns rmb200_status. */
+RMB200_API int rmb200_calc_metrics_f32(
+    const float *A, size_t lda, const float *B, size_t ldb,
+    int32_t m, int32_t n, int32_t k,
+    const int32_t *Xtrain_csr_p, const int32_t *Xtrain_csr_i,
+    const int32_t *Xtest_csr_p, const int32_t *Xtest_csr_i, const float *Xtest_csr,
+    int32_t k_metrics, int cumulative, int break_ties_with_noise,
+    float *p_at_k, float *tp_at_k, float *r_at_k, float *ap_at_k, float *tap_at_k,
+    float *ndcg_at_k, float *hit_at_k, float *rr_at_k, float *roc_auc, float *pr_auc,
+    int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test,
+    int32_t nthreads, uint64_t seed);
+
+/* Drop-in for calc_metrics_double (src/recometrics_signatures.hpp:48-72). */
+RMB200_API int rmb200_calc_metrics_f64(
+    const double *A, size_t lda, const double *B, size_t ldb,
+    int32_t m, int32_t n, int32_t k,
+    const int32_t *Xtrain_csr_p, const int32_t *Xtrain_csr_i,
+    const int32_t *Xtest_csr_p, const int32_t *Xtest_csr_i, const double *Xtest_csr,
+    int32_t k_metrics, int cumulative, int break_ties_with_noise,
+    double *p_at_k, double *tp_at_k, double *r_at_k, double *ap_at_k, double *tap_at_k,
+    double *ndcg_at_k, double *hit_at_k, double *rr_at_k, double *roc_auc, double *pr_auc,
+    int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test,
+    int32_t nthreads, uint64_t seed);
+
+/* Same call with two additions: item_biases[n] taken as a separate vector and added to the score
+ * inside the scoring kernel (replaces the np.c_[A,1] / np.c_[B,bias] copies of
+ * recometrics/__init__.py:548-551; NULL = none), and the extension block above. */
+RMB200_API int rmb200_calc_metrics_ex_f32(
+    const float *A, size_t lda, const float *B, size_t ldb,
+    int32_t m, int32_t n, int32_t k,
+    const int32_t *Xtrain_csr_p, const int32_t *Xtrain_csr_i,
+    const int32_t *Xtest_csr_p, const int32_t *Xtest_csr_i, const float *Xtest_csr,
+    int32_t k_metrics, int cumulative, int break_ties_with_noise,
+    float *p_at_k, float *tp_at_k, float *r_at_k, float *ap_at_k, float *tap_at_k,
+    float *ndcg_at_k, float *hit_at_k, float *rr_at_k, float *roc_auc, float *pr_auc,
+    int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test,
+    int32_t nthreads, uint64_t seed,
+    const float *item_biases, const rmb200_extra_t *extra);
+
+RMB200_API int rmb200_calc_metrics_ex_f64(
+    const double *A, size_t lda, const double *B, size_t ldb,
+    int32_t m, int32_t n, int32_t k,
+    const int32_t *Xtrain_csr_p, const int32_t *Xtrain_csr_i,
+    const int32_t *Xtest_csr_p, const int32_t *Xtest_csr_i, const double *Xtest_csr,
+    int32_t k_metrics, int cumulative, int break_ties_with_noise,
+    double *p_at_k, double *tp_at_k, double *r_at_k, double *ap_at_k, double *tap_at_k,
+    double *ndcg_at_k, double *hit_at_k, double *rr_at_k, double *roc_auc, double *pr_auc,
+    int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test,
+    int32_t nthreads, uint64_t seed,
+    const double *item_biases, const rmb200_extra_t *extra);
+
+/* Number of usable CUDA devices (0 = the library cannot compute). */
+RMB200_API int rmb200_device_count(void);
+/* RMB200_VERSION of the loaded library. */
+RMB200_API int rmb200_version(void);
+/* Message of the last failing call on this thread ("" if none).  Never NULL. */
+RMB200_API const char *rmb200_last_error(void);
+/* Ask a running call to stop at the next user-batch boundary (what SIGINT does). */
+RMB200_API void rmb200_request_interrupt(void);
+/* Measured FP32 / FP64 FMA throughput of `device` in TFLOP/s (register-resident FMA chains on all
+ * SMs; the roofline denominator for the scoring kernel).  dtype_bytes = 4 or 8.  <0 on error. */
+RMB200_API double rmb200_measure_fma_peak(int device, int dtype_bytes, double *elapsed_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RECOMETRICS_B200_H */

@@ -1,0 +1,167 @@
+"""ctypes binding of ``librecometrics_b200.so`` (the C-ABI declared in ``include/recometrics_b200.h``).
+
+This is the only door from Python into the product's native code.  It fails loudly when the library
+is missing or when no CUDA device is usable: there is no CPU fallback anywhere in the package.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librecometrics_b200.so")
+
+OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_INTERRUPTED, ERR_UNSUPPORTED = range(7)
+MAX_K = 384
+
+# order of the ten outputs in the C signature (src/recometrics_signatures.hpp:56-65 of the reference)
+METRIC_ORDER = ("p", "tp", "r", "ap", "tap", "ndcg", "hit", "rr", "roc", "pr")
+TOPK_METRICS = METRIC_ORDER[:8]
+
+EXPORTS = (
+    "rmb200_calc_metrics_f32", "rmb200_calc_metrics_f64",
+    "rmb200_calc_metrics_ex_f32", "rmb200_calc_metrics_ex_f64",
+    "rmb200_device_count", "rmb200_version", "rmb200_last_error",
+    "rmb200_request_interrupt", "rmb200_measure_fma_peak",
+)
+
+
+class Timing(ctypes.Structure):
+    _fields_ = [
+        ("total_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("prep_ms", ctypes.c_double),
+        ("score_select_ms", ctypes.c_double), ("metrics_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
+        ("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+    ]
+
+    def as_dict(self):
+        return {name: getattr(self, name) for name, _ in self._fields_}
+
+
+class Extra(ctypes.Structure):
+    _fields_ = [
+        ("struct_size", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("user_begin", ctypes.c_int32), ("user_end", ctypes.c_int32),
+        ("inputs_on_device", ctypes.c_int32), ("strict_min_pos_test", ctypes.c_int32),
+        ("topk_items", ctypes.c_void_p), ("topk_scores", ctypes.c_void_p),
+        ("pos_rank", ctypes.c_void_p), ("status", ctypes.c_void_p),
+        ("timing", ctypes.POINTER(Timing)),
+    ]
+
+
+class NativeLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once).  Raises NativeLibraryError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeLibraryError(
+            "recometrics_b200: %s is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "or `make -C recometrics_b200/csrc`.  There is no CPU fallback." % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    for name in EXPORTS:
+        if not hasattr(lib, name):
+            raise NativeLibraryError("recometrics_b200: %s does not export %s" % (LIB_PATH, name))
+    lib.rmb200_device_count.restype = ctypes.c_int
+    lib.rmb200_version.restype = ctypes.c_int
+    lib.rmb200_last_error.restype = ctypes.c_char_p
+    lib.rmb200_request_interrupt.restype = None
+    lib.rmb200_measure_fma_peak.restype = ctypes.c_double
+    lib.rmb200_measure_fma_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+    for name in EXPORTS[:4]:
+        getattr(lib, name).restype = ctypes.c_int
+    _lib = lib
+    return lib
+
+
+def device_count():
+    return int(load().rmb200_device_count())
+
+
+def last_error():
+    return load().rmb200_last_error().decode("utf-8", "replace")
+
+
+def measure_fma_peak(device=-1, dtype=np.float32):
+    ms = ctypes.c_double(0)
+    v = load().rmb200_measure_fma_peak(int(device), 4 if np.dtype(dtype) == np.float32 else 8, ctypes.byref(ms))
+    if v < 0:
+        raise RuntimeError("rmb200_measure_fma_peak failed: " + last_error())
+    return float(v), float(ms.value)
+
+
+def raise_for_status(rc):
+    """Map rmb200_status to the exceptions the reference's Cython layer would surface
+    (``except +`` in recometrics/wrapper.pyx:62,145: bad_alloc -> MemoryError, runtime_error -> RuntimeError)."""
+    if rc == OK:
+        return
+    msg = last_error()
+    if rc == ERR_BAD_ARG:
+        raise ValueError(msg)
+    if rc == ERR_OOM:
+        raise MemoryError(msg)
+    if rc == ERR_INTERRUPTED:
+        raise RuntimeError("Error: procedure was interrupted.")
+    if rc == ERR_UNSUPPORTED:
+        raise NotImplementedError(msg)
+    if rc == ERR_NO_DEVICE:
+        raise RuntimeError("recometrics_b200 needs a CUDA device (no CPU fallback): " + msg)
+    raise RuntimeError("recometrics_b200 CUDA failure: " + msg)
+
+
+def _vp(x):
+    """void* from a numpy array (host), an int (device address) or None."""
+    if x is None:
+        return ctypes.c_void_p(None)
+    if isinstance(x, (int, np.integer)):
+        return ctypes.c_void_p(int(x))
+    if x.size == 0:
+        return ctypes.c_void_p(None)
+    return ctypes.c_void_p(x.ctypes.data)
+
+
+def calc_metrics(dtype, A, lda, B, ldb, m, n, k, trp, tri, tep, tei, tev, k_metrics, cumulative,
+                 break_ties_with_noise, outs, consider_cold_start, min_items_pool, min_pos_test,
+                 nthreads=1, seed=1, item_biases=None, extra=None):
+    """Thin call into rmb200_calc_metrics_ex_{f32,f64}.  Array arguments are numpy arrays (host
+    memory), raw integer addresses (device memory, with extra.inputs_on_device=1) or None.
+    `outs` maps metric name -> array/address/None in METRIC_ORDER.  Returns the status code."""
+    lib = load()
+    fn = lib.rmb200_calc_metrics_ex_f32 if np.dtype(dtype) == np.float32 else lib.rmb200_calc_metrics_ex_f64
+    args = [
+        _vp(A), ctypes.c_size_t(int(lda)), _vp(B), ctypes.c_size_t(int(ldb)),
+        ctypes.c_int32(int(m)), ctypes.c_int32(int(n)), ctypes.c_int32(int(k)),
+        _vp(trp), _vp(tri), _vp(tep), _vp(tei), _vp(tev),
+        ctypes.c_int32(int(k_metrics)), ctypes.c_int(int(bool(cumulative))), ctypes.c_int(int(bool(break_ties_with_noise))),
+    ]
+    args += [_vp(outs.get(q)) for q in METRIC_ORDER]
+    args += [
+        ctypes.c_int(int(bool(consider_cold_start))), ctypes.c_int32(int(min_items_pool)), ctypes.c_int32(int(min_pos_test)),
+        ctypes.c_int32(int(nthreads)), ctypes.c_uint64(int(seed)),
+        _vp(item_biases), ctypes.byref(extra) if extra is not None else ctypes.c_void_p(None),
+    ]
+    return int(fn(*args))
+
+
+def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, strict_min_pos_test=False,
+               topk_items=None, topk_scores=None, pos_rank=None, status=None, timing=None):
+    ex = Extra()
+    ex.struct_size = ctypes.sizeof(Extra)
+    ex.device = int(device)
+    ex.user_begin = int(user_begin)
+    ex.user_end = int(user_end)
+    ex.inputs_on_device = int(bool(inputs_on_device))
+    ex.strict_min_pos_test = int(bool(strict_min_pos_test))
+    ex.topk_items = _vp(topk_items)
+    ex.topk_scores = _vp(topk_scores)
+    ex.pos_rank = _vp(pos_rank)
+    ex.status = _vp(status)
+    if timing is not None:
+        ex.timing = ctypes.pointer(timing)
+    return ex

@@ -1,0 +1,636 @@
+// api.cu -- C-ABI of librecometrics_b200.so and the host orchestration of one call.
+//
+// Stands where /root/reference/src/recometrics_instantiated.cpp:43-143 stands in the reference: the
+// non-template entry points its bindings call (calc_metrics_float / calc_metrics_double), here
+// driving the GPU instead of an OpenMP loop.  The host prologue mirrors
+// /root/reference/src/recometrics.hpp:387-393 (clamps) and :426 / :488 / :964 (SIGINT latch).
+#include "../../include/recometrics_b200.h"
+
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <csignal>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <limits>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "metrics.cuh"
+#include "prep.cuh"
+#include "score_select.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<int> g_interrupt{0};
+std::mutex g_call_mutex;   // one call at a time per process (the SIGINT latch is process-wide)
+
+void set_err(const char* what, const char* detail = nullptr)
+{
+    g_err = what;
+    if (detail) { g_err += ": "; g_err += detail; }
+}
+
+extern "C" void rmb200_sigint_handler(int) { g_interrupt.store(1); }
+
+// /root/reference/src/recometrics.hpp:126-174 (SignalSwitcher): swap the SIGINT handler for the
+// duration of the call, poll the latch between user batches, restore + re-raise afterwards.
+struct SignalLatch {
+    void (*old_handler)(int) = SIG_DFL;
+    bool active = false;
+    SignalLatch()
+    {
+        g_interrupt.store(0);
+        old_handler = std::signal(SIGINT, rmb200_sigint_handler);
+        active = (old_handler != SIG_ERR);
+    }
+    void restore()
+    {
+        if (active) { std::signal(SIGINT, old_handler); active = false; }
+    }
+    ~SignalLatch() { restore(); }
+};
+
+struct DevBuf {
+    void* p = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    ~DevBuf() { release(); }
+    void release() { if (p) { cudaFree(p); p = nullptr; } }
+    cudaError_t alloc(size_t bytes)
+    {
+        release();
+        if (bytes == 0) bytes = 16;
+        return cudaMalloc(&p, bytes);
+    }
+    template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
+};
+
+#define CK(call)                                                                         \
+    do {                                                                                 \
+        cudaError_t e_ = (call);                                                         \
+        if (e_ != cudaSuccess) {                                                         \
+            set_err(#call, cudaGetErrorString(e_));                                      \
+            cudaGetLastError();                                                          \
+            return (e_ == cudaErrorMemoryAllocation) ? RMB200_ERR_OOM : RMB200_ERR_CUDA; \
+        }                                                                                \
+    } while (0)
+
+inline int round_up(int x, int q) { return (x + q - 1) / q * q; }
+
+struct PhaseTimer {
+    cudaStream_t st;
+    cudaEvent_t a = nullptr, b = nullptr;
+    explicit PhaseTimer(cudaStream_t s) : st(s) { cudaEventCreate(&a); cudaEventCreate(&b); }
+    ~PhaseTimer() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+    void start() { cudaEventRecord(a, st); }
+    void stop(double& acc)
+    {
+        cudaEventRecord(b, st);
+        cudaEventSynchronize(b);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, a, b);
+        acc += ms;
+    }
+};
+
+__global__ void rebase_indptr_kernel(const int* __restrict__ src, const int lo, int* __restrict__ dst, const int cnt)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < cnt) dst[i] = src[i] - lo;
+}
+
+template <typename T>
+struct CallArgs {
+    const T* A; size_t lda; const T* B; size_t ldb;
+    int m, n, k;
+    const int32_t *trp, *tri, *tep, *tei; const T* tev;
+    int K, cumulative, noise;
+    T* out[10];   // p tp r ap tap ndcg hit rr roc pr
+    int consider_cold_start, min_items_pool, min_pos_test;
+    const T* bias;
+    const rmb200_extra_t* ex;
+};
+
+template <typename T, int C, bool AUC>
+cudaError_t launch_score_select_inst(const rmb::ScoreSelectParams<T>& P, int n_user_tiles, cudaStream_t st)
+{
+    auto kern = rmb::score_select_kernel<T, C, AUC>;
+    const size_t smem = rmb::score_select_smem_bytes<T>();
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<n_user_tiles, rmb::NTHREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool auc, int n_user_tiles, cudaStream_t st)
+{
+    if (C == 256) return auc ? launch_score_select_inst<T, 256, true>(P, n_user_tiles, st)
+                             : launch_score_select_inst<T, 256, false>(P, n_user_tiles, st);
+    return auc ? launch_score_select_inst<T, 512, true>(P, n_user_tiles, st)
+               : launch_score_select_inst<T, 512, false>(P, n_user_tiles, st);
+}
+
+// Copy a row-major host/device matrix slab [rows][cols] (leading dimension ld) into a compact
+// device buffer when it lives on the host; on-device inputs are used in place.
+template <typename T>
+int stage_rows(const T* src, size_t ld, int rows, int cols, bool on_dev, DevBuf& staging,
+               const T** dev_src, size_t* dev_ld, cudaStream_t st, rmb200_timing_t& tm)
+{
+    if (on_dev) { *dev_src = src; *dev_ld = ld; return RMB200_OK; }
+    CK(cudaMemcpy2DAsync(staging.p, (size_t)cols * sizeof(T), src, ld * sizeof(T), (size_t)cols * sizeof(T),
+                         (size_t)rows, cudaMemcpyHostToDevice, st));
+    tm.h2d_bytes += (int64_t)rows * cols * (int64_t)sizeof(T);
+    *dev_src = staging.as<T>();
+    *dev_ld = (size_t)cols;
+    return RMB200_OK;
+}
+
+template <typename T>
+int run_call(const CallArgs<T>& a)
+{
+    using namespace rmb;
+    const auto t_begin = std::chrono::steady_clock::now();
+    const rmb200_extra_t* ex = a.ex;
+    const bool on_dev = ex && ex->inputs_on_device;
+    rmb200_timing_t tm;
+    std::memset(&tm, 0, sizeof(tm));
+
+    // ---- argument checks (shape errors are the binding's job in the reference,
+    //      recometrics/wrapper.pyx:261-268; here they become RMB200_ERR_BAD_ARG) ----
+    if (a.m <= 0 || a.n <= 0 || a.k <= 0 || a.K <= 0) { set_err("bad argument", "m, n, k and k_metrics must be positive"); return RMB200_ERR_BAD_ARG; }
+    if (!a.A || !a.B || !a.trp || !a.tep) { set_err("bad argument", "A, B, Xtrain_csr_p and Xtest_csr_p are required"); return RMB200_ERR_BAD_ARG; }
+    if (a.lda < (size_t)a.k || a.ldb < (size_t)a.k) { set_err("bad argument", "lda/ldb smaller than k"); return RMB200_ERR_BAD_ARG; }
+    if (a.out[5] && !a.tev) { set_err("bad argument", "NDCG requested but Xtest_csr (values) is NULL"); return RMB200_ERR_BAD_ARG; }
+    if (a.noise) { set_err("unsupported", "break_ties_with_noise=true is not implemented in this build; pass false"); return RMB200_ERR_UNSUPPORTED; }
+    if (a.K > RMB200_MAX_K) { set_err("unsupported", "k_metrics larger than RMB200_MAX_K (384)"); return RMB200_ERR_UNSUPPORTED; }
+    if (ex && ex->struct_size != (int32_t)sizeof(rmb200_extra_t)) { set_err("bad argument", "rmb200_extra_t::struct_size mismatch"); return RMB200_ERR_BAD_ARG; }
+    bool any_out = false;
+    for (int q = 0; q < 10; q++) any_out |= (a.out[q] != nullptr);
+    const bool want_extras = ex && (ex->topk_items || ex->topk_scores || ex->pos_rank || ex->status);
+    if (!any_out && !want_extras) return RMB200_OK;
+
+    int ub = 0, ue = a.m;
+    if (ex && (ex->user_begin != 0 || ex->user_end != 0)) { ub = ex->user_begin; ue = ex->user_end; }
+    if (ub < 0 || ue > a.m || ub > ue) { set_err("bad argument", "user range outside [0, m]"); return RMB200_ERR_BAD_ARG; }
+    const int mr = ue - ub;   // users of this call ("shard"); device-side rows are shard-local
+    if (mr == 0) return RMB200_OK;
+
+    // ---- device ----
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_err("no CUDA device", "librecometrics_b200 has no CPU fallback");
+        return RMB200_ERR_NO_DEVICE;
+    }
+    int dev = -1;
+    if (ex && ex->device >= 0) dev = ex->device;
+    else if (const char* env = std::getenv("RMB200_DEVICE")) dev = std::atoi(env);
+    if (dev < 0) CK(cudaGetDevice(&dev));
+    if (dev >= ndev) { set_err("bad argument", "device ordinal out of range"); return RMB200_ERR_BAD_ARG; }
+    CK(cudaSetDevice(dev));
+
+    std::lock_guard<std::mutex> lock(g_call_mutex);
+    SignalLatch latch;
+    cudaStream_t st = nullptr;   // legacy default stream: ordered after the caller's default-stream work
+    PhaseTimer pt(st);
+
+    // hpp:391-393
+    int mip = a.min_items_pool < a.K ? a.K : a.min_items_pool;
+    if (mip < 2) mip = 2;
+    int mpt = a.min_pos_test;
+    if (!(ex && ex->strict_min_pos_test)) mpt = mpt < 1 ? mpt : 1;   // std::min(min_pos_test, 1): quirk Q1
+
+    const int K = a.K;
+    const int C = (K <= 256 - BN) ? 256 : 512;
+    const bool want_roc = a.out[8] != nullptr, want_pr = a.out[9] != nullptr;
+    const bool count_ranks = want_roc || want_pr || (ex && ex->pos_rank);
+    const int p_pad = round_up(a.k, BK);
+    const int n_pad = round_up(a.n, BN);
+    const size_t rs = a.cumulative ? (size_t)K : 1;
+
+    // ---- CSR slices of users [ub, ue), index pointers re-based to the slice ----
+    int lo_hi[4];   // trp[ub], trp[ue], tep[ub], tep[ue]
+    if (!on_dev) {
+        lo_hi[0] = a.trp[ub]; lo_hi[1] = a.trp[ue]; lo_hi[2] = a.tep[ub]; lo_hi[3] = a.tep[ue];
+    } else {
+        CK(cudaMemcpy(&lo_hi[0], a.trp + ub, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&lo_hi[1], a.trp + ue, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&lo_hi[2], a.tep + ub, sizeof(int), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&lo_hi[3], a.tep + ue, sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    if (lo_hi[1] < lo_hi[0] || lo_hi[3] < lo_hi[2]) { set_err("bad argument", "CSR index pointers decrease"); return RMB200_ERR_BAD_ARG; }
+    const size_t nnz_tr = (size_t)(lo_hi[1] - lo_hi[0]);
+    const size_t nnz_te = (size_t)(lo_hi[3] - lo_hi[2]);
+    if ((nnz_tr && !a.tri) || (nnz_te && !a.tei)) { set_err("bad argument", "CSR indices missing"); return RMB200_ERR_BAD_ARG; }
+
+    DevBuf d_trp, d_tri, d_tep, d_tei, d_tev;
+    CK(d_trp.alloc((size_t)(mr + 1) * sizeof(int)));
+    CK(d_tep.alloc((size_t)(mr + 1) * sizeof(int)));
+    const int* tri_d = nullptr; const int* tei_d = nullptr; const T* tev_d = nullptr;
+    pt.start();
+    if (!on_dev) {
+        std::vector<int> tmp1((size_t)mr + 1), tmp2((size_t)mr + 1);
+        for (int i = 0; i <= mr; i++) { tmp1[i] = a.trp[ub + i] - lo_hi[0]; tmp2[i] = a.tep[ub + i] - lo_hi[2]; }
+        CK(cudaMemcpyAsync(d_trp.p, tmp1.data(), tmp1.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(cudaMemcpyAsync(d_tep.p, tmp2.data(), tmp2.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        CK(d_tri.alloc(nnz_tr * sizeof(int)));
+        CK(d_tei.alloc(nnz_te * sizeof(int)));
+        if (nnz_tr) CK(cudaMemcpyAsync(d_tri.p, a.tri + lo_hi[0], nnz_tr * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (nnz_te) CK(cudaMemcpyAsync(d_tei.p, a.tei + lo_hi[2], nnz_te * sizeof(int), cudaMemcpyHostToDevice, st));
+        if (a.tev) {
+            CK(d_tev.alloc(nnz_te * sizeof(T)));
+            if (nnz_te) CK(cudaMemcpyAsync(d_tev.p, a.tev + lo_hi[2], nnz_te * sizeof(T), cudaMemcpyHostToDevice, st));
+            tev_d = d_tev.as<T>();
+        }
+        CK(cudaStreamSynchronize(st));   // tmp1/tmp2 go out of scope
+        tri_d = d_tri.as<int>(); tei_d = d_tei.as<int>();
+        tm.h2d_bytes += (int64_t)(2 * (size_t)(mr + 1) * sizeof(int) + (nnz_tr + nnz_te) * sizeof(int) + (a.tev ? nnz_te * sizeof(T) : 0));
+        pt.stop(tm.h2d_ms);
+    } else {
+        rebase_indptr_kernel<<<(mr + 1 + 255) / 256, 256, 0, st>>>(a.trp + ub, lo_hi[0], d_trp.as<int>(), mr + 1);
+        rebase_indptr_kernel<<<(mr + 1 + 255) / 256, 256, 0, st>>>(a.tep + ub, lo_hi[2], d_tep.as<int>(), mr + 1);
+        CK(cudaGetLastError());
+        tm.kernel_launches += 2;
+        tri_d = a.tri ? a.tri + lo_hi[0] : nullptr;
+        tei_d = a.tei ? a.tei + lo_hi[2] : nullptr;
+        tev_d = a.tev ? a.tev + lo_hi[2] : nullptr;
+        pt.stop(tm.prep_ms);
+    }
+    const int* trp_d = d_trp.as<int>();
+    const int* tep_d = d_tep.as<int>();
+
+    // ---- item factors: k-major, zero padded (+ biases) ----
+    DevBuf d_Bt, d_bias;
+    CK(d_Bt.alloc((size_t)p_pad * n_pad * sizeof(T)));
+    {
+        DevBuf d_Brow;
+        const T* Bsrc = nullptr; size_t Bld = 0;
+        if (!on_dev) {
+            CK(d_Brow.alloc((size_t)a.n * a.k * sizeof(T)));
+            pt.start();
+            int rc = stage_rows<T>(a.B, a.ldb, a.n, a.k, false, d_Brow, &Bsrc, &Bld, st, tm);
+            if (rc) return rc;
+            pt.stop(tm.h2d_ms);
+        } else { Bsrc = a.B; Bld = a.ldb; }
+        pt.start();
+        dim3 grid(n_pad / 32, (p_pad + 31) / 32), block(32, 8);
+        transpose_pad_kernel<T><<<grid, block, 0, st>>>(Bsrc, Bld, a.n, a.k, d_Bt.as<T>(), n_pad, n_pad, p_pad);
+        CK(cudaGetLastError());
+        tm.kernel_launches++;
+        pt.stop(tm.prep_ms);   // (synchronises: d_Brow may now be freed)
+    }
+    const T* bias_d = nullptr;
+    if (a.bias) {
+        CK(d_bias.alloc((size_t)n_pad * sizeof(T)));
+        DevBuf d_braw;
+        const T* bsrc = a.bias;
+        if (!on_dev) {
+            CK(d_braw.alloc((size_t)a.n * sizeof(T)));
+            pt.start();
+            CK(cudaMemcpyAsync(d_braw.p, a.bias, (size_t)a.n * sizeof(T), cudaMemcpyHostToDevice, st));
+            tm.h2d_bytes += (int64_t)a.n * (int64_t)sizeof(T);
+            pt.stop(tm.h2d_ms);
+            bsrc = d_braw.as<T>();
+        }
+        pt.start();
+        pad_copy_kernel<T><<<(n_pad + 255) / 256, 256, 0, st>>>(bsrc, a.n, d_bias.as<T>(), n_pad);
+        CK(cudaGetLastError());
+        tm.kernel_launches++;
+        pt.stop(tm.prep_ms);
+        bias_d = d_bias.as<T>();
+    }
+
+    // ---- per-user state ----
+    DevBuf d_status, d_flags, d_umin, d_pos_raw, d_pos_sorted, d_pos_perm, d_auc, d_log2, d_pos_rank;
+    CK(d_status.alloc((size_t)mr * sizeof(int)));
+    CK(d_flags.alloc((size_t)mr * sizeof(int)));
+    if (count_ranks) {
+        CK(d_umin.alloc((size_t)mr * sizeof(unsigned long long)));
+        CK(d_pos_raw.alloc(nnz_te * sizeof(T)));
+        CK(d_pos_sorted.alloc(nnz_te * sizeof(T)));
+        CK(d_pos_perm.alloc(nnz_te * sizeof(int)));
+        CK(d_auc.alloc((nnz_te + (size_t)mr) * sizeof(unsigned int)));
+        CK(cudaMemsetAsync(d_auc.p, 0, (nnz_te + (size_t)mr) * sizeof(unsigned int), st));
+        CK(cudaMemsetAsync(d_pos_sorted.p, 0, nnz_te * sizeof(T) + (nnz_te ? 0 : 16), st));
+        CK(cudaMemsetAsync(d_pos_perm.p, 0, nnz_te * sizeof(int) + (nnz_te ? 0 : 16), st));
+    }
+    long long* pos_rank_d = nullptr;
+    if (ex && ex->pos_rank) {
+        if (on_dev) pos_rank_d = reinterpret_cast<long long*>(ex->pos_rank) + lo_hi[2];
+        else { CK(d_pos_rank.alloc(nnz_te * sizeof(long long))); pos_rank_d = d_pos_rank.as<long long>(); }
+        CK(cudaMemsetAsync(pos_rank_d, 0, nnz_te * sizeof(long long), st));
+    }
+    {
+        std::vector<double> l2((size_t)K);
+        for (int i = 0; i < K; i++) l2[i] = std::log2((double)(i + 2));   // hpp:620 std::log2(ix+2)
+        CK(d_log2.alloc((size_t)K * sizeof(double)));
+        CK(cudaMemcpy(d_log2.p, l2.data(), (size_t)K * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    pt.start();
+    {
+        StatusParams sp;
+        sp.trp = trp_d; sp.tep = tep_d; sp.n = a.n; sp.K = K; sp.user_begin = 0; sp.user_end = mr;
+        sp.has_ndcg = a.out[5] != nullptr;
+        sp.has_rescue = (a.out[8] || a.out[9] || a.out[3] || a.out[4] || a.out[7]) ? 1 : 0;   // hpp:485
+        sp.consider_cold_start = a.consider_cold_start; sp.min_items_pool = mip; sp.min_pos_test = mpt;
+        sp.ustatus = d_status.as<int>(); sp.uflags = d_flags.as<int>();
+        sp.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
+        user_status_kernel<<<(mr + 255) / 256, 256, 0, st>>>(sp);
+        CK(cudaGetLastError());
+        tm.kernel_launches++;
+    }
+    pt.stop(tm.prep_ms);
+
+    // ---- user batches ----
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
+    const int wave_users = nsm * BM;                       // one CTA (128 users) per SM
+    int UB = 8 * wave_users;                               // users per batch (8 full waves)
+    if (const char* env = std::getenv("RMB200_BATCH_USERS")) { const int v = std::atoi(env); if (v > 0) UB = round_up(v, BM); }
+    if (UB > round_up(mr, BM)) UB = round_up(mr, BM);
+
+    DevBuf d_At, d_Arow, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out;
+    CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
+    if (!on_dev) CK(d_Arow.alloc((size_t)UB * a.k * sizeof(T)));
+    CK(d_cs.alloc((size_t)UB * C * sizeof(T)));
+    CK(d_ci.alloc((size_t)UB * C * sizeof(int)));
+    CK(d_cc.alloc((size_t)UB * sizeof(int)));
+    if (!on_dev) {
+        for (int q = 0; q < 10; q++)
+            if (a.out[q]) CK(d_out[q].alloc((size_t)UB * (q < 8 ? rs : 1) * sizeof(T)));
+        if (ex && ex->topk_items) CK(d_tki.alloc((size_t)UB * K * sizeof(int)));
+        if (ex && ex->topk_scores) CK(d_tks.alloc((size_t)UB * K * sizeof(T)));
+        if (ex && ex->status) CK(d_stat_out.alloc((size_t)UB * sizeof(int)));
+    }
+
+    for (int b0 = 0; b0 < mr; b0 += UB) {
+        if (g_interrupt.load()) break;                     // hpp:488-489
+        const int nb = (mr - b0) < UB ? (mr - b0) : UB;
+        const int nb_pad = round_up(nb, BM);
+
+        // user factors of the batch -> k-major
+        const T* Asrc = nullptr; size_t Ald = 0;
+        if (!on_dev) {
+            pt.start();
+            int rc = stage_rows<T>(a.A + (size_t)(ub + b0) * a.lda, a.lda, nb, a.k, false, d_Arow, &Asrc, &Ald, st, tm);
+            if (rc) return rc;
+            pt.stop(tm.h2d_ms);
+        } else { Asrc = a.A + (size_t)(ub + b0) * a.lda; Ald = a.lda; }
+        pt.start();
+        {
+            dim3 grid(nb_pad / 32, (p_pad + 31) / 32), block(32, 8);
+            transpose_pad_kernel<T><<<grid, block, 0, st>>>(Asrc, Ald, nb, a.k, d_At.as<T>(), UB, nb_pad, p_pad);
+            CK(cudaGetLastError());
+            tm.kernel_launches++;
+        }
+        if (count_ranks) {
+            const int blocks = (nb + 7) / 8 < 8 * nsm ? (nb + 7) / 8 : 8 * nsm;
+            score_entries_kernel<T><<<blocks, 256, 0, st>>>(d_At.as<T>(), UB, d_Bt.as<T>(), n_pad, bias_d, p_pad, b0, nb,
+                                                             tep_d, tei_d, d_status.as<int>(), d_pos_raw.as<T>());
+            CK(cudaGetLastError());
+            sort_positives_kernel<T><<<blocks, 256, 0, st>>>(b0, nb, tep_d, d_status.as<int>(), d_pos_raw.as<T>(),
+                                                              d_pos_sorted.as<T>(), d_pos_perm.as<int>());
+            CK(cudaGetLastError());
+            tm.kernel_launches += 2;
+        }
+        pt.stop(tm.prep_ms);
+
+        // fused score / exclude / select (/ rank counting)
+        pt.start();
+        {
+            ScoreSelectParams<T> sp;
+            sp.At = d_At.as<T>(); sp.Bt = d_Bt.as<T>(); sp.bias = bias_d;
+            sp.ldA = UB; sp.ldB = n_pad; sp.p_pad = p_pad; sp.n = a.n; sp.mb = nb; sp.user0 = b0;
+            sp.trp = trp_d; sp.tri = tri_d; sp.tep = tep_d; sp.ustatus = d_status.as<int>();
+            sp.cand_score = d_cs.as<T>(); sp.cand_item = d_ci.as<int>(); sp.cand_count = d_cc.as<int>();
+            sp.uflags = d_flags.as<int>(); sp.K = K;
+            sp.pos_sorted = count_ranks ? d_pos_sorted.as<T>() : nullptr;
+            sp.auc_cnt = count_ranks ? d_auc.as<unsigned int>() : nullptr;
+            sp.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
+            // note: At of this batch starts at column 0 of d_At, so batch-local user == column
+            ScoreSelectParams<T> spb = sp;
+            spb.user0 = b0;
+            CK(launch_score_select<T>(spb, C, count_ranks, nb_pad / BM, st));
+            tm.kernel_launches++;
+        }
+        pt.stop(tm.score_select_ms);
+
+        // per-user metrics
+        pt.start();
+        {
+            MetricsParams<T> mp;
+            mp.n = a.n; mp.K = K; mp.C = C; mp.user0 = b0; mp.mb = nb; mp.cumulative = a.cumulative;
+            mp.want_roc = want_roc; mp.want_pr = want_pr; mp.count_ranks = count_ranks;
+            mp.trp = trp_d; mp.tep = tep_d; mp.tei = tei_d; mp.tev = tev_d;
+            mp.ustatus = d_status.as<int>(); mp.uflags = d_flags.as<int>();
+            mp.cand_score = d_cs.as<T>(); mp.cand_item = d_ci.as<int>(); mp.cand_count = d_cc.as<int>();
+            mp.auc_cnt = d_auc.as<unsigned int>(); mp.umin = d_umin.as<unsigned long long>();
+            mp.pos_perm = d_pos_perm.as<int>(); mp.log2tab = d_log2.as<double>();
+            mp.nan_value = std::numeric_limits<T>::quiet_NaN();
+            T* outs[10];
+            for (int q = 0; q < 10; q++) {
+                const size_t stride = q < 8 ? rs : 1;
+                if (!a.out[q]) outs[q] = nullptr;
+                else if (on_dev) outs[q] = a.out[q] + (size_t)(ub + b0) * stride;
+                else outs[q] = d_out[q].as<T>();
+            }
+            mp.p = outs[0]; mp.tp = outs[1]; mp.r = outs[2]; mp.ap = outs[3]; mp.tap = outs[4];
+            mp.ndcg = outs[5]; mp.hit = outs[6]; mp.rr = outs[7]; mp.roc = outs[8]; mp.pr = outs[9];
+            mp.status_out = nullptr; mp.topk_items = nullptr; mp.topk_scores = nullptr;
+            if (ex && ex->status) mp.status_out = on_dev ? ex->status + ub + b0 : d_stat_out.as<int>();
+            if (ex && ex->topk_items) mp.topk_items = on_dev ? ex->topk_items + (size_t)(ub + b0) * K : d_tki.as<int>();
+            if (ex && ex->topk_scores) mp.topk_scores = on_dev ? reinterpret_cast<T*>(ex->topk_scores) + (size_t)(ub + b0) * K : d_tks.as<T>();
+            mp.pos_rank = pos_rank_d;
+            user_metrics_kernel<T><<<(nb + 127) / 128, 128, 0, st>>>(mp);
+            CK(cudaGetLastError());
+            tm.kernel_launches++;
+        }
+        pt.stop(tm.metrics_ms);
+
+        // results of the batch -> caller's arrays at the shard's row offset (no gather collective:
+        // every shard writes its own disjoint rows)
+        if (!on_dev) {
+            pt.start();
+            for (int q = 0; q < 10; q++) {
+                if (!a.out[q]) continue;
+                const size_t stride = q < 8 ? rs : 1;
+                const size_t bytes = (size_t)nb * stride * sizeof(T);
+                CK(cudaMemcpyAsync(a.out[q] + (size_t)(ub + b0) * stride, d_out[q].p, bytes, cudaMemcpyDeviceToHost, st));
+                tm.d2h_bytes += (int64_t)bytes;
+            }
+            if (ex && ex->status) { CK(cudaMemcpyAsync(ex->status + ub + b0, d_stat_out.p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)nb * 4; }
+            if (ex && ex->topk_items) { CK(cudaMemcpyAsync(ex->topk_items + (size_t)(ub + b0) * K, d_tki.p, (size_t)nb * K * sizeof(int), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)nb * K * 4; }
+            if (ex && ex->topk_scores) { CK(cudaMemcpyAsync(reinterpret_cast<T*>(ex->topk_scores) + (size_t)(ub + b0) * K, d_tks.p, (size_t)nb * K * sizeof(T), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)nb * K * (int64_t)sizeof(T); }
+            pt.stop(tm.d2h_ms);
+        }
+    }
+    if (!on_dev && ex && ex->pos_rank && !g_interrupt.load()) {
+        pt.start();
+        CK(cudaMemcpyAsync(ex->pos_rank + lo_hi[2], pos_rank_d, nnz_te * sizeof(long long), cudaMemcpyDeviceToHost, st));
+        tm.d2h_bytes += (int64_t)(nnz_te * sizeof(long long));
+        pt.stop(tm.d2h_ms);
+    }
+    CK(cudaStreamSynchronize(st));
+
+    tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    if (ex && ex->timing) *ex->timing = tm;
+
+    if (g_interrupt.load()) {   // hpp:167-173: restore the handler, re-raise, report
+        latch.restore();
+        std::raise(SIGINT);
+        set_err("interrupted", "procedure was interrupted");
+        return RMB200_ERR_INTERRUPTED;
+    }
+    return RMB200_OK;
+}
+
+template <typename T>
+int entry(const T* A, size_t lda, const T* B, size_t ldb, int32_t m, int32_t n, int32_t k,
+          const int32_t* trp, const int32_t* tri, const int32_t* tep, const int32_t* tei, const T* tev,
+          int32_t K, int cumulative, int noise,
+          T* p, T* tp, T* r, T* ap, T* tap, T* ndcg, T* hit, T* rr, T* roc, T* pr,
+          int ccs, int32_t mip, int32_t mpt, const T* bias, const rmb200_extra_t* ex)
+{
+    g_err.clear();
+    CallArgs<T> a;
+    a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.m = m; a.n = n; a.k = k;
+    a.trp = trp; a.tri = tri; a.tep = tep; a.tei = tei; a.tev = tev;
+    a.K = K; a.cumulative = cumulative ? 1 : 0; a.noise = noise ? 1 : 0;
+    T* outs[10] = {p, tp, r, ap, tap, ndcg, hit, rr, roc, pr};
+    for (int q = 0; q < 10; q++) a.out[q] = outs[q];
+    a.consider_cold_start = ccs ? 1 : 0; a.min_items_pool = mip; a.min_pos_test = mpt;
+    a.bias = bias; a.ex = ex;
+    try {
+        return run_call<T>(a);
+    } catch (const std::bad_alloc&) {
+        set_err("host allocation failed");
+        return RMB200_ERR_OOM;
+    } catch (...) {
+        set_err("unexpected C++ exception");
+        return RMB200_ERR_CUDA;
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+int rmb200_calc_metrics_f32(
+    const float* A, size_t lda, const float* B, size_t ldb, int32_t m, int32_t n, int32_t k,
+    const int32_t* Xtrain_csr_p, const int32_t* Xtrain_csr_i,
+    const int32_t* Xtest_csr_p, const int32_t* Xtest_csr_i, const float* Xtest_csr,
+    int32_t k_metrics, int cumulative, int break_ties_with_noise,
+    float* p_at_k, float* tp_at_k, float* r_at_k, float* ap_at_k, float* tap_at_k,
+    float* ndcg_at_k, float* hit_at_k, float* rr_at_k, float* roc_auc, float* pr_auc,
+    int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, int32_t nthreads, uint64_t seed)
+{
+    (void)nthreads; (void)seed;
+    return entry<float>(A, lda, B, ldb, m, n, k, Xtrain_csr_p, Xtrain_csr_i, Xtest_csr_p, Xtest_csr_i, Xtest_csr,
+                        k_metrics, cumulative, break_ties_with_noise, p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k,
+                        ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc, consider_cold_start, min_items_pool,
+                        min_pos_test, nullptr, nullptr);
+}
+
+int rmb200_calc_metrics_f64(
+    const double* A, size_t lda, const double* B, size_t ldb, int32_t m, int32_t n, int32_t k,
+    const int32_t* Xtrain_csr_p, const int32_t* Xtrain_csr_i,
+    const int32_t* Xtest_csr_p, const int32_t* Xtest_csr_i, const double* Xtest_csr,
+    int32_t k_metrics, int cumulative, int break_ties_with_noise,
+    double* p_at_k, double* tp_at_k, double* r_at_k, double* ap_at_k, double* tap_at_k,
+    double* ndcg_at_k, double* hit_at_k, double* rr_at_k, double* roc_auc, double* pr_auc,
+    int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, int32_t nthreads, uint64_t seed)
+{
+    (void)nthreads; (void)seed;
+    return entry<double>(A, lda, B, ldb, m, n, k, Xtrain_csr_p, Xtrain_csr_i, Xtest_csr_p, Xtest_csr_i, Xtest_csr,
+                         k_metrics, cumulative, break_ties_with_noise, p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k,
+                         ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc, consider_cold_start, min_items_pool,
+                         min_pos_test, nullptr, nullptr);
+}
+
+int rmb200_calc_metrics_ex_f32(
+    const float* A, size_t lda, const float* B, size_t ldb, int32_t m, int32_t n, int32_t k,
+    const int32_t* Xtrain_csr_p, const int32_t* Xtrain_csr_i,
+    const int32_t* Xtest_csr_p, const int32_t* Xtest_csr_i, const float* Xtest_csr,
+    int32_t k_metrics, int cumulative, int break_ties_with_noise,
+    float* p_at_k, float* tp_at_k, float* r_at_k, float* ap_at_k, float* tap_at_k,
+    float* ndcg_at_k, float* hit_at_k, float* rr_at_k, float* roc_auc, float* pr_auc,
+    int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, int32_t nthreads, uint64_t seed,
+    const float* item_biases, const rmb200_extra_t* extra)
+{
+    (void)nthreads; (void)seed;
+    return entry<float>(A, lda, B, ldb, m, n, k, Xtrain_csr_p, Xtrain_csr_i, Xtest_csr_p, Xtest_csr_i, Xtest_csr,
+                        k_metrics, cumulative, break_ties_with_noise, p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k,
+                        ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc, consider_cold_start, min_items_pool,
+                        min_pos_test, item_biases, extra);
+}
+
+int rmb200_calc_metrics_ex_f64(
+    const double* A, size_t lda, const double* B, size_t ldb, int32_t m, int32_t n, int32_t k,
+    const int32_t* Xtrain_csr_p, const int32_t* Xtrain_csr_i,
+    const int32_t* Xtest_csr_p, const int32_t* Xtest_csr_i, const double* Xtest_csr,
+    int32_t k_metrics, int cumulative, int break_ties_with_noise,
+    double* p_at_k, double* tp_at_k, double* r_at_k, double* ap_at_k, double* tap_at_k,
+    double* ndcg_at_k, double* hit_at_k, double* rr_at_k, double* roc_auc, double* pr_auc,
+    int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, int32_t nthreads, uint64_t seed,
+    const double* item_biases, const rmb200_extra_t* extra)
+{
+    (void)nthreads; (void)seed;
+    return entry<double>(A, lda, B, ldb, m, n, k, Xtrain_csr_p, Xtrain_csr_i, Xtest_csr_p, Xtest_csr_i, Xtest_csr,
+                         k_metrics, cumulative, break_ties_with_noise, p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k,
+                         ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc, consider_cold_start, min_items_pool,
+                         min_pos_test, item_biases, extra);
+}
+
+int rmb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int rmb200_version(void) { return RMB200_VERSION; }
+
+const char* rmb200_last_error(void) { return g_err.c_str(); }
+
+void rmb200_request_interrupt(void) { g_interrupt.store(1); }
+
+double rmb200_measure_fma_peak(int device, int dtype_bytes, double* elapsed_ms)
+{
+    g_err.clear();
+    int ndev = rmb200_device_count();
+    if (ndev <= 0) { set_err("no CUDA device"); return -1.0; }
+    if (device < 0) cudaGetDevice(&device);
+    if (device >= ndev || cudaSetDevice(device) != cudaSuccess) { set_err("bad device"); return -1.0; }
+    int nsm = 148;
+    cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, device);
+    const int threads = 256, blocks = nsm * 8;
+    const int iters = dtype_bytes == 4 ? 40000 : 20000;
+    DevBuf out;
+    if (out.alloc((size_t)blocks * threads * 8) != cudaSuccess) { set_err("alloc"); return -1.0; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        if (dtype_bytes == 4) rmb::fma_peak_kernel<float><<<blocks, threads>>>(out.as<float>(), iters, 1.0f);
+        else rmb::fma_peak_kernel<double><<<blocks, threads>>>(out.as<double>(), iters, 1.0);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { set_err("fma peak kernel failed"); cudaGetLastError(); return -1.0; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (elapsed_ms) *elapsed_ms = best;
+    const double flops = (double)blocks * threads * (double)iters * 8.0 * 16.0 * 2.0;
+    return flops / (best * 1e-3) / 1e12;
+}
+
+}  // extern "C"

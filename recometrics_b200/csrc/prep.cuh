@@ -1,0 +1,139 @@
+// prep.cuh -- layout and pre-pass kernels around the fused scoring kernel.
+//
+//   transpose_pad_kernel   row-major factors (the reference's layout, hpp:213-227) -> k-major, padded
+//   user_status_kernel     eligibility filter of /root/reference/src/recometrics.hpp:439-448, :479-486
+//   score_entries_kernel   scores of the held-out (test) items, same FMA order as the tile kernel
+//   sort_positives_kernel  per-user ascending order of those scores (rank by counting)
+#pragma once
+#include "score_select.cuh"
+
+namespace rmb {
+
+// dst[c][r] = src[r][c] (r < rows, c < cols), zero elsewhere; dst is [cols_pad][ld_dst], r < rows_pad.
+template <typename T>
+__global__ void transpose_pad_kernel(const T* __restrict__ src, const size_t ld_src, const int rows, const int cols,
+                                     T* __restrict__ dst, const int ld_dst, const int rows_pad, const int cols_pad)
+{
+    __shared__ T tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? src[(size_t)r * ld_src + c] : (T)0;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (c < cols_pad && r < rows_pad) dst[(size_t)c * ld_dst + r] = tile[tx][i];
+    }
+}
+
+template <typename T>
+__global__ void pad_copy_kernel(const T* __restrict__ src, const int n, T* __restrict__ dst, const int n_pad)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_pad) dst[i] = i < n ? src[i] : (T)0;
+}
+
+struct StatusParams {
+    const int* trp; const int* tep;
+    int n, K, user_begin, user_end;
+    int has_ndcg, has_rescue;      // rescue = roc || pr || ap || tap || rr  (hpp:485)
+    int consider_cold_start, min_items_pool, min_pos_test;
+    int* ustatus;                  // [m]
+    int* uflags;                   // [m] cleared
+    unsigned long long* umin;      // [m] or nullptr, set to ~0
+};
+
+// hpp:439-448 (status 1) and hpp:483-486 (status 2); 0 = the user gets ranked.
+__global__ void user_status_kernel(const StatusParams P)
+{
+    const int u = P.user_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= P.user_end) return;
+    const int ntrain = P.trp[u + 1] - P.trp[u];
+    const int npos = P.tep[u + 1] - P.tep[u];
+    int st = 0;
+    if (npos <= 0 || ((ntrain + npos) >= P.n && !P.has_ndcg) || (P.n - ntrain) < P.min_items_pool ||
+        (!P.consider_cold_start && ntrain == 0) || npos < P.min_pos_test)
+        st = 1;
+    else if ((P.n - ntrain) <= P.K && !P.has_rescue)
+        st = 2;
+    P.ustatus[u] = st;
+    P.uflags[u] = 0;
+    if (P.umin) P.umin[u] = ~0ull;
+}
+
+// One warp per user: score every held-out item of the user.  The accumulation is the sequential
+// fma chain over k = 0..p_pad-1 (then + bias) that score_select_kernel performs for the same
+// (user,item) pair, so both kernels produce bit-identical values.
+template <typename T>
+__global__ void score_entries_kernel(const T* __restrict__ At, const int ldA, const T* __restrict__ Bt, const int ldB,
+                                     const T* __restrict__ bias, const int p_pad, const int user0, const int mb,
+                                     const int* __restrict__ tep, const int* __restrict__ tei,
+                                     const int* __restrict__ ustatus, T* __restrict__ pos_raw)
+{
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int ul = blockIdx.x * warps_per_block + (threadIdx.x >> 5); ul < mb; ul += gridDim.x * warps_per_block) {
+        const int u = user0 + ul;
+        if (ustatus[u] != 0) continue;
+        const int e0 = tep[u], e1 = tep[u + 1];
+        for (int e = e0 + lane; e < e1; e += 32) {
+            const int item = tei[e];
+            T acc = (T)0;
+            for (int k = 0; k < p_pad; k++)
+                acc = NumTraits<T>::fma(At[(size_t)k * ldA + ul], Bt[(size_t)k * ldB + item], acc);
+            if (bias != nullptr) acc += bias[item];
+            pos_raw[e] = acc;
+        }
+    }
+}
+
+// One warp per user: rank-by-counting sort (ascending, stable) of the user's held-out scores.
+// pos_perm[sorted position] = entry offset inside the row.
+template <typename T>
+__global__ void sort_positives_kernel(const int user0, const int mb, const int* __restrict__ tep,
+                                      const int* __restrict__ ustatus, const T* __restrict__ pos_raw,
+                                      T* __restrict__ pos_sorted, int* __restrict__ pos_perm)
+{
+    const int warps_per_block = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int ul = blockIdx.x * warps_per_block + (threadIdx.x >> 5); ul < mb; ul += gridDim.x * warps_per_block) {
+        const int u = user0 + ul;
+        if (ustatus[u] != 0) continue;
+        const int e0 = tep[u];
+        const int npos = tep[u + 1] - e0;
+        for (int e = lane; e < npos; e += 32) {
+            const T v = pos_raw[e0 + e];
+            int rank = 0;
+            for (int j = 0; j < npos; j++) {
+                const T w = pos_raw[e0 + j];
+                rank += (w < v) || (w == v && j < e);
+            }
+            pos_sorted[e0 + rank] = v;
+            pos_perm[e0 + rank] = e;
+        }
+    }
+}
+
+// Register-resident FMA chains on every SM: measured FP32 / FP64 FMA peak (roofline denominator).
+template <typename T>
+__global__ void fma_peak_kernel(T* out, const int iters, const T seed)
+{
+    T a[16];
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = seed + (T)(threadIdx.x + i);
+    const T x = (T)1.0000001, y = (T)1e-9;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 8; rep++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) a[i] = NumTraits<T>::fma(a[i], x, y);
+    }
+    T s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s += a[i];
+    if (s == (T)123456789) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keep the chains alive
+}
+
+}  // namespace rmb

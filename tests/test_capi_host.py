@@ -1,0 +1,101 @@
+"""CPU: the C-ABI library loads, exports every symbol include/*.h declares, and refuses to compute
+without a device (no CPU fallback).  No compute calls are made here."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_symbols():
+    names = []
+    for h in glob.glob(os.path.join(ROOT, "include", "*.h")):
+        txt = open(h).read()
+        names += re.findall(r"RMB200_API\s+[\w\s\*]+?\b(rmb200_\w+)\s*\(", txt)
+    return sorted(set(names))
+
+
+def test_header_declares_the_boundary():
+    names = _declared_symbols()
+    for want in ("rmb200_calc_metrics_f32", "rmb200_calc_metrics_f64", "rmb200_calc_metrics_ex_f32",
+                 "rmb200_calc_metrics_ex_f64", "rmb200_last_error", "rmb200_device_count"):
+        assert want in names
+
+
+def test_library_exports_every_declared_symbol(rb):
+    from recometrics_b200 import _capi
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for name in _declared_symbols():
+        assert hasattr(lib, name), name
+    assert set(_declared_symbols()) == set(_capi.EXPORTS)
+    assert lib.rmb200_version() == 100
+
+
+def test_extra_struct_layout_matches_header(rb):
+    """ctypes mirror of rmb200_extra_t / rmb200_timing_t has the C layout (LP64)."""
+    from recometrics_b200 import _capi
+    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 3 * 8
+    assert ctypes.sizeof(_capi.Extra) == 6 * 4 + 5 * 8
+    assert _capi.Extra.topk_items.offset == 24
+
+
+def test_no_device_means_error_not_fallback(rb):
+    """On a machine without a GPU every compute entry fails loudly (the product has no CPU path)."""
+    from recometrics_b200 import _capi
+    if _capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from tools import synth
+    d = synth.make(1, m=40, n=60, p=4, k=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=3, break_ties_with_noise=False)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: nothing under recometrics_b200/ may reference it."""
+    for path in glob.glob(os.path.join(ROOT, "recometrics_b200", "**", "*"), recursive=True):
+        if os.path.isfile(path) and path.endswith((".py", ".cu", ".cuh", ".h", ".hpp")):
+            txt = open(path, errors="replace").read()
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, re.M), path
+            assert "librmoracle" not in txt and "librecometrics_ref" not in txt, path
+
+
+def test_frontend_validation_mirrors_reference(rb):
+    """Argument errors are raised on the host before anything touches the GPU
+    (reference: recometrics/__init__.py:426-467, :499-500, :531-532)."""
+    from scipy.sparse import csr_array
+    from tools import synth
+    d = synth.make(1, m=30, n=50, p=4, k=3)
+    Xtr, Xte, A, B = d["X_train"], d["X_test"], d["A"], d["B"]
+    with pytest.raises(ValueError, match="passed together"):
+        rb.calc_reco_metrics(Xtr, Xte, A, None)
+    with pytest.raises(ValueError, match="same number of columns"):
+        rb.calc_reco_metrics(Xtr, Xte, A, B[:, :3])
+    with pytest.raises(ValueError, match="Number of users"):
+        rb.calc_reco_metrics(Xtr, Xte, A[:10], B)
+    with pytest.raises(ValueError, match="Number of items"):
+        rb.calc_reco_metrics(Xtr, Xte, A, B[:10])
+    with pytest.raises(ValueError, match="at least one metric"):
+        rb.calc_reco_metrics(Xtr, Xte, A, B, precision=False, average_precision=False, ndcg=False, recall=True)
+    with pytest.raises(ValueError, match="smaller than the number of items"):
+        rb.calc_reco_metrics(Xtr, Xte, A, B, k=51)
+    with pytest.raises(ValueError, match="empty"):
+        rb.calc_reco_metrics(Xtr, csr_array(Xte.shape, dtype=np.float32), A, B)
+    with pytest.raises(ValueError, match="item biases"):
+        rb.calc_reco_metrics(Xtr, Xte, None, None)
+    with pytest.raises(ValueError, match="item_biases"):
+        rb.calc_reco_metrics(Xtr, Xte, A, B, item_biases=np.ones(10, dtype=np.float32))
+
+
+def test_shard_bounds_partition():
+    from recometrics_b200.dist import shard_bounds
+    for m in (1, 7, 128, 1000, 1000003):
+        for w in (1, 2, 3, 8):
+            blocks = [shard_bounds(m, w, r) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == m
+            assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
+            sizes = [e - b for b, e in blocks]
+            assert max(sizes) - min(sizes) <= 1

@@ -1,0 +1,318 @@
+"""GPU: parity of the CUDA path (called through the C-ABI) with the oracle, on the BASELINE
+configurations at sizes the oracle finishes in seconds, on the committed golden vectors of the
+unmodified reference, and on the edge cases the reference's own tests cover.
+
+Rule (north star): integer outputs and top-K ids exact except inside a stated 1e-6 relative score gap
+(float64 re-scoring decides, parity_utils.ambiguity); float metrics within 1e-6, NaN pattern equal."""
+import json
+import os
+
+import numpy as np
+import pytest
+from scipy.sparse import csr_array
+
+import parity_utils as pu
+from golden_io import case_names, load_case
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
+
+
+def _log(rep):
+    os.makedirs(os.path.dirname(REPORT), exist_ok=True)
+    with open(REPORT, "a") as f:
+        f.write(json.dumps(rep) + "\n")
+
+
+def _check(rb, oracle_mod, data, metrics, k, cumulative=False, label="", product_kw=None, oracle_kw=None, **cmp_kw):
+    res = pu.run_product(rb, data, metrics, k, cumulative=cumulative, **(product_kw or {}))
+    orc = pu.run_oracle(oracle_mod, data, metrics, k, cumulative=cumulative, **(oracle_kw or {}))
+    rep = pu.compare(res, orc, data, metrics, k, cumulative=cumulative, label=label, **cmp_kw)
+    rep["timing"] = res.timing
+    _log(rep)
+    return res, orc, rep
+
+
+# ---------------------------------------------------------------- BASELINE configurations
+def test_cfg1_full_all_metrics(rb, oracle_mod):
+    """configs[0]: 6,040 x 3,706, p=32, f32, K=10, all ten metrics -- at full size."""
+    d = synth.make(1)
+    _check(rb, oracle_mod, d, synth.ALL10, 10, label="cfg1 full")
+
+
+def test_cfg1_full_cumulative(rb, oracle_mod):
+    d = synth.make(1)
+    _check(rb, oracle_mod, d, ("p", "tp", "r", "ap", "tap", "ndcg", "hit", "rr"), 10, cumulative=True, label="cfg1 full cumulative")
+
+
+def test_cfg2_shape_item_biases(rb, oracle_mod):
+    """configs[1] shape: p=64 + item_biases, K=10, P/R/AP/NDCG.  Biases go in as a separate vector
+    (fused add) on the product side, folded into the factors on the oracle side (reference way)."""
+    d = synth.make(2, m=4000, n=6000)
+    _check(rb, oracle_mod, d, ("p", "r", "ap", "ndcg"), 10, label="cfg2 4000x6000 separate bias")
+    # and through the plain drop-in signature (bias folded by the caller: p' = 65, not a multiple of 16)
+    _check(rb, oracle_mod, d, ("p", "r", "ap", "ndcg"), 10, label="cfg2 4000x6000 folded bias",
+           product_kw=dict(separate_bias=False))
+
+
+def test_cfg3_shape_auc(rb, oracle_mod):
+    """configs[2] shape: p=128, K=20, P/R/AP/NDCG + ROC-AUC + PR-AUC (full-rank counting)."""
+    d = synth.make(3, m=1500, n=20000)
+    _check(rb, oracle_mod, d, ("p", "r", "ap", "ndcg", "roc", "pr"), 20, label="cfg3 1500x20000")
+
+
+def test_cfg4_shape_k100(rb, oracle_mod):
+    """configs[3] shape: p=128, K=100, P/R/AP/NDCG."""
+    d = synth.make(4, m=1200, n=40000)
+    _check(rb, oracle_mod, d, ("p", "r", "ap", "ndcg"), 100, label="cfg4 1200x40000")
+
+
+def test_cfg5_shape_f64_cumulative(rb, oracle_mod):
+    """configs[4] shape: float64, p=64, cumulative K=1..50 AP/NDCG, min_pos_test=2 (clamped like the
+    reference, quirk Q1), 2% cold-start users."""
+    d = synth.make(5, m=2500, n=12000)
+    _check(rb, oracle_mod, d, ("ap", "ndcg"), 50, cumulative=True, label="cfg5 2500x12000 f64",
+           product_kw=dict(min_pos_test=2), oracle_kw=dict(min_pos_test=2))
+
+
+def test_f64_all_metrics_with_auc(rb, oracle_mod):
+    d = synth.make(1, m=1500, n=2500)
+    d["A"] = d["A"].astype(np.float64)
+    d["B"] = d["B"].astype(np.float64)
+    res, orc, rep = _check(rb, oracle_mod, d, synth.ALL10, 10, label="f64 all metrics 1500x2500")
+    # in float64 the accumulation-order differences are ~1e-15: everything is in fact identical
+    assert rep["topk_rows_differing"] == 0
+
+
+# ---------------------------------------------------------------- golden vectors of the reference
+@pytest.mark.parametrize("name", case_names())
+def test_golden_vectors(rb, name):
+    c = load_case(name)
+    res = pu.run_product(rb, c, c["metrics"], c["k"], cumulative=c["cumulative"], extras=True, **c["params"])
+    S64 = pu.scores_f64(c["A"], c["B"])
+    topk_amb, rank_amb, _ = pu.ambiguity(S64, c["X_train"], c["X_test"], c["k"])
+    # exact ties in the scores (hand-made cases): the reference's order there is libstdc++'s
+    for u in range(S64.shape[0]):
+        s = np.sort(S64[u])
+        if np.any(np.diff(s) == 0):
+            topk_amb[u] = rank_amb[u] = True
+    for q in c["metrics"]:
+        if q in ("hit", "rr") and not any(x in c["metrics"] for x in ("p", "tp", "r", "ap", "tap", "ndcg")):
+            continue   # reference returns uninitialised memory there (quirk Q2)
+        if q == "pr" and "roc" not in c["metrics"]:
+            continue   # reference walks a partially sorted list there (quirk Q3)
+        g, o = res.metrics[pu.KEY[q]], c["ref"][q]
+        ok = pu.nan_equal_close(g, o, pu.METRIC_TOL)
+        if ok.ndim == 2:
+            ok = ok.all(axis=1)
+        amb = rank_amb if q in ("roc", "pr") else topk_amb
+        assert (ok | amb).all(), f"{name}: {q}: {np.asarray(g)[~ok & ~amb][:4]} vs {np.asarray(o)[~ok & ~amb][:4]}"
+
+
+# ---------------------------------------------------------------- edge cases
+def _tiny(n=10, scores=None, te=(2, 3, 7), vals=(1, 2, 3), tr=(), dtype=np.float64):
+    A = np.ones((1, 1), dtype=dtype)
+    B = np.asarray(scores, dtype=dtype).reshape(n, 1)
+    Xtr = csr_array((np.ones(len(tr)), np.array(tr, dtype=np.int32), np.array([0, len(tr)], dtype=np.int32)), shape=(1, n))
+    Xte = csr_array((np.array(vals, dtype=dtype), np.array(te, dtype=np.int32), np.array([0, len(te)], dtype=np.int32)), shape=(1, n))
+    return dict(A=A, B=B, X_train=Xtr, X_test=Xte, item_biases=None)
+
+
+def test_reference_r_tests_invalid_cases(rb):
+    """tests/testthat/test-ndcg.R:7-35: constant / NaN / Inf scores give NaN."""
+    for scores in ([0.0] * 10, [1.0] * 10, [np.nan] * 10, [np.inf] * 10):
+        d = _tiny(scores=scores)
+        r = rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=5, precision=False, average_precision=False,
+                                 ndcg=True, as_df=False, break_ties_with_noise=False)
+        assert np.isnan(r["NDCG@K"][0]), scores
+    rng = np.random.default_rng(1)
+    s = rng.standard_normal(10)
+    s2 = s.copy(); s2[1] = np.nan; s2[3] = np.nan
+    s3 = s.copy(); s3[1] = -np.inf; s3[3] = np.inf
+    for scores in (s2, s3):
+        d = _tiny(scores=scores)
+        r = rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=5, precision=False, average_precision=False,
+                                 ndcg=True, as_df=False, break_ties_with_noise=False)
+        assert np.isnan(r["NDCG@K"][0])
+
+
+def test_reference_r_tests_auc(rb):
+    """tests/testthat/test-auc.R:22-61: perfect ranking -> ROC=PR=1; inverted -> ROC=0; random -> ~0.5."""
+    rng = np.random.default_rng(1)
+    n, npos = 100, 20
+    pos = np.sort(rng.choice(n, npos, replace=False))
+    for sign, want in ((1.0, 1.0), (-1.0, 0.0)):
+        B = np.full((n, 2), -100.0 * sign)
+        B[pos] = 100.0 * sign
+        B += rng.standard_normal(B.shape)
+        A = np.ones((1, 2))
+        Xte = csr_array((np.ones(npos), pos.astype(np.int32), np.array([0, npos], dtype=np.int32)), shape=(1, n))
+        r = rb.calc_reco_metrics(None, Xte, A, B, k=10, precision=False, average_precision=False, ndcg=False,
+                                 roc_auc=True, pr_auc=True, as_df=False, break_ties_with_noise=False)
+        assert r["ROC_AUC"][0] == want
+        if want == 1.0:
+            assert r["PR_AUC"][0] == 1.0
+    m, n, k = 400, 20, 3
+    A = rng.standard_normal((m, k)).astype(np.float32)
+    B = rng.standard_normal((n, k)).astype(np.float32)
+    X = (rng.random((m, n)) < 0.1).astype(np.float32)
+    r = rb.calc_reco_metrics(None, csr_array(X), A, B, k=3, precision=False, average_precision=False, ndcg=False,
+                             roc_auc=True, as_df=False, break_ties_with_noise=False)
+    assert abs(np.nanmean(r["ROC_AUC"]) - 0.5) < 0.03
+
+
+@pytest.mark.parametrize("k", [1, 2, 31, 32, 33, 64, 128, 129, 200, 384])
+def test_k_sweep_selection_boundaries(rb, oracle_mod, k):
+    """K across the selection-buffer boundaries (32-lane groups; C=256 up to K=128, C=512 above)."""
+    d = synth.make(4, m=300, n=3000, p=24)
+    _check(rb, oracle_mod, d, ("p", "tp", "r", "ap", "tap", "ndcg", "hit", "rr"), k, label=f"k sweep K={k}")
+
+
+@pytest.mark.parametrize("p", [1, 3, 15, 16, 17, 33, 100])
+def test_factor_counts_not_multiple_of_tile(rb, oracle_mod, p):
+    d = synth.make(1, m=260, n=700, p=p)
+    _check(rb, oracle_mod, d, ("p", "ap", "ndcg", "roc", "pr"), 7, label=f"p={p}", max_amb_frac=0.6 if p < 3 else 0.25)
+
+
+@pytest.mark.parametrize("m,n", [(1, 130), (127, 128), (129, 127), (257, 1000), (5, 11)])
+def test_ragged_shapes(rb, oracle_mod, m, n):
+    d = synth.make(1, m=m, n=n, p=8)
+    k = min(5, n // 3)
+    _check(rb, oracle_mod, d, synth.ALL10, k, label=f"ragged {m}x{n}", max_amb_frac=1.0)
+
+
+def test_no_train_matrix_and_cold_start_rule(rb, oracle_mod):
+    d = synth.make(1, m=500, n=800, p=8)
+    # X_train=None => empty train, cold start forced on (reference __init__.py:471-473)
+    r = rb.calc_reco_metrics(None, d["X_test"], d["A"], d["B"], k=5, as_df=False, break_ties_with_noise=False)
+    empty = csr_array(d["X_test"].shape, dtype=np.float32)
+    o = oracle_mod.oracle_calc(d["A"], d["B"], empty, d["X_test"], 5, metrics=("p", "ap", "ndcg"))
+    assert pu.nan_equal_close(r["P@K"], o["p"], 1e-6).all()
+    # consider_cold_start=False: users without train rows are NaN (hpp:446)
+    Xtr = d["X_train"].copy().tolil()
+    Xtr[:50] = 0
+    Xtr = Xtr.tocsr(); Xtr.eliminate_zeros()
+    d2 = dict(d, X_train=csr_array(Xtr))
+    _check(rb, oracle_mod, d2, ("p", "ap", "ndcg", "roc"), 5, label="no cold start",
+           product_kw=dict(consider_cold_start=False), oracle_kw=dict(consider_cold_start=False))
+
+
+def test_quirks_eligibility_rules(rb, oracle_mod):
+    """Q1 (min_pos_test clamp), Q4 (frozen cumulative NDCG), Q6 (cand == K), only_ndcg,
+    min_items_pool -- against the oracle restatement (itself pinned to the reference on the same cases)."""
+    c = load_case("g_edge_f64_all")
+    for cum in (False, True):
+        for k in (5, 7):
+            _check(rb, oracle_mod, c, synth.ALL10, k, cumulative=cum, label=f"edge cases k={k} cum={cum}", max_amb_frac=1.0)
+    # Q1: min_pos_test > 1 is ignored by default, honoured with strict_min_pos_test
+    d = synth.make(1, m=400, n=600, p=8)
+    a = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, min_pos_test=1, break_ties_with_noise=False)
+    b = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, min_pos_test=30, break_ties_with_noise=False)
+    c2 = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, min_pos_test=30, strict_min_pos_test=True,
+                                 break_ties_with_noise=False)
+    assert pu.nan_equal_close(a.metrics["P@K"], b.metrics["P@K"], 0).all()
+    npos = np.diff(d["X_test"].indptr)
+    assert np.isnan(c2.metrics["P@K"][npos < 30]).all() and not np.isnan(c2.metrics["P@K"][npos >= 30]).any()
+
+
+def test_hit_rr_alone_are_computed(rb, oracle_mod):
+    """Quirk Q2: the reference leaves Hit@K / RR@K uninitialised when requested alone; here they are
+    computed and equal the values of an all-metrics call."""
+    d = synth.make(1, m=300, n=500, p=8)
+    a = rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=5, precision=False, average_precision=False,
+                             ndcg=False, hit=True, rr=True, as_df=False, break_ties_with_noise=False)
+    b = rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=5, all_metrics=True, as_df=False,
+                             break_ties_with_noise=False)
+    assert pu.nan_equal_close(a["Hit@K"], b["Hit@K"], 0).all() and pu.nan_equal_close(a["RR@K"], b["RR@K"], 0).all()
+
+
+def test_strided_factors_and_dataframe_output(rb, oracle_mod):
+    """lda/ldb > k (row-strided views, reference _as_row_major :11-16) and the DataFrame packaging."""
+    d = synth.make(1, m=200, n=300, p=8)
+    Abig = np.zeros((200, 13), dtype=np.float32); Abig[:, :8] = d["A"]
+    Bbig = np.zeros((300, 11), dtype=np.float32); Bbig[:, :8] = d["B"]
+    df = rb.calc_reco_metrics(d["X_train"], d["X_test"], Abig[:, :8], Bbig[:, :8], k=5, break_ties_with_noise=False)
+    assert list(df.columns) == ["P@5", "AP@5", "NDCG@5"] and df.shape[0] == 200
+    o = oracle_mod.oracle_calc(d["A"], d["B"], d["X_train"], d["X_test"], 5, metrics=("p", "ap", "ndcg"))
+    assert pu.nan_equal_close(df["P@5"].to_numpy(), o["p"], 1e-6).all()
+    dfc = rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=3, cumulative=True, break_ties_with_noise=False)
+    assert list(dfc.columns)[:3] == ["P@1", "P@2", "P@3"]
+
+
+def test_non_personalised_model_biases_only(rb, oracle_mod):
+    """A=B=None: score = item bias (reference __init__.py:429-436)."""
+    d = synth.make(2, m=300, n=500, p=4)
+    bias = d["item_biases"].astype(np.float64)
+    r = rb.calc_reco_metrics(d["X_train"], d["X_test"], None, None, k=5, item_biases=bias, as_df=False,
+                             break_ties_with_noise=False)
+    o = oracle_mod.oracle_calc(np.ones((300, 1)), bias.reshape(-1, 1), d["X_train"], d["X_test"], 5,
+                               metrics=("p", "ap", "ndcg"), dtype=np.float64)
+    assert pu.nan_equal_close(r["P@K"], o["p"], 1e-6).all() and pu.nan_equal_close(r["NDCG@K"], o["ndcg"], 1e-6).all()
+
+
+# ---------------------------------------------------------------- sharding / residency
+def test_user_range_shards_equal_full_call(rb):
+    """The multi-GPU unit: evaluating [0,h) and [h,m) separately writes the same rows as one call."""
+    d = synth.make(3, m=900, n=3000, p=32)
+    kw = dict(k=20, all_metrics=True, break_ties_with_noise=False, return_topk=True, return_ranks=True)
+    full = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], **kw)
+    h = 389
+    lo = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], user_range=(0, h), **kw)
+    hi = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], user_range=(h, 900), **kw)
+    for key, v in full.metrics.items():
+        if key == "K":
+            continue
+        assert pu.nan_equal_close(v[:h], lo.metrics[key][:h], 0).all(), key
+        assert pu.nan_equal_close(v[h:], hi.metrics[key][h:], 0).all(), key
+        assert np.isnan(lo.metrics[key][h:]).all()
+    assert (full.topk_items[:h] == lo.topk_items[:h]).all() and (full.topk_items[h:] == hi.topk_items[h:]).all()
+    split = d["X_test"].indptr[h]
+    assert (full.pos_rank[:split] == lo.pos_rank[:split]).all() and (full.pos_rank[split:] == hi.pos_rank[split:]).all()
+
+
+def test_small_batches_equal_single_batch(rb, monkeypatch):
+    """User batches are an implementation detail: forcing 128-user batches changes nothing."""
+    d = synth.make(1, m=700, n=900, p=16)
+    kw = dict(k=10, all_metrics=True, break_ties_with_noise=False)
+    a = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], **kw)
+    monkeypatch.setenv("RMB200_BATCH_USERS", "128")
+    b = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], **kw)
+    for key, v in a.metrics.items():
+        if key != "K":
+            assert pu.nan_equal_close(v, b.metrics[key], 0).all(), key
+    assert b.timing["kernel_launches"] > a.timing["kernel_launches"]
+
+
+def test_device_resident_call_equals_host_call(rb):
+    """inputs_on_device=1 (HBM-resident inputs and outputs, what bench.py's `value` times) gives
+    bit-identical results to the host-pointer call."""
+    import torch
+    from recometrics_b200 import _capi
+    d = synth.make(2, m=1000, n=2000)
+    A, B, bias = d["A"], d["B"], d["item_biases"]
+    Xtr, Xte = d["X_train"], d["X_test"]
+    host = rb.calc_reco_metrics_ex(Xtr, Xte, A, B, k=10, item_biases=bias, recall=True, break_ties_with_noise=False)
+    dev = torch.device("cuda", 0)
+    t = lambda x: torch.from_numpy(np.ascontiguousarray(x)).to(dev)
+    tA, tB, tb = t(A), t(B), t(bias)
+    trp, tri, tep, tei, tev = t(Xtr.indptr), t(Xtr.indices), t(Xte.indptr), t(Xte.indices), t(Xte.data.astype(np.float32))
+    m, n, p = A.shape[0], B.shape[0], A.shape[1]
+    outs = {q: torch.empty(m, dtype=torch.float32, device=dev) for q in ("p", "r", "ap", "ndcg")}
+    ex = _capi.make_extra(device=0, inputs_on_device=True)
+    rc = _capi.calc_metrics(np.float32, tA.data_ptr(), p, tB.data_ptr(), p, m, n, p, trp.data_ptr(), tri.data_ptr(),
+                            tep.data_ptr(), tei.data_ptr(), tev.data_ptr(), 10, False, False,
+                            {q: v.data_ptr() for q, v in outs.items()}, True, 2, 1, item_biases=tb.data_ptr(), extra=ex)
+    _capi.raise_for_status(rc)
+    torch.cuda.synchronize()
+    for q, key in (("p", "P@K"), ("r", "R@K"), ("ap", "AP@K"), ("ndcg", "NDCG@K")):
+        assert pu.nan_equal_close(outs[q].cpu().numpy(), host.metrics[key], 0).all(), q
+
+
+def test_unsupported_requests_fail_loudly(rb):
+    d = synth.make(1, m=100, n=900, p=8)
+    with pytest.raises(NotImplementedError):
+        rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=500, break_ties_with_noise=False)
+    with pytest.raises(NotImplementedError):
+        rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=5, break_ties_with_noise=True)

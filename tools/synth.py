@@ -61,7 +61,8 @@ def _user_block(cfg, block, rows, n):
     cold = cold[:rows]
     u = np.repeat(np.arange(rows, dtype=np.int64), c)
     it = np.minimum(np.floor(n * rng_it.random(u.shape[0]) ** 2), n - 1).astype(np.int64)
-    key = np.unique(u * n + it)          # sorted, duplicate-free (user, item) pairs
+    key = np.sort(u * n + it, kind="stable")
+    key = key[np.concatenate(([True], key[1:] != key[:-1]))]   # sorted, duplicate-free (user, item) pairs
     u = key // n
     it = (key - u * n).astype(np.int32)
     is_test = rng_split.random(key.shape[0]) < 0.3
