@@ -4,7 +4,10 @@ north-star's rule:
   * float metrics within 1e-6 (same NaN pattern),
   * top-K item ids, hit counts and held-out ranks bit-exact,
   * EXCEPT for users flagged by a float64 re-scoring as near-tied: two candidate scores within a
-    relative gap of 1e-6 at a place where their order matters.  Those users are
+    relative gap of 1e-6 at a place where their order matters.  "Relative" is taken
+    against the user's score scale S_u = max_j |score(u,j)| over the candidates: the rounding error
+    of a p-term dot product does not shrink when the sum happens to land near zero, so a gap
+    relative to the two scores themselves would be meaningless mid-ranking.  Those users are
     compared as sets / with a rank band, and their number is reported and bounded.
 """
 import numpy as np
@@ -44,15 +47,15 @@ def ambiguity(S64, X_train, X_test, K):
             continue
         order = np.argsort(-s, kind="stable")[:cand]
         so = s[order]
+        S_u = max(abs(so[0]), abs(so[-1]))            # the user's score scale
         top = so[: min(K + 1, cand)]
         gaps = np.abs(np.diff(top))
-        scale = np.maximum(np.abs(top[:-1]), np.abs(top[1:]))
-        topk_amb[u] = bool(np.any(gaps <= REL_GAP * scale))
+        topk_amb[u] = bool(np.any(gaps <= REL_GAP * S_u))
         if te.shape[0]:
             asc = so[::-1]
+            tol = REL_GAP * S_u
             for q, item in enumerate(te):
                 v = s[item]
-                tol = REL_GAP * abs(v) * (1 + REL_GAP)
                 lo = np.searchsorted(asc, v - tol, side="left")
                 hi = np.searchsorted(asc, v + tol, side="right")
                 band[X_test.indptr[u] + q] = hi - lo - 1
@@ -138,12 +141,39 @@ def compare(res, orc, data, metrics, k, cumulative=False, check_ranks=True, max_
     ok = nan_equal_close(sg / scale, so / scale, eps) | ~row_equal[:, None]
     assert ok.all(), f"{label}: top-K scores differ beyond accumulation-order tolerance"
 
-    # ---- float metrics within 1e-6 with the same NaN pattern (non-ambiguous users)
+    # ---- float metrics within 1e-6 with the same NaN pattern.  Users on a near-tie: top-K metrics are
+    #      exempt (their ids are checked above to differ only at the near-tied positions); ROC/PR-AUC get
+    #      the tolerance that their rank bands allow (a rank moving by d changes ROC by d/(npos*nneg)).
+    user_of = np.repeat(np.arange(m), np.diff(X_test.indptr))
+    npos_u = np.diff(X_test.indptr).astype(np.float64)
+    cand_u = (X_test.shape[1] - np.diff(X_train.indptr)).astype(np.float64)
+    tot_band = np.zeros(m, dtype=np.float64)
+    np.add.at(tot_band, user_of, band)
+    tot_band += 2.0 * ((tie & 2) != 0)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        roc_tol = METRIC_TOL + 2.0 * tot_band / np.maximum(npos_u * (cand_u - npos_u), 1.0)
+    pr_tol = np.full(m, METRIC_TOL)
+    if orc.get("pos_rank") is not None and ("pr" in metrics):
+        ro = orc["pos_rank"].astype(np.float64)
+        for u in np.nonzero(rank_amb)[0]:
+            r = np.sort(ro[X_test.indptr[u]:X_test.indptr[u + 1]])
+            if r.size == 0 or r[0] <= 0:
+                continue
+            h = np.arange(1, r.size + 1, dtype=np.float64)
+            lo_rank = np.maximum(r - 2 * tot_band[u], h)
+            pr_tol[u] += 2.0 * float(np.sum(h / lo_rank - h / r)) / r.size
     worst = 0.0
     for q in metrics:
         g, o = res.metrics[KEY[q]], orc[q]
-        amb = rank_amb if q in ("roc", "pr") else topk_amb
-        okm = nan_equal_close(g, o, METRIC_TOL)
+        if q == "roc":
+            okm = nan_equal_close(g, o, roc_tol)
+            amb = np.zeros(m, dtype=bool)
+        elif q == "pr":
+            okm = nan_equal_close(g, o, pr_tol)
+            amb = np.zeros(m, dtype=bool)
+        else:
+            okm = nan_equal_close(g, o, METRIC_TOL)
+            amb = topk_amb
         if okm.ndim == 2:
             okm = okm.all(axis=1)
         badm = ~okm & ~amb
@@ -153,9 +183,11 @@ def compare(res, orc, data, metrics, k, cumulative=False, check_ranks=True, max_
             d = np.abs(np.asarray(g, dtype=np.float64) - np.asarray(o, dtype=np.float64))
         if d.ndim == 2:
             d = np.nanmax(np.where(np.isnan(d), 0, d), axis=1)
-        d = np.where(amb | np.isnan(d), 0, d)
+        excl = (rank_amb if q in ("roc", "pr") else topk_amb) | np.isnan(d)
+        rep["max_abs_diff_" + q] = float(np.where(np.isnan(d), 0, d).max()) if d.size else 0.0
+        d = np.where(excl, 0, d)
         worst = max(worst, float(d.max()) if d.size else 0.0)
-        rep["mismatch_" + q] = int((~okm).sum())
+        rep["mismatch_" + q] = int((~nan_equal_close(g, o, METRIC_TOL).reshape(m, -1).all(axis=1)).sum())
     rep["max_metric_abs_diff_nonambiguous"] = worst
 
     # ---- hit counts (integers) recovered from P@K: exact for non-ambiguous users
@@ -167,19 +199,16 @@ def compare(res, orc, data, metrics, k, cumulative=False, check_ranks=True, max_
     # ---- ranks of held-out items: exact, or within the band of near-tied candidates
     if check_ranks and res.pos_rank is not None and ("roc" in metrics or "pr" in metrics):
         rg, ro = res.pos_rank, orc["pos_rank"]
-        user_of = np.repeat(np.arange(m), np.diff(X_test.indptr))
         slack = band.copy()
         slack[((tie & 2) != 0)[user_of]] += 2
         # a near-tie between two other candidates cannot move this entry, but near-ties of
         # held-out items among themselves shift each other: allow the user's total band
-        tot_band = np.zeros(m, dtype=np.int64)
-        np.add.at(tot_band, user_of, band)
-        slack = np.where(band > 0, tot_band[user_of] + slack, slack)
+        slack = np.where(band > 0, tot_band[user_of].astype(np.int64) + slack, slack)
         badr = np.abs(rg - ro) > slack
         assert not badr.any(), (f"{label}: held-out ranks differ beyond the near-tie band for entries "
                                 f"{np.nonzero(badr)[0][:10]}: {rg[badr][:5]} vs {ro[badr][:5]} slack {slack[badr][:5]}")
         rep["rank_entries_differing"] = int((rg != ro).sum())
 
-    frac = max(rep["topk_ambiguous"], rep["rank_ambiguous"] if ("roc" in metrics or "pr" in metrics) else 0) / max(m, 1)
+    frac = rep["topk_ambiguous"] / max(m, 1)
     assert frac <= max_amb_frac, f"{label}: {frac:.3f} of users ambiguous -- test data too degenerate to prove parity"
     return rep

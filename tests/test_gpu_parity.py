@@ -167,7 +167,9 @@ def test_reference_r_tests_auc(rb):
 def test_k_sweep_selection_boundaries(rb, oracle_mod, k):
     """K across the selection-buffer boundaries (32-lane groups; C=256 up to K=128, C=512 above)."""
     d = synth.make(4, m=300, n=3000, p=24)
-    _check(rb, oracle_mod, d, ("p", "tp", "r", "ap", "tap", "ndcg", "hit", "rr"), k, label=f"k sweep K={k}")
+    # (top-384 of 3000 items: neighbours are dense, many users sit on a near-tie somewhere in the list;
+    #  the comparator then requires the lists to differ ONLY at float64-near-tied positions)
+    _check(rb, oracle_mod, d, ("p", "tp", "r", "ap", "tap", "ndcg", "hit", "rr"), k, label=f"k sweep K={k}", max_amb_frac=1.0)
 
 
 @pytest.mark.parametrize("p", [1, 3, 15, 16, 17, 33, 100])

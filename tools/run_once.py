@@ -1,0 +1,32 @@
+"""Run the hot path a few times on one synthetic workload (used under ncu / for quick timings)."""
+import argparse, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from tools import synth
+import recometrics_b200 as rb
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", type=int, default=4)
+ap.add_argument("--users", type=int, default=18944)
+ap.add_argument("--items", type=int, default=0)
+ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--f64", action="store_true")
+a = ap.parse_args()
+cfg = synth.CONFIGS[a.config]
+d = synth.make(a.config, m=a.users, n=a.items or cfg.n)
+flags = {q: (q in cfg.metrics) for q in synth.ALL10}
+kw = dict(precision=flags["p"], trunc_precision=flags["tp"], recall=flags["r"], average_precision=flags["ap"],
+          trunc_average_precision=flags["tap"], ndcg=flags["ndcg"], hit=flags["hit"], rr=flags["rr"],
+          roc_auc=flags["roc"], pr_auc=flags["pr"])
+A, B = d["A"], d["B"]
+if a.f64:
+    A, B = A.astype(np.float64), B.astype(np.float64)
+F = synth.algorithmic_flops(cfg, d["X_train"], d["X_test"])
+for i in range(a.reps):
+    r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=cfg.k, item_biases=d["item_biases"],
+                                cumulative=cfg.cumulative, break_ties_with_noise=False, min_pos_test=cfg.min_pos_test, **kw)
+    t = r.timing
+    print(json.dumps({"rep": i, "users": a.users, "kernel_ms": t["score_select_ms"], "tflops": F / t["score_select_ms"] / 1e9,
+                      "prep_ms": t["prep_ms"], "metrics_ms": t["metrics_ms"], "h2d_ms": t["h2d_ms"], "d2h_ms": t["d2h_ms"],
+                      "total_ms": t["total_ms"], "users_per_s_kernel": a.users / t["score_select_ms"] * 1e3}))
