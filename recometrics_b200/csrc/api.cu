@@ -121,7 +121,7 @@ template <typename T, int C, bool AUC>
 cudaError_t launch_score_select_inst(const rmb::ScoreSelectParams<T>& P, int n_user_tiles, cudaStream_t st)
 {
     auto kern = rmb::score_select_kernel<T, C, AUC>;
-    const size_t smem = rmb::score_select_smem_bytes<T>();
+    const size_t smem = rmb::score_select_smem_bytes<T, AUC>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<n_user_tiles, rmb::NTHREADS, smem, st>>>(P);
@@ -133,8 +133,10 @@ cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool 
 {
     if (C == 256) return auc ? launch_score_select_inst<T, 256, true>(P, n_user_tiles, st)
                              : launch_score_select_inst<T, 256, false>(P, n_user_tiles, st);
-    return auc ? launch_score_select_inst<T, 512, true>(P, n_user_tiles, st)
-               : launch_score_select_inst<T, 512, false>(P, n_user_tiles, st);
+    if (C == 512) return auc ? launch_score_select_inst<T, 512, true>(P, n_user_tiles, st)
+                             : launch_score_select_inst<T, 512, false>(P, n_user_tiles, st);
+    return auc ? launch_score_select_inst<T, 1024, true>(P, n_user_tiles, st)
+               : launch_score_select_inst<T, 1024, false>(P, n_user_tiles, st);
 }
 
 // Copy a row-major host/device matrix slab [rows][cols] (leading dimension ld) into a compact
@@ -208,10 +210,12 @@ int run_call(const CallArgs<T>& a)
     if (!(ex && ex->strict_min_pos_test)) mpt = mpt < 1 ? mpt : 1;   // std::min(min_pos_test, 1): quirk Q1
 
     const int K = a.K;
-    const int C = (K <= 256 - BN) ? 256 : 512;
+    // candidate buffer: K kept + 128 appended per tile + head-room between two re-sorts
+    const int C = (K <= 64) ? 256 : (K <= 192 ? 512 : 1024);
     const bool want_roc = a.out[8] != nullptr, want_pr = a.out[9] != nullptr;
     const bool count_ranks = want_roc || want_pr || (ex && ex->pos_rank);
-    const int p_pad = round_up(a.k, BK);
+    const int p_pad = round_up(a.k, KPAD);
+    constexpr int BN = NumTraits<T>::BN;
     const int n_pad = round_up(a.n, BN);
     const size_t rs = a.cumulative ? (size_t)K : 1;
 
@@ -281,7 +285,7 @@ int run_call(const CallArgs<T>& a)
         } else { Bsrc = a.B; Bld = a.ldb; }
         pt.start();
         dim3 grid(n_pad / 32, (p_pad + 31) / 32), block(32, 8);
-        transpose_pad_kernel<T><<<grid, block, 0, st>>>(Bsrc, Bld, a.n, a.k, d_Bt.as<T>(), n_pad, n_pad, p_pad);
+        pack_tiles_kernel<T, BN><<<grid, block, 0, st>>>(Bsrc, Bld, a.n, a.k, d_Bt.as<T>(), n_pad, p_pad);
         CK(cudaGetLastError());
         tm.kernel_launches++;
         pt.stop(tm.prep_ms);   // (synchronises: d_Brow may now be freed)
@@ -316,8 +320,8 @@ int run_call(const CallArgs<T>& a)
         CK(d_pos_raw.alloc(nnz_te * sizeof(T)));
         CK(d_pos_sorted.alloc(nnz_te * sizeof(T)));
         CK(d_pos_perm.alloc(nnz_te * sizeof(int)));
-        CK(d_auc.alloc((nnz_te + (size_t)mr) * sizeof(unsigned int)));
-        CK(cudaMemsetAsync(d_auc.p, 0, (nnz_te + (size_t)mr) * sizeof(unsigned int), st));
+        CK(d_auc.alloc(nnz_te * sizeof(unsigned int)));
+        CK(cudaMemsetAsync(d_auc.p, 0, nnz_te * sizeof(unsigned int) + (nnz_te ? 0 : 16), st));
         CK(cudaMemsetAsync(d_pos_sorted.p, 0, nnz_te * sizeof(T) + (nnz_te ? 0 : 16), st));
         CK(cudaMemsetAsync(d_pos_perm.p, 0, nnz_te * sizeof(int) + (nnz_te ? 0 : 16), st));
     }
@@ -386,13 +390,13 @@ int run_call(const CallArgs<T>& a)
         pt.start();
         {
             dim3 grid(nb_pad / 32, (p_pad + 31) / 32), block(32, 8);
-            transpose_pad_kernel<T><<<grid, block, 0, st>>>(Asrc, Ald, nb, a.k, d_At.as<T>(), UB, nb_pad, p_pad);
+            pack_tiles_kernel<T, BM><<<grid, block, 0, st>>>(Asrc, Ald, nb, a.k, d_At.as<T>(), nb_pad, p_pad);
             CK(cudaGetLastError());
             tm.kernel_launches++;
         }
         if (count_ranks) {
             const int blocks = (nb + 7) / 8 < 8 * nsm ? (nb + 7) / 8 : 8 * nsm;
-            score_entries_kernel<T><<<blocks, 256, 0, st>>>(d_At.as<T>(), UB, d_Bt.as<T>(), n_pad, bias_d, p_pad, b0, nb,
+            score_entries_kernel<T><<<blocks, 256, 0, st>>>(d_At.as<T>(), d_Bt.as<T>(), bias_d, p_pad, b0, nb,
                                                              tep_d, tei_d, d_status.as<int>(), d_pos_raw.as<T>());
             CK(cudaGetLastError());
             sort_positives_kernel<T><<<blocks, 256, 0, st>>>(b0, nb, tep_d, d_status.as<int>(), d_pos_raw.as<T>(),
@@ -407,17 +411,14 @@ int run_call(const CallArgs<T>& a)
         {
             ScoreSelectParams<T> sp;
             sp.At = d_At.as<T>(); sp.Bt = d_Bt.as<T>(); sp.bias = bias_d;
-            sp.ldA = UB; sp.ldB = n_pad; sp.p_pad = p_pad; sp.n = a.n; sp.mb = nb; sp.user0 = b0;
+            sp.p_pad = p_pad; sp.n = a.n; sp.mb = nb; sp.user0 = b0;
             sp.trp = trp_d; sp.tri = tri_d; sp.tep = tep_d; sp.ustatus = d_status.as<int>();
             sp.cand_score = d_cs.as<T>(); sp.cand_item = d_ci.as<int>(); sp.cand_count = d_cc.as<int>();
             sp.uflags = d_flags.as<int>(); sp.K = K;
             sp.pos_sorted = count_ranks ? d_pos_sorted.as<T>() : nullptr;
             sp.auc_cnt = count_ranks ? d_auc.as<unsigned int>() : nullptr;
             sp.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
-            // note: At of this batch starts at column 0 of d_At, so batch-local user == column
-            ScoreSelectParams<T> spb = sp;
-            spb.user0 = b0;
-            CK(launch_score_select<T>(spb, C, count_ranks, nb_pad / BM, st));
+            CK(launch_score_select<T>(sp, C, count_ranks, nb_pad / BM, st));
             tm.kernel_launches++;
         }
         pt.stop(tm.score_select_ms);
@@ -619,7 +620,7 @@ double rmb200_measure_fma_peak(int device, int dtype_bytes, double* elapsed_ms)
     float best = 1e30f;
     for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        if (dtype_bytes == 4) rmb::fma_peak_kernel<float><<<blocks, threads>>>(out.as<float>(), iters, 1.0f);
+        if (dtype_bytes == 4) rmb::fma2_peak_kernel<<<blocks, threads>>>(out.as<float>(), iters, 1.0f);   // 4 x 16 FFMA2 = 8 x 16 FMA per iteration
         else rmb::fma_peak_kernel<double><<<blocks, threads>>>(out.as<double>(), iters, 1.0);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) { set_err("fma peak kernel failed"); cudaGetLastError(); return -1.0; }

@@ -205,16 +205,14 @@ __global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
             if (P.roc) P.roc[ul] = NaN;
             if (P.pr) P.pr[ul] = NaN;
         } else {
-            // buckets[b] = number of candidates with exactly b held-out scores strictly below theirs.
-            // Walking the held-out items from the best (i = npos) down, the suffix sum is the number
-            // of candidates scoring strictly above the i-th smallest held-out score.
-            const unsigned int* bk = P.auc_cnt + (size_t)tp0 + (size_t)u;
-            unsigned long long above = 0, prev_rank = 0, sum_ranks = 0;
+            // above[j] = number of candidates scoring strictly above the j-th smallest held-out score
+            // (counted by score_select_kernel); walk the held-out items from the best down.
+            const unsigned int* ab = P.auc_cnt + (size_t)tp0;
+            unsigned long long prev_rank = 0, sum_ranks = 0;
             double ap_full = 0;
             for (int h = 1; h <= npos; h++) {
                 const int i = npos - h + 1;
-                above += bk[i];
-                unsigned long long rank = above + 1;
+                unsigned long long rank = (unsigned long long)ab[i - 1] + 1;
                 if (rank <= prev_rank) rank = prev_rank + 1;   // tied held-out scores take consecutive ranks
                 prev_rank = rank;
                 sum_ranks += rank;

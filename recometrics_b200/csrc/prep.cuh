@@ -1,6 +1,6 @@
 // prep.cuh -- layout and pre-pass kernels around the fused scoring kernel.
 //
-//   transpose_pad_kernel   row-major factors (the reference's layout, hpp:213-227) -> k-major, padded
+//   pack_tiles_kernel      row-major factors (the reference's layout, hpp:213-227) -> 128-wide k-major slabs
 //   user_status_kernel     eligibility filter of /root/reference/src/recometrics.hpp:439-448, :479-486
 //   score_entries_kernel   scores of the held-out (test) items, same FMA order as the tile kernel
 //   sort_positives_kernel  per-user ascending order of those scores (rank by counting)
@@ -9,10 +9,12 @@
 
 namespace rmb {
 
-// dst[c][r] = src[r][c] (r < rows, c < cols), zero elsewhere; dst is [cols_pad][ld_dst], r < rows_pad.
-template <typename T>
-__global__ void transpose_pad_kernel(const T* __restrict__ src, const size_t ld_src, const int rows, const int cols,
-                                     T* __restrict__ dst, const int ld_dst, const int rows_pad, const int cols_pad)
+// Re-tile a row-major factor matrix src[rows][cols] (leading dimension ld_src) into W-row slabs,
+// k-major inside a slab and zero padded:  dst[(r / W) * cols_pad + c][r % W] = src[r][c].
+// One slab chunk of `kcount` factors is then a contiguous block of kcount*W elements (one TMA bulk copy).
+template <typename T, int W>
+__global__ void pack_tiles_kernel(const T* __restrict__ src, const size_t ld_src, const int rows, const int cols,
+                                  T* __restrict__ dst, const int rows_pad, const int cols_pad)
 {
     __shared__ T tile[32][33];
     const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -24,7 +26,8 @@ __global__ void transpose_pad_kernel(const T* __restrict__ src, const size_t ld_
     __syncthreads();
     for (int i = ty; i < 32; i += 8) {
         const int c = c0 + i, r = r0 + tx;
-        if (c < cols_pad && r < rows_pad) dst[(size_t)c * ld_dst + r] = tile[tx][i];
+        if (c < cols_pad && r < rows_pad)
+            dst[((size_t)(r / W) * cols_pad + c) * W + (r % W)] = tile[tx][i];
     }
 }
 
@@ -65,9 +68,9 @@ __global__ void user_status_kernel(const StatusParams P)
 
 // One warp per user: score every held-out item of the user.  The accumulation is the sequential
 // fma chain over k = 0..p_pad-1 (then + bias) that score_select_kernel performs for the same
-// (user,item) pair, so both kernels produce bit-identical values.
+// (user,item) pair, so both kernels produce bit-identical values.  At / Bt are the tiled slabs.
 template <typename T>
-__global__ void score_entries_kernel(const T* __restrict__ At, const int ldA, const T* __restrict__ Bt, const int ldB,
+__global__ void score_entries_kernel(const T* __restrict__ At, const T* __restrict__ Bt,
                                      const T* __restrict__ bias, const int p_pad, const int user0, const int mb,
                                      const int* __restrict__ tep, const int* __restrict__ tei,
                                      const int* __restrict__ ustatus, T* __restrict__ pos_raw)
@@ -78,11 +81,14 @@ __global__ void score_entries_kernel(const T* __restrict__ At, const int ldA, co
         const int u = user0 + ul;
         if (ustatus[u] != 0) continue;
         const int e0 = tep[u], e1 = tep[u + 1];
+        constexpr int BN = NumTraits<T>::BN;
+        const T* a = At + (size_t)(ul / BM) * p_pad * BM + (ul % BM);
         for (int e = e0 + lane; e < e1; e += 32) {
             const int item = tei[e];
+            const T* b = Bt + (size_t)(item / BN) * p_pad * BN + (item % BN);
             T acc = (T)0;
             for (int k = 0; k < p_pad; k++)
-                acc = NumTraits<T>::fma(At[(size_t)k * ldA + ul], Bt[(size_t)k * ldB + item], acc);
+                acc = NumTraits<T>::fma(a[(size_t)k * BM], b[(size_t)k * BN], acc);
             if (bias != nullptr) acc += bias[item];
             pos_raw[e] = acc;
         }
@@ -134,6 +140,25 @@ __global__ void fma_peak_kernel(T* out, const int iters, const T seed)
 #pragma unroll
     for (int i = 0; i < 16; i++) s += a[i];
     if (s == (T)123456789) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keep the chains alive
+}
+
+// The same with packed fma.rn.f32x2 (FFMA2): 2 fp32 FMAs per instruction, the form the scoring kernel uses.
+__global__ void fma2_peak_kernel(float* out, const int iters, const float seed)
+{
+    u64 a[16];
+    const u64 x = pack2(1.0000001f, 1.0000001f), y = pack2(1e-9f, 1e-9f);
+#pragma unroll
+    for (int i = 0; i < 16; i++) a[i] = pack2(seed + (float)(threadIdx.x + i), seed - (float)i);
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int rep = 0; rep < 4; rep++)
+#pragma unroll
+            for (int i = 0; i < 16; i++) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(a[i]) : "l"(x), "l"(y));
+    }
+    u64 s = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) s ^= a[i];
+    if (s == 123456789ull) out[blockIdx.x * blockDim.x + threadIdx.x] = (float)s;
 }
 
 }  // namespace rmb

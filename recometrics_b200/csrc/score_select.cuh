@@ -6,23 +6,30 @@
 //   partial_sort / sort /root/reference/src/recometrics.hpp:537-563
 //   (the AUC walks of :795-865 become a counting pass over the same score tiles)
 //
-// Design (sm_100a, FP32 FFMA / FP64 DFMA pipes):
-//   * A is stored k-major (At[p_pad][m_pad]) and B k-major (Bt[p_pad][n_pad]) so that a
-//     (BK x 128) operand slab is 16-byte-chunk contiguous: cp.async.cg 16B copies land it in shared
-//     memory in exactly the layout the FMA micro-kernel reads (no transposition in the hot loop).
-//   * CTA = 256 threads = 8 warps (4 along users x 2 along items); CTA tile 128 users x 128 items;
-//     thread micro-tile 8x8 held in registers; 4-stage (f32) / 3-stage (f64) cp.async ring over the
-//     flattened (item tile, k chunk) iteration space; one CTA per SM (grid = user tiles).
-//   * The score tile never leaves registers: each score is compared with the user's running
-//     K-th best (tau).  Survivors (~K ln(n/K) per user over the whole catalogue) are checked against
-//     the user's train row and appended to a per-user candidate buffer of C >= K + 128 entries in
-//     global memory (L2 resident); a warp re-sorts a user's buffer (bitonic network in registers)
-//     when it passes C - 128 entries, which refreshes tau.  At the end the buffer head holds the
-//     user's top-K in rank order.
-//   * AUC mode (ROC/PR requested): every candidate score additionally increments the bucket
-//     "number of this user's held-out items scoring strictly below it"; ranks of the held-out
-//     items follow from a suffix sum (metrics.cuh).  Scores of held-out items are pre-computed with
-//     the same FMA order (prep.cuh) so the comparison with themselves is exact.
+// Design (sm_100a; FP32 on the packed FFMA2 pipe, FP64 on DFMA):
+//   * Factors are re-tiled once per call into slabs  At[user tile][k][128]  /  Bt[item tile][k][128]
+//     (k-major inside a 128-wide tile), so the operand chunk of one pipeline stage is ONE contiguous
+//     block: a single TMA bulk copy (cp.async.bulk, SASS UBLKCP) lands it in shared memory in
+//     exactly the layout the FMA micro-kernel reads.
+//   * CTA = 8 compute warps + 1 producer warp.  The producer's elected lane runs the TMA ring
+//     (full/empty mbarriers, STAGES deep) over the flattened (item tile, k chunk) space; compute
+//     warps never meet at a CTA barrier.
+//   * CTA tile 128 users x 128 items; a compute warp OWNS 16 users x 128 items (thread micro-tile
+//     8 users x 8 items in registers), so all per-user selection state is warp-private.
+//     fp32: the 8x8 micro-tile is 32 packed accumulators updated with fma.rn.f32x2, user factor as
+//     the scalar-broadcast operand (SASS: FFMA2 Rd, Ra.F32, Rb.F32x2, Rc.F32x2) -- half the issue
+//     slots of FFMA and no register-bank conflicts (profiles/r01_ubench_fma.txt).
+//   * The score tile never leaves registers: per user row a thread takes the max of its 8 scores
+//     and compares it with the user's running K-th best (tau).  Survivors (~K ln(n/K) per user over
+//     the whole catalogue) are checked against the user's train row (only in item tiles the sorted
+//     train row intersects -- a per-row cursor keeps the next train item id) and appended to a
+//     per-user candidate buffer of C entries in global memory (L2 resident); the owning warp
+//     re-sorts a buffer (bitonic network in registers) when it passes C - 128 entries, which
+//     refreshes tau.  At the end the buffer head holds the user's top-K in rank order.
+//   * AUC mode (ROC/PR requested): the warp stages its 16x128 score block (train items masked) in
+//     shared memory and every lane counts, for the held-out items it owns, the candidates scoring
+//     strictly higher (compare + add, no atomics, counters in registers).  Scores of held-out
+//     items are pre-computed with the same FMA order (prep.cuh) so comparisons are exact.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -32,23 +39,26 @@
 
 namespace rmb {
 
-constexpr int BM = 128;       // users per CTA tile
-constexpr int BN = 128;       // items per tile
-constexpr int BK = 16;        // factors per pipeline stage
-constexpr int NTHREADS = 256;
+constexpr int BM = 128;             // users per CTA tile (items per tile: NumTraits<T>::BN)
+constexpr int NCWARPS = 8;          // compute warps (16 user rows each)
+constexpr int NTHREADS = (NCWARPS + 1) * 32;   // + 1 producer warp
+constexpr int KPAD = 8;             // factors are zero-padded to a multiple of this
 constexpr unsigned FULL = 0xffffffffu;
+typedef unsigned long long u64;
 
 template <typename T> struct NumTraits;
 template <> struct NumTraits<float> {
+    static constexpr int BN = 128;      // items per tile (thread micro-tile 8 users x 8 items)
+    static constexpr int BK = 32;       // factors per pipeline stage
     static constexpr int STAGES = 4;
     __device__ __forceinline__ static float inf() { return CUDART_INF_F; }
     __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
-    __device__ __forceinline__ static unsigned long long orderable(float x) {
+    __device__ __forceinline__ static u64 orderable(float x) {
         unsigned u = __float_as_uint(x);
         u ^= (u >> 31) ? 0xffffffffu : 0x80000000u;
-        return (unsigned long long)u;
+        return (u64)u;
     }
-    __host__ __device__ static float from_orderable(unsigned long long o) {
+    __host__ __device__ static float from_orderable(u64 o) {
         unsigned u = (unsigned)o;
         u ^= (u >> 31) ? 0x80000000u : 0xffffffffu;
 #ifdef __CUDA_ARCH__
@@ -59,15 +69,18 @@ template <> struct NumTraits<float> {
     }
 };
 template <> struct NumTraits<double> {
+    static constexpr int BN = 64;       // items per tile (thread micro-tile 8 users x 4 items: the
+                                        // register file of a 9-warp CTA holds 168 registers per thread)
+    static constexpr int BK = 32;
     static constexpr int STAGES = 3;
     __device__ __forceinline__ static double inf() { return CUDART_INF; }
     __device__ __forceinline__ static double fma(double a, double b, double c) { return ::fma(a, b, c); }
-    __device__ __forceinline__ static unsigned long long orderable(double x) {
-        unsigned long long u = (unsigned long long)__double_as_longlong(x);
+    __device__ __forceinline__ static u64 orderable(double x) {
+        u64 u = (u64)__double_as_longlong(x);
         u ^= (u >> 63) ? 0xffffffffffffffffull : 0x8000000000000000ull;
         return u;
     }
-    __host__ __device__ static double from_orderable(unsigned long long u) {
+    __host__ __device__ static double from_orderable(u64 u) {
         u ^= (u >> 63) ? 0x8000000000000000ull : 0xffffffffffffffffull;
 #ifdef __CUDA_ARCH__
         return __longlong_as_double((long long)u);
@@ -77,6 +90,7 @@ template <> struct NumTraits<double> {
     }
 };
 
+// ------------------------------------------------------------------ ranking helpers
 // total order used for ranking: score descending, ties by ascending item id
 // (the reference's comparator is a strict '>' on the score, hpp:538-540 / :552-554; its tie order
 //  is whatever libstdc++ does -- SURVEY quirk Q8 -- so a deterministic refinement is chosen here)
@@ -165,14 +179,14 @@ __device__ __noinline__ void compact_user(T* cs, int* ci, const int nv, const in
 
 template <typename T>
 struct ScoreSelectParams {
-    const T* __restrict__ At;      // [p_pad][ldA]  user factors of this batch, k-major, zero padded
-    const T* __restrict__ Bt;      // [p_pad][ldB]  item factors, k-major, zero padded
-    const T* __restrict__ bias;    // [ldB] item biases or nullptr
-    int ldA, ldB, p_pad;
+    const T* __restrict__ At;      // [user tiles][p_pad][128]  user factors of this batch, zero padded
+    const T* __restrict__ Bt;      // [item tiles][p_pad][128]  item factors, zero padded
+    const T* __restrict__ bias;    // [item tiles * 128] item biases (zero padded) or nullptr
+    int p_pad;
     int n;                          // items
     int mb;                         // users in this batch
-    int user0;                      // absolute row of the batch's first user
-    const int* __restrict__ trp;    // train CSR (absolute rows)
+    int user0;                      // row (of the CSR / status arrays) of the batch's first user
+    const int* __restrict__ trp;    // train CSR
     const int* __restrict__ tri;
     const int* __restrict__ tep;    // test CSR indptr
     const int* __restrict__ ustatus;// [m] 0 = user is ranked, !=0 = NaN row decided before scoring
@@ -183,75 +197,216 @@ struct ScoreSelectParams {
     int K;
     // rank counting (AUC mode)
     const T* __restrict__ pos_sorted;   // [nnz_test] held-out item scores, ascending per user
-    unsigned int* auc_cnt;              // [nnz_test + m] buckets of user u start at tep[u] + u
-    unsigned long long* umin;           // [m] orderable(min candidate score), init ~0
+    unsigned int* auc_cnt;              // [nnz_test] number of candidates scoring strictly above
+                                        // the j-th smallest held-out score of the row (zeroed)
+    u64* umin;                          // [m] orderable(min candidate score), init ~0
 };
 
-// 16-byte shared-memory load into consecutive elements of a register array
-__device__ __forceinline__ void lds_vec(const float* p, float* dst)
+// ------------------------------------------------------------------ PTX wrappers (TMA ring)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(const unsigned bar, const unsigned count)
 {
-    const float4 v = *reinterpret_cast<const float4*>(p);
-    dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void lds_vec(const double* p, double* dst)
+__device__ __forceinline__ void mbar_fence_init()
 {
-    const double2 v = *reinterpret_cast<const double2*>(p);
-    dst[0] = v.x; dst[1] = v.y;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(const unsigned bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(const unsigned bar, const unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned parity)
+{
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy executed by the TMA unit, completion counted on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(const unsigned dst, const void* src, const unsigned bytes, const unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem)
+__device__ __forceinline__ u64 pack2(const float lo, const float hi)
 {
-    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem));
+    u64 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
-
-// is `item` in the sorted train row of absolute user u ?  (hpp:494-495 moves those out of the pool)
-__device__ __forceinline__ bool in_train_row(const int* __restrict__ trp, const int* __restrict__ tri,
-                                             const int u, const int item)
+__device__ __forceinline__ void unpack2(const u64 v, float& lo, float& hi)
 {
-    int lo = trp[u], hi = trp[u + 1];
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+// d = a * b + d on two packed fp32 lanes (each lane an IEEE fma, same rounding as fmaf)
+__device__ __forceinline__ void fma2(u64& d, const u64 a, const u64 b)
+{
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(d) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ float max_nan(const float a, const float b)
+{
+    float r;
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(b));
+    return r;
+}
+__device__ __forceinline__ double max_nan(const double a, const double b)
+{
+    return (a != a || b != b) ? CUDART_NAN : (a > b ? a : b);
+}
+
+__device__ __forceinline__ void lds_vec(const float* p, float (&v)[4])
+{
+    const float4 f = *reinterpret_cast<const float4*>(p);
+    v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+}
+__device__ __forceinline__ void lds_vec(const double* p, double (&v)[2])
+{
+    const double2 f = *reinterpret_cast<const double2*>(p);
+    v[0] = f.x; v[1] = f.y;
+}
+__device__ __forceinline__ void sts4(float* p, const float* v)
+{
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+}
+__device__ __forceinline__ void sts4(double* p, const double* v)
+{
+    *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+}
+
+// ------------------------------------------------------------------ register micro-tiles
+// Thread (ly = lane >> 4, lx = lane & 15) of a compute warp holds, of the warp's 16 x BN block,
+//   rows  ly*4 + (i & 3) + (i >> 2) * 8      i = 0..7
+//   cols  lx*4 + (c & 3) + (c >> 2) * 64     c = 0..NC-1   (NC = BN / 16: 8 for fp32, 4 for fp64)
+template <typename T> struct MicroTile;
+
+template <> struct MicroTile<float> {
+    static constexpr int NC = 8;
+    u64 acc[8][4];   // acc[i][c/2] = scores (i, c), (i, c+1)
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) acc[i][q] = 0ull;
+    }
+    // sA: the warp's 16 user values of factor k; sB: the tile's 128 item values of factor k
+    __device__ __forceinline__ void step(const float* __restrict__ sA, const float* __restrict__ sB, const int ly, const int lx)
+    {
+        const float4 a0 = *reinterpret_cast<const float4*>(sA + ly * 4);
+        const float4 a1 = *reinterpret_cast<const float4*>(sA + 8 + ly * 4);
+        const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sB + lx * 4);
+        const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(sB + 64 + lx * 4);
+        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+        const u64 b[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+        for (int q = 0; q < 4; q++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) fma2(acc[i][q], pack2(a[i], a[i]), b[q]);
+    }
+    __device__ __forceinline__ void row(const int i, float (&s)[8]) const
+    {
+#pragma unroll
+        for (int q = 0; q < 4; q++) unpack2(acc[i][q], s[2 * q], s[2 * q + 1]);
+    }
+};
+
+template <> struct MicroTile<double> {
+    static constexpr int NC = 4;
+    double acc[8][4];
+    __device__ __forceinline__ void zero()
+    {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) acc[i][c] = 0.;
+    }
+    __device__ __forceinline__ void step(const double* __restrict__ sA, const double* __restrict__ sB, const int ly, const int lx)
+    {
+        double a[8], b[4];
+#pragma unroll
+        for (int g = 0; g < 2; g++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                const double2 va = *reinterpret_cast<const double2*>(sA + g * 8 + ly * 4 + h * 2);
+                a[g * 4 + h * 2] = va.x; a[g * 4 + h * 2 + 1] = va.y;
+            }
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+            const double2 vb = *reinterpret_cast<const double2*>(sB + lx * 4 + h * 2);
+            b[h * 2] = vb.x; b[h * 2 + 1] = vb.y;
+        }
+#pragma unroll
+        for (int c = 0; c < 4; c++)
+#pragma unroll
+            for (int i = 0; i < 8; i++) acc[i][c] = ::fma(a[i], b[c], acc[i][c]);
+    }
+    __device__ __forceinline__ void row(const int i, double (&s)[4]) const
+    {
+#pragma unroll
+        for (int c = 0; c < 4; c++) s[c] = acc[i][c];
+    }
+};
+
+// ------------------------------------------------------------------ per-CTA shared state
+template <typename T>
+struct RowState {
+    T tau[BM];          // running K-th best score; +inf = row is not ranked (padding / NaN-row user)
+    int cnt[BM];        // entries in the row's candidate buffer
+    int nan[BM];        // a candidate score was NaN
+    int nxt_train[BM];  // smallest train item id >= first item of the current tile (INT_MAX: none)
+    int cur_train[BM];  // its position in the train CSR
+    int end_train[BM];
+};
+
+template <typename T, bool AUC>
+inline size_t score_select_smem_bytes()
+{
+    constexpr int BN = NumTraits<T>::BN;
+    size_t b = (size_t)NumTraits<T>::STAGES * NumTraits<T>::BK * (BM + BN) * sizeof(T);   // operand ring
+    b += sizeof(RowState<T>);
+    b += 2 * NumTraits<T>::STAGES * sizeof(u64);                                          // mbarriers
+    if (AUC) b += (size_t)NCWARPS * 8 * BN * sizeof(T);                                   // score half-blocks
+    return b + 128;
+}
+
+// is `item` in the sorted train row segment [lo, hi) ?  (hpp:494-495 moves those out of the pool)
+__device__ __forceinline__ bool in_train_segment(const int* __restrict__ tri, int lo, int hi, const int item)
+{
+    const int end = hi;
     while (lo < hi) {
         const int mid = (lo + hi) >> 1;
-        const int v = tri[mid];
-        if (v < item) lo = mid + 1; else hi = mid;
+        if (tri[mid] < item) lo = mid + 1; else hi = mid;
     }
-    return lo < trp[u + 1] && tri[lo] == item;
+    return lo < end && tri[lo] == item;
 }
 
-// Slow path of the selection filter (taken by ~K ln(n/K) scores per user): candidate checks,
-// then append to the user's buffer.  Returns true when the buffer passed the compaction trigger.
+// Slow path of the selection filter (taken by ~K ln(n/K) scores per user): candidate checks, then
+// append to the user's buffer.
 template <typename T, int C>
-__device__ __noinline__ bool select_insert(const ScoreSelectParams<T>& P, const T s, const int row,
-                                           const int ulocal, const int item,
-                                           int* cnt_s, int* nan_s)
+__device__ __noinline__ void select_insert(const ScoreSelectParams<T>& P, RowState<T>* rs, const T s, const int row,
+                                           const int ulocal, const int item, const int item_end)
 {
-    if (ulocal >= P.mb || item >= P.n) return false;          // padding rows / columns
-    const int u = P.user0 + ulocal;
-    if (in_train_row(P.trp, P.tri, u, item)) return false;    // not a candidate
-    if (s != s) { nan_s[row] = 1; return false; }             // NaN candidate score => NaN row
-    const int slot = atomicAdd(&cnt_s[row], 1);
+    if (item >= P.n) return;                                    // padding column
+    if (rs->nxt_train[row] < item_end &&                        // the train row intersects this tile
+        in_train_segment(P.tri, rs->cur_train[row], rs->end_train[row], item)) return;   // not a candidate
+    if (s != s) { rs->nan[row] = 1; return; }                   // NaN candidate score => NaN row
+    const int slot = atomicAdd(&rs->cnt[row], 1);
     // slot < C always: the buffer holds <= C-BN entries when a tile starts and a tile adds <= BN
     const size_t base = (size_t)ulocal * C;
     P.cand_score[base + slot] = s;
     P.cand_item[base + slot] = item;
-    return (slot + 1) > (C - BN);
-}
-
-// AUC mode: per candidate score, bucket = number of the user's held-out item scores strictly below.
-template <typename T>
-__device__ __forceinline__ void auc_count(const ScoreSelectParams<T>& P, const T s, const int u,
-                                          const int tp0, const int npos)
-{
-    int lo = 0, hi = npos;
-    const T* __restrict__ ps = P.pos_sorted + tp0;
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (ps[mid] < s) lo = mid + 1; else hi = mid;
-    }
-    atomicAdd(&P.auc_cnt[(size_t)tp0 + u + lo], 1u);
 }
 
 template <typename T, int C, bool AUC>
@@ -259,205 +414,259 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 {
     constexpr int S = NumTraits<T>::STAGES;
-    constexpr int VEC = 16 / (int)sizeof(T);          // elements per 16-byte shared load
-    constexpr int NG = 8 / VEC;                        // vector groups per 8-wide micro-tile edge
-    constexpr int CHUNKS = BK * BM * (int)sizeof(T) / 16;   // 16B chunks per operand slab
+    constexpr int BK = NumTraits<T>::BK;
+    constexpr int BN = NumTraits<T>::BN;
+    constexpr int NC = MicroTile<T>::NC;            // item columns per thread
+    constexpr int VEC = 16 / (int)sizeof(T);
 
-    extern __shared__ __align__(16) unsigned char smem_raw[];
+    extern __shared__ __align__(128) unsigned char smem_raw[];
     T* As = reinterpret_cast<T*>(smem_raw);                       // [S][BK][BM]
     T* Bs = As + (size_t)S * BK * BM;                             // [S][BK][BN]
-    T* tau_s = Bs + (size_t)S * BK * BN;                          // [BM]
-    int* cnt_s = reinterpret_cast<int*>(tau_s + BM);              // [BM]
-    int* nan_s = cnt_s + BM;                                      // [BM]
+    RowState<T>* rs = reinterpret_cast<RowState<T>*>(Bs + (size_t)S * BK * BN);
+    u64* bars = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(rs) + ((sizeof(RowState<T>) + 15) & ~size_t(15)));
+    T* blk_all = reinterpret_cast<T*>(bars + 2 * S);              // AUC: [NCWARPS][8][BN]
+    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + S);
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int warp_m = warp & 3, warp_n = warp >> 2;
-    const int ly = lane >> 3, lx = lane & 7;
-    const int row_base = warp_m * 32 + ly * VEC;    // + g*(4*VEC) + (r % VEC)
-    const int col_base = warp_n * 64 + lx * VEC;    // + g*(8*VEC) + (c % VEC)
-
     const int tile_u0 = blockIdx.x * BM;            // first user (batch-local) of this CTA
-    const int KC = P.p_pad / BK;
+    const int KC = (P.p_pad + BK - 1) / BK;
     const int NT = (P.n + BN - 1) / BN;
     const int total = NT * KC;
 
-    // per-user selection state
+    // ---- one-time setup: per-row selection state, train cursors, barriers ----
     for (int r = tid; r < BM; r += NTHREADS) {
         const int ul = tile_u0 + r;
         const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0);
-        tau_s[r] = ranked ? -NumTraits<T>::inf() : NumTraits<T>::inf();
-        cnt_s[r] = 0;
-        nan_s[r] = 0;
+        rs->tau[r] = ranked ? -NumTraits<T>::inf() : NumTraits<T>::inf();
+        rs->cnt[r] = 0;
+        rs->nan[r] = 0;
+        int cur = 0, end = 0;
+        if (ranked) { cur = P.trp[P.user0 + ul]; end = P.trp[P.user0 + ul + 1]; }
+        rs->cur_train[r] = cur;
+        rs->end_train[r] = end;
+        rs->nxt_train[r] = cur < end ? P.tri[cur] : INT_MAX;
+    }
+    if (tid == 0) {
+        for (int s = 0; s < S; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, NCWARPS); }
+        mbar_fence_init();
+    }
+    __syncthreads();   // the only CTA-wide barrier
+
+    if (warp == NCWARPS) {
+        // ===================== producer: TMA ring over (item tile, k chunk) =====================
+        if (lane == 0) {
+            const T* gA = P.At + (size_t)blockIdx.x * P.p_pad * BM;
+            int tile = 0, kc = 0;
+            for (int it = 0; it < total; it++) {
+                const int s = it % S;
+                if (it >= S) mbar_wait(bar_empty + 8 * s, ((it / S) - 1) & 1);
+                const int k0 = kc * BK;
+                const int kcount = (P.p_pad - k0) < BK ? (P.p_pad - k0) : BK;
+                const unsigned bytes_a = (unsigned)(kcount * BM * sizeof(T)), bytes_b = (unsigned)(kcount * BN * sizeof(T));
+                mbar_arrive_expect_tx(bar_full + 8 * s, bytes_a + bytes_b);
+                tma_bulk_g2s(smem_u32(As + (size_t)s * BK * BM), gA + (size_t)k0 * BM, bytes_a, bar_full + 8 * s);
+                tma_bulk_g2s(smem_u32(Bs + (size_t)s * BK * BN), P.Bt + ((size_t)tile * P.p_pad + k0) * BN, bytes_b,
+                             bar_full + 8 * s);
+                if (++kc == KC) { kc = 0; tile++; }
+            }
+        }
+        return;
     }
 
-    T acc[8][8];
-#pragma unroll
-    for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int c = 0; c < 8; c++) acc[r][c] = (T)0;
+    // ===================== compute warps =====================
+    const int ly = lane >> 4, lx = lane & 15;
+    const int wrow0 = warp * 16;                    // first CTA row of this warp
+    T* blk = AUC ? (blk_all + (size_t)warp * 8 * BN) : nullptr;
 
-    T rowmin[8];
+    // AUC: held-out items owned by this lane (slot lx of rows wrow0 + 2*q + ly, q = 0..7)
+    T pj0[AUC ? 8 : 1];
+    unsigned cnt0[AUC ? 8 : 1];
+    T rowmin[AUC ? 8 : 1];
     if (AUC) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) rowmin[r] = NumTraits<T>::inf();
+        for (int q = 0; q < 8; q++) {
+            const int row = wrow0 + 2 * q + ly;
+            const int ul = tile_u0 + row;
+            pj0[q] = NumTraits<T>::inf();
+            cnt0[q] = 0;
+            rowmin[q] = NumTraits<T>::inf();
+            if (rs->tau[row] != NumTraits<T>::inf()) {
+                const int u = P.user0 + ul;
+                const int tp0 = P.tep[u], npos = P.tep[u + 1] - tp0;
+                if (lx < npos) pj0[q] = P.pos_sorted[tp0 + lx];
+            }
+        }
     }
 
-    const T* gA = P.At + tile_u0;
-    auto load_stage = [&](const int stage, const int tile, const int kc) {
-        const T* srcA = gA + (size_t)(kc * BK) * P.ldA;
-        const T* srcB = P.Bt + (size_t)(kc * BK) * P.ldB + (size_t)tile * BN;
-        T* dA = As + (size_t)stage * BK * BM;
-        T* dB = Bs + (size_t)stage * BK * BN;
-        constexpr int CPR = BM * (int)sizeof(T) / 16;     // chunks per k-row
+    MicroTile<T> mt;
+    int it = 0;
+    for (int tile = 0; tile < NT; tile++) {
+        const int item0 = tile * BN;
+        mt.zero();
+        for (int kc = 0; kc < KC; kc++, it++) {
+            const int s = it % S;
+            mbar_wait(bar_full + 8 * s, (it / S) & 1);
+            const int k0 = kc * BK;
+            const int kcount = (P.p_pad - k0) < BK ? (P.p_pad - k0) : BK;
+            const T* sA = As + (size_t)s * BK * BM + wrow0;
+            const T* sB = Bs + (size_t)s * BK * BN;
+            for (int kk0 = 0; kk0 < kcount; kk0 += KPAD) {
 #pragma unroll
-        for (int i = tid; i < CHUNKS; i += NTHREADS) {
-            const int kr = i / CPR, ch = i % CPR;
-            cp_async16(dA + kr * BM + ch * VEC, srcA + (size_t)kr * P.ldA + ch * VEC);
-            cp_async16(dB + kr * BN + ch * VEC, srcB + (size_t)kr * P.ldB + ch * VEC);
-        }
-    };
-
-    // prologue: S-1 stages in flight
-    int ld_tile = 0, ld_kc = 0;
-#pragma unroll
-    for (int s = 0; s < S - 1; s++) {
-        if (s < total) {
-            load_stage(s, ld_tile, ld_kc);
-            if (++ld_kc == KC) { ld_kc = 0; ld_tile++; }
-        }
-        cp_async_commit();
-    }
-
-    int tile = 0, kc = 0;
-    for (int it = 0; it < total; it++) {
-        cp_async_wait<S - 2>();
-        __syncthreads();
-        {
-            const int nxt = it + S - 1;
-            if (nxt < total) {
-                load_stage(nxt % S, ld_tile, ld_kc);
-                if (++ld_kc == KC) { ld_kc = 0; ld_tile++; }
+                for (int kk = 0; kk < KPAD; kk++) mt.step(sA + (kk0 + kk) * BM, sB + (kk0 + kk) * BN, ly, lx);
             }
-            cp_async_commit();
-        }
-        const T* sA = As + (size_t)(it % S) * BK * BM;
-        const T* sB = Bs + (size_t)(it % S) * BK * BN;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk++) {
-            T a[8], b[8];
-#pragma unroll
-            for (int g = 0; g < NG; g++) {
-                lds_vec(sA + kk * BM + row_base + g * 4 * VEC, &a[g * VEC]);
-                lds_vec(sB + kk * BN + col_base + g * 8 * VEC, &b[g * VEC]);
-            }
-#pragma unroll
-            for (int r = 0; r < 8; r++)
-#pragma unroll
-                for (int c = 0; c < 8; c++) acc[r][c] = NumTraits<T>::fma(a[r], b[c], acc[r][c]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }
 
-        if (++kc == KC) {
-            // ---------------- epilogue of item tile `tile` ----------------
-            kc = 0;
-            const int item0 = tile * BN;
-            T biasv[8];
-            if (P.bias != nullptr) {
+        // ---------------- epilogue of item tile `tile` (warp-private) ----------------
+        T biasv[NC];
+        if (P.bias != nullptr) {
 #pragma unroll
-                for (int c = 0; c < 8; c++)
-                    biasv[c] = P.bias[item0 + col_base + (c / VEC) * 8 * VEC + (c % VEC)];
-            }
-            bool trig = false;
+            for (int c = 0; c < NC; c++) biasv[c] = P.bias[item0 + lx * 4 + (c & 3) + (c >> 2) * 64];
+        }
+        bool inserted = false;
 #pragma unroll
-            for (int r = 0; r < 8; r++) {
-                const int row = row_base + (r / VEC) * 4 * VEC + (r % VEC);
-                const T tau = tau_s[row];
-                const int ulocal = tile_u0 + row;
-                int tp0 = 0, npos = 0;
-                bool ranked = false, row_has_train = false;
+        for (int h = 0; h < 2; h++) {
+#pragma unroll
+            for (int i4 = 0; i4 < 4; i4++) {
+                const int i = h * 4 + i4;
+                const int row = wrow0 + ly * 4 + i4 + h * 8;
+                T s[NC];
+                mt.row(i, s);
+                if (P.bias != nullptr) {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) s[c] += biasv[c];
+                }
+                const T tau = rs->tau[row];
+                T m = max_nan(max_nan(s[0], s[1]), max_nan(s[2], s[3]));
+                if (NC == 8) m = max_nan(m, max_nan(max_nan(s[NC - 4], s[NC - 3]), max_nan(s[NC - 2], s[NC - 1])));
+                if (!(m < tau) && tau != NumTraits<T>::inf()) {
+#pragma unroll
+                    for (int c = 0; c < NC; c++) {
+                        if (!(s[c] < tau)) {
+                            select_insert<T, C>(P, rs, s[c], row, tile_u0 + row, item0 + lx * 4 + (c & 3) + (c >> 2) * 64, item0 + BN);
+                            inserted = true;
+                        }
+                    }
+                }
                 if (AUC) {
-                    ranked = (tau != NumTraits<T>::inf());   // tau == +inf <=> padding / NaN-row user
-                    if (ranked) {
-                        const int u = P.user0 + ulocal;
-                        tp0 = P.tep[u];
-                        npos = P.tep[u + 1] - tp0;
-                        // does the train row intersect this item tile at all?
-                        int lo = P.trp[u], hi = P.trp[u + 1];
-                        const int end = hi;
-                        while (lo < hi) {
-                            const int mid = (lo + hi) >> 1;
-                            if (P.tri[mid] < item0) lo = mid + 1; else hi = mid;
-                        }
-                        row_has_train = (lo < end) && (P.tri[lo] < item0 + BN);
-                    }
-                }
+                    // mask what is not a candidate, track the smallest candidate score, stage the row
+                    const bool ranked = tau != NumTraits<T>::inf();
+                    const bool has_train = rs->nxt_train[row] < item0 + BN;
+                    T rmin = NumTraits<T>::inf();
 #pragma unroll
-                for (int c = 0; c < 8; c++) {
-                    T s = acc[r][c];
-                    if (P.bias != nullptr) s += biasv[c];
-                    acc[r][c] = (T)0;
-                    const int item = item0 + col_base + (c / VEC) * 8 * VEC + (c % VEC);
-                    if (AUC) {
-                        if (ranked && item < P.n &&
-                            !(row_has_train && in_train_row(P.trp, P.tri, P.user0 + ulocal, item))) {
-                            if (s == s) {
-                                rowmin[r] = s < rowmin[r] ? s : rowmin[r];
-                                auc_count<T>(P, s, P.user0 + ulocal, tp0, npos);
-                            }
+                    for (int c = 0; c < NC; c++) {
+                        const int item = item0 + lx * 4 + (c & 3) + (c >> 2) * 64;
+                        bool drop = !ranked || item >= P.n || (s[c] != s[c]);
+                        if (!drop && has_train) drop = in_train_segment(P.tri, rs->cur_train[row], rs->end_train[row], item);
+                        s[c] = drop ? -NumTraits<T>::inf() : s[c];
+                        rmin = drop ? rmin : (s[c] < rmin ? s[c] : rmin);
+                    }
+                    rowmin[i] = rmin < rowmin[i] ? rmin : rowmin[i];
+                    T* dst = blk + (size_t)(ly * 4 + i4) * BN + lx * 4;
+                    sts4(dst, &s[0]);
+                    if (NC == 8) sts4(dst + 64, &s[NC - 4]);
+                }
+            }
+            if (AUC) {
+                // count: rows wrow0 + 8h + b, b = 2*q4 + ly; this lane owns held-out slots lx, lx+16, ...
+                __syncwarp();
+#pragma unroll
+                for (int q4 = 0; q4 < 4; q4++) {
+                    const int b = 2 * q4 + ly;
+                    const int q = h * 4 + q4;                  // index into pj0 / cnt0 (row wrow0 + 8h + b)
+                    const T* src = blk + (size_t)b * BN;
+                    const T pj = pj0[q];
+                    unsigned c0 = 0;
+#pragma unroll 8
+                    for (int x = 0; x < BN; x += VEC) {
+                        T v[VEC];
+                        lds_vec(src + x, v);
+#pragma unroll
+                        for (int e = 0; e < VEC; e++) c0 += (v[e] > pj) ? 1u : 0u;
+                    }
+                    cnt0[q] += c0;
+                    // rows with more than 16 held-out items: remaining slots straight to global counters
+                    const int row = wrow0 + 8 * h + b;
+                    if (rs->tau[row] != NumTraits<T>::inf()) {
+                        const int u = P.user0 + tile_u0 + row;
+                        const int tp0 = P.tep[u], npos = P.tep[u + 1] - tp0;
+                        for (int j = lx + 16; j < npos; j += 16) {
+                            const T pjj = P.pos_sorted[tp0 + j];
+                            unsigned cj = 0;
+                            for (int x = 0; x < BN; x++) cj += (src[x] > pjj) ? 1u : 0u;
+                            if (cj) atomicAdd(&P.auc_cnt[(size_t)tp0 + j], cj);
                         }
                     }
-                    if (!(s < tau))
-                        trig |= select_insert<T, C>(P, s, row, ulocal, item, cnt_s, nan_s);
                 }
+                __syncwarp();
             }
-            // re-sort the buffers that passed the trigger (rare after the first few tiles)
-            if (__syncthreads_or(trig ? 1 : 0)) {
-                for (int q = 0; q < BM / 8; q++) {
-                    const int row = warp * (BM / 8) + q;
-                    const int nv = cnt_s[row];
-                    if (nv > C - BN) {
-                        const size_t base = (size_t)(tile_u0 + row) * C;
-                        compact_user<T, C>(P.cand_score + base, P.cand_item + base, nv, P.K, lane,
-                                           &tau_s[row], &cnt_s[row]);
-                    }
-                }
-                __syncthreads();
-            }
-            tile++;
         }
-    }
-    cp_async_wait<0>();
-    __syncthreads();
 
-    // final ranking of every user of the tile
-    for (int q = 0; q < BM / 8; q++) {
-        const int row = warp * (BM / 8) + q;
+        // advance the train cursors of the warp's rows past this tile (lanes 0..15, rare)
+        __syncwarp();
+        if (lane < 16) {
+            const int row = wrow0 + lane;
+            int nxt = rs->nxt_train[row];
+            if (nxt < item0 + BN) {
+                int cur = rs->cur_train[row];
+                const int end = rs->end_train[row];
+                while (cur < end && (nxt = P.tri[cur]) < item0 + BN) cur++;
+                rs->cur_train[row] = cur;
+                rs->nxt_train[row] = cur < end ? nxt : INT_MAX;
+            }
+        }
+        // re-sort the buffers of this warp that passed the trigger (rare after the first few tiles)
+        if (__any_sync(FULL, inserted)) {
+            __syncwarp();
+            const int nv_l = lane < 16 ? rs->cnt[wrow0 + lane] : 0;
+            unsigned need = __ballot_sync(FULL, nv_l > C - BN);
+            while (need) {
+                const int r = __ffs(need) - 1;
+                need &= need - 1;
+                const int row = wrow0 + r;
+                const size_t base = (size_t)(tile_u0 + row) * C;
+                compact_user<T, C>(P.cand_score + base, P.cand_item + base, rs->cnt[row], P.K, lane, &rs->tau[row], &rs->cnt[row]);
+            }
+        }
+        __syncwarp();
+    }
+
+    // ---- final ranking of the warp's users ----
+    for (int r = 0; r < 16; r++) {
+        const int row = wrow0 + r;
         const int ul = tile_u0 + row;
         if (ul < P.mb) {
             const size_t base = (size_t)ul * C;
-            compact_user<T, C>(P.cand_score + base, P.cand_item + base, cnt_s[row], P.K, lane,
-                               &tau_s[row], &cnt_s[row]);
+            compact_user<T, C>(P.cand_score + base, P.cand_item + base, rs->cnt[row], P.K, lane, &rs->tau[row], &rs->cnt[row]);
             if (lane == 0) {
-                P.cand_count[ul] = cnt_s[row];
-                if (nan_s[row]) atomicOr(&P.uflags[P.user0 + ul], 1);
+                P.cand_count[ul] = rs->cnt[row];
+                if (rs->nan[row]) atomicOr(&P.uflags[P.user0 + ul], 1);
             }
         }
     }
     if (AUC) {
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            const int row = row_base + (r / VEC) * 4 * VEC + (r % VEC);
+        for (int q = 0; q < 8; q++) {
+            // counters: row wrow0 + 8*(q>>2) + 2*(q&3) + ly, slot lx
+            const int row = wrow0 + 8 * (q >> 2) + 2 * (q & 3) + ly;
             const int ul = tile_u0 + row;
-            if (ul < P.mb && rowmin[r] != NumTraits<T>::inf())
-                atomicMin(&P.umin[P.user0 + ul], NumTraits<T>::orderable(rowmin[r]));
+            if (ul < P.mb && P.ustatus[P.user0 + ul] == 0) {
+                const int u = P.user0 + ul;
+                const int tp0 = P.tep[u], npos = P.tep[u + 1] - tp0;
+                if (lx < npos) P.auc_cnt[(size_t)tp0 + lx] = cnt0[q];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            // smallest candidate score: thread row i = CTA row wrow0 + ly*4 + (i&3) + (i>>2)*8
+            const int row = wrow0 + ly * 4 + (i & 3) + (i >> 2) * 8;
+            const int ul = tile_u0 + row;
+            if (ul < P.mb && rowmin[i] != NumTraits<T>::inf())
+                atomicMin(&P.umin[P.user0 + ul], NumTraits<T>::orderable(rowmin[i]));
         }
     }
-}
-
-template <typename T>
-inline size_t score_select_smem_bytes()
-{
-    return (size_t)NumTraits<T>::STAGES * BK * (BM + BN) * sizeof(T) + BM * sizeof(T) + 2 * BM * sizeof(int);
 }
 
 }  // namespace rmb
