@@ -139,6 +139,19 @@ cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool 
                : launch_score_select_inst<T, 1024, false>(P, n_user_tiles, st);
 }
 
+// order the <= K survivors of every user (warp per user, bitonic network sized to K)
+template <typename T>
+cudaError_t launch_rank_topk(T* cs, int* ci, const int* cc, int C, int nb, int K, cudaStream_t st)
+{
+    const int blocks = (nb + 7) / 8;
+    if (K <= 32) rmb::rank_topk_kernel<T, 1><<<blocks, 256, 0, st>>>(cs, ci, cc, C, nb);
+    else if (K <= 64) rmb::rank_topk_kernel<T, 2><<<blocks, 256, 0, st>>>(cs, ci, cc, C, nb);
+    else if (K <= 128) rmb::rank_topk_kernel<T, 4><<<blocks, 256, 0, st>>>(cs, ci, cc, C, nb);
+    else if (K <= 256) rmb::rank_topk_kernel<T, 8><<<blocks, 256, 0, st>>>(cs, ci, cc, C, nb);
+    else rmb::rank_topk_kernel<T, 16><<<blocks, 256, 0, st>>>(cs, ci, cc, C, nb);
+    return cudaGetLastError();
+}
+
 // Copy a row-major host/device matrix slab [rows][cols] (leading dimension ld) into a compact
 // device buffer when it lives on the host; on-device inputs are used in place.
 template <typename T>
@@ -419,7 +432,8 @@ int run_call(const CallArgs<T>& a)
             sp.auc_cnt = count_ranks ? d_auc.as<unsigned int>() : nullptr;
             sp.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
             CK(launch_score_select<T>(sp, C, count_ranks, nb_pad / BM, st));
-            tm.kernel_launches++;
+            CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
+            tm.kernel_launches += 2;
         }
         pt.stop(tm.score_select_ms);
 

@@ -23,13 +23,16 @@
 //     and compares it with the user's running K-th best (tau).  Survivors (~K ln(n/K) per user over
 //     the whole catalogue) are checked against the user's train row (only in item tiles the sorted
 //     train row intersects -- a per-row cursor keeps the next train item id) and appended to a
-//     per-user candidate buffer of C entries in global memory (L2 resident); the owning warp
-//     re-sorts a buffer (bitonic network in registers) when it passes C - 128 entries, which
-//     refreshes tau.  At the end the buffer head holds the user's top-K in rank order.
-//   * AUC mode (ROC/PR requested): the warp stages its 16x128 score block (train items masked) in
-//     shared memory and every lane counts, for the held-out items it owns, the candidates scoring
-//     strictly higher (compare + add, no atomics, counters in registers).  Scores of held-out
-//     items are pre-computed with the same FMA order (prep.cuh) so comparisons are exact.
+//     per-user candidate buffer of C entries in global memory (L2 resident).  When a buffer passes
+//     C - BN entries its warp cuts it back to the best K with a bitwise radix select on the
+//     order-preserving integer image of the scores (warp REDUX counts; ties at the cut resolved by
+//     item id), which refreshes tau.  rank_topk_kernel finally orders the K survivors.
+//   * AUC mode (ROC/PR requested): the warp stages its 16 x BN score block in shared memory, masks
+//     train items there, and every lane counts, for the held-out items it owns, the candidates
+//     scoring strictly higher (compare + add, no atomics).  Scores of held-out items are
+//     pre-computed with the same FMA order (prep.cuh) so comparisons are exact.
+//   * Everything outside the FMA loop is written as rolled loops / out-of-line calls: the epilogue
+//     runs once per item tile and must not evict the FMA loop from the instruction cache.
 #pragma once
 #include <cuda_runtime.h>
 #include <math_constants.h>
@@ -51,7 +54,11 @@ template <> struct NumTraits<float> {
     static constexpr int BN = 128;      // items per tile (thread micro-tile 8 users x 8 items)
     static constexpr int BK = 32;       // factors per pipeline stage
     static constexpr int STAGES = 4;
+    typedef unsigned key_t;             // order-preserving integer image of a score
+    static constexpr int KEYBITS = 32;
+    __device__ __forceinline__ static key_t key(float x) { return (key_t)orderable(x); }
     __device__ __forceinline__ static float inf() { return CUDART_INF_F; }
+    __device__ __forceinline__ static float nan() { return CUDART_NAN_F; }
     __device__ __forceinline__ static float fma(float a, float b, float c) { return fmaf(a, b, c); }
     __device__ __forceinline__ static u64 orderable(float x) {
         unsigned u = __float_as_uint(x);
@@ -71,9 +78,13 @@ template <> struct NumTraits<float> {
 template <> struct NumTraits<double> {
     static constexpr int BN = 64;       // items per tile (thread micro-tile 8 users x 4 items: the
                                         // register file of a 9-warp CTA holds 168 registers per thread)
-    static constexpr int BK = 32;
-    static constexpr int STAGES = 3;
+    static constexpr int BK = 16;
+    static constexpr int STAGES = 4;
+    typedef u64 key_t;
+    static constexpr int KEYBITS = 64;
+    __device__ __forceinline__ static key_t key(double x) { return orderable(x); }
     __device__ __forceinline__ static double inf() { return CUDART_INF; }
+    __device__ __forceinline__ static double nan() { return CUDART_NAN; }
     __device__ __forceinline__ static double fma(double a, double b, double c) { return ::fma(a, b, c); }
     __device__ __forceinline__ static u64 orderable(double x) {
         u64 u = (u64)__double_as_longlong(x);
@@ -142,41 +153,6 @@ __device__ __forceinline__ void warp_sort_ranked(T (&s)[E], int (&it)[E], const 
     }
 }
 
-// One warp: sort the first nv entries of a user's candidate buffer, keep the best min(nv,K) at the
-// head (rank order), publish the new K-th best score (tau) and the new count.
-template <typename T, int C>
-__device__ __noinline__ void compact_user(T* cs, int* ci, const int nv, const int K, const int lane,
-                                          T* tau_out, int* cnt_out)
-{
-    constexpr int E = C / 32;
-    T s[E];
-    int it[E];
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const int idx = e * 32 + lane;
-        const bool v = idx < nv;
-        s[e] = v ? cs[idx] : -NumTraits<T>::inf();
-        it[e] = v ? ci[idx] : INT_MAX;
-    }
-    warp_sort_ranked<T, E>(s, it, lane);
-    const int keep = nv < K ? nv : K;
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const int idx = e * 32 + lane;
-        if (idx < keep) { cs[idx] = s[e]; ci[idx] = it[e]; }
-    }
-    if (nv >= K) {
-        T kth = -NumTraits<T>::inf();
-#pragma unroll
-        for (int e = 0; e < E; e++)
-            if (e == ((K - 1) >> 5)) kth = s[e];
-        kth = __shfl_sync(FULL, kth, (K - 1) & 31);
-        if (lane == 0) *tau_out = kth;
-    }
-    if (lane == 0) *cnt_out = keep;
-    __syncwarp();
-}
-
 template <typename T>
 struct ScoreSelectParams {
     const T* __restrict__ At;      // [user tiles][p_pad][128]  user factors of this batch, zero padded
@@ -192,7 +168,7 @@ struct ScoreSelectParams {
     const int* __restrict__ ustatus;// [m] 0 = user is ranked, !=0 = NaN row decided before scoring
     T* cand_score;                  // [mb_pad][C]
     int* cand_item;                 // [mb_pad][C]
-    int* cand_count;                // [mb_pad] final number of ranked entries at the head (<= K)
+    int* cand_count;                // [mb_pad] entries left at the head of the buffer (<= K, unordered)
     int* uflags;                    // [m] bit0: a candidate score was NaN
     int K;
     // rank counting (AUC mode)
@@ -359,6 +335,7 @@ template <> struct MicroTile<double> {
     }
 };
 
+
 // ------------------------------------------------------------------ per-CTA shared state
 template <typename T>
 struct RowState {
@@ -368,17 +345,98 @@ struct RowState {
     int nxt_train[BM];  // smallest train item id >= first item of the current tile (INT_MAX: none)
     int cur_train[BM];  // its position in the train CSR
     int end_train[BM];
+    int tp0[BM];        // first entry of the held-out (test) row
+    int npos[BM];       // its length (0 for rows that are not ranked)
+};
+
+template <typename T>
+struct SmemLayout {
+    static constexpr int S = NumTraits<T>::STAGES, BK = NumTraits<T>::BK, BN = NumTraits<T>::BN;
+    static constexpr size_t a_off = 0;                                            // [S][BK][BM]
+    static constexpr size_t b_off = (size_t)S * BK * BM * sizeof(T);              // [S][BK][BN]
+    static constexpr size_t rs_off = b_off + (size_t)S * BK * BN * sizeof(T);
+    static constexpr size_t bar_off = rs_off + ((sizeof(RowState<T>) + 15) & ~size_t(15));   // full[S], empty[S]
+    static constexpr size_t plain_bytes = bar_off + 2 * S * sizeof(u64);
+    // AUC mode only
+    static constexpr size_t blk_off = plain_bytes;                                // [NCWARPS][16][BN] score blocks
+    static constexpr size_t pj_off = blk_off + (size_t)NCWARPS * 16 * BN * sizeof(T);    // [BM][16] thresholds
+    static constexpr size_t cj_off = pj_off + (size_t)BM * 16 * sizeof(T);               // [BM][16] counters
+    static constexpr size_t auc_bytes = cj_off + (size_t)BM * 16 * sizeof(unsigned);
 };
 
 template <typename T, bool AUC>
-inline size_t score_select_smem_bytes()
+inline size_t score_select_smem_bytes() { return AUC ? SmemLayout<T>::auc_bytes : SmemLayout<T>::plain_bytes; }
+
+extern __shared__ __align__(128) unsigned char smem_raw[];
+template <typename T>
+__device__ __forceinline__ RowState<T>* row_state() { return reinterpret_cast<RowState<T>*>(smem_raw + SmemLayout<T>::rs_off); }
+
+// ------------------------------------------------------------------ selection: out-of-line slow paths
+// One warp: cut the first nv (>= K) entries of a user's candidate buffer back to the best K
+// (score descending, ties at the cut by ascending item id -- the order of ranks_before), left
+// unordered at the head; publish the K-th best score (tau) and the new count.
+template <typename T, int C>
+__device__ __noinline__ void compact_user(T* cs, int* ci, const int nv, const int K, const int lane,
+                                          T* tau_out, int* cnt_out)
 {
-    constexpr int BN = NumTraits<T>::BN;
-    size_t b = (size_t)NumTraits<T>::STAGES * NumTraits<T>::BK * (BM + BN) * sizeof(T);   // operand ring
-    b += sizeof(RowState<T>);
-    b += 2 * NumTraits<T>::STAGES * sizeof(u64);                                          // mbarriers
-    if (AUC) b += (size_t)NCWARPS * 8 * BN * sizeof(T);                                   // score half-blocks
-    return b + 128;
+    typedef typename NumTraits<T>::key_t key_t;
+    constexpr int E = C / 32;
+    if (nv < K) return;                       // nothing to drop yet; tau stays -inf
+    key_t key[E];
+    int it[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int idx = e * 32 + lane;
+        const bool v = idx < nv;
+        key[e] = v ? NumTraits<T>::key(cs[idx]) : (key_t)0;     // 0 sorts below every score (NaN is never stored)
+        it[e] = v ? ci[idx] : INT_MAX;
+    }
+    __syncwarp();
+    // K-th largest key, bit by bit from the top: the largest t with #(key >= t) >= K
+    key_t t = 0;
+    for (int b = NumTraits<T>::KEYBITS - 1; b >= 0; b--) {
+        const key_t cand = t | ((key_t)1 << b);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) c += (key[e] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(FULL, c);
+        if (c >= K) t = cand;
+    }
+    int cgt = 0, cge = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) { cgt += (key[e] > t) ? 1 : 0; cge += (key[e] >= t) ? 1 : 0; }
+    cgt = __reduce_add_sync(FULL, cgt);
+    cge = __reduce_add_sync(FULL, cge);
+    unsigned id_cut = 0x7fffffffu;            // keep tied entries with item id <= id_cut
+    if (cge > K) {
+        // more entries tie with the K-th score than fit: keep the (K - cgt) smallest item ids among them,
+        // i.e. id_cut = max{x : #(tied, id < x) < need}
+        const int need = K - cgt;
+        unsigned x = 0;
+        for (int b = 30; b >= 0; b--) {
+            const unsigned cand = x | (1u << b);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < E; e++) c += (key[e] == t && (unsigned)it[e] < cand) ? 1 : 0;
+            c = __reduce_add_sync(FULL, c);
+            if (c < need) x = cand;
+        }
+        id_cut = x;
+    }
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const bool keep = (key[e] > t) || (key[e] == t && (unsigned)it[e] <= id_cut);
+        const unsigned mask = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+            cs[pos] = NumTraits<T>::from_orderable((u64)key[e]);
+            ci[pos] = it[e];
+        }
+        base += __popc(mask);
+    }
+    if (lane == 0) { *tau_out = NumTraits<T>::from_orderable((u64)t); *cnt_out = base; }
+    __syncwarp();
 }
 
 // is `item` in the sorted train row segment [lo, hi) ?  (hpp:494-495 moves those out of the pool)
@@ -395,8 +453,8 @@ __device__ __forceinline__ bool in_train_segment(const int* __restrict__ tri, in
 // Slow path of the selection filter (taken by ~K ln(n/K) scores per user): candidate checks, then
 // append to the user's buffer.
 template <typename T, int C>
-__device__ __noinline__ void select_insert(const ScoreSelectParams<T>& P, RowState<T>* rs, const T s, const int row,
-                                           const int ulocal, const int item, const int item_end)
+__device__ __forceinline__ void insert_candidate(const ScoreSelectParams<T>& P, RowState<T>* rs, const T s, const int row,
+                                                 const int ulocal, const int item, const int item_end)
 {
     if (item >= P.n) return;                                    // padding column
     if (rs->nxt_train[row] < item_end &&                        // the train row intersects this tile
@@ -409,23 +467,67 @@ __device__ __noinline__ void select_insert(const ScoreSelectParams<T>& P, RowSta
     P.cand_item[base + slot] = item;
 }
 
+// A thread's scores of one user row in one item tile, at least one of which is not below tau.
+// item_lo = id of the thread's first column; columns c >= 4 sit 64 items further.
+template <typename T, int C>
+__device__ __noinline__ void row_slow(const ScoreSelectParams<T>& P, const T tau, const int row, const int ulocal,
+                                      const int item_lo, const int item_end,
+                                      const T s0, const T s1, const T s2, const T s3)
+{
+    RowState<T>* rs = row_state<T>();
+    if (!(s0 < tau)) insert_candidate<T, C>(P, rs, s0, row, ulocal, item_lo, item_end);
+    if (!(s1 < tau)) insert_candidate<T, C>(P, rs, s1, row, ulocal, item_lo + 1, item_end);
+    if (!(s2 < tau)) insert_candidate<T, C>(P, rs, s2, row, ulocal, item_lo + 2, item_end);
+    if (!(s3 < tau)) insert_candidate<T, C>(P, rs, s3, row, ulocal, item_lo + 3, item_end);
+}
+
+// number of a / b / c / d strictly above p, subtracted as 0 / -1 masks (SASS: FSET + IADD3)
+__device__ __forceinline__ unsigned gt_mask(const float a, const float p)
+{
+    unsigned r;
+    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned gt_mask(const double a, const double p)
+{
+    unsigned r;
+    asm("set.gt.u32.f64 %0, %1, %2;" : "=r"(r) : "d"(a), "d"(p));
+    return r;
+}
+
+// AUC counting of one staged row (BN scores at src) against up to 4 thresholds per lane.
+template <typename T, int NT>
+__device__ __forceinline__ void count_above(const T* __restrict__ src, const T (&thr)[NT], unsigned (&cnt)[NT])
+{
+    constexpr int BN = NumTraits<T>::BN;
+    constexpr int VEC = 16 / (int)sizeof(T);
+#pragma unroll 4
+    for (int x = 0; x < BN; x += VEC) {
+        T v[VEC];
+        lds_vec(src + x, v);
+#pragma unroll
+        for (int q = 0; q < NT; q++)
+#pragma unroll
+            for (int e = 0; e < VEC; e++) cnt[q] -= gt_mask(v[e], thr[q]);
+    }
+}
+
 template <typename T, int C, bool AUC>
 __global__ void __launch_bounds__(NTHREADS, 1)
 score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 {
+    typedef SmemLayout<T> L;
     constexpr int S = NumTraits<T>::STAGES;
     constexpr int BK = NumTraits<T>::BK;
     constexpr int BN = NumTraits<T>::BN;
     constexpr int NC = MicroTile<T>::NC;            // item columns per thread
-    constexpr int VEC = 16 / (int)sizeof(T);
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    T* As = reinterpret_cast<T*>(smem_raw);                       // [S][BK][BM]
-    T* Bs = As + (size_t)S * BK * BM;                             // [S][BK][BN]
-    RowState<T>* rs = reinterpret_cast<RowState<T>*>(Bs + (size_t)S * BK * BN);
-    u64* bars = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(rs) + ((sizeof(RowState<T>) + 15) & ~size_t(15)));
-    T* blk_all = reinterpret_cast<T*>(bars + 2 * S);              // AUC: [NCWARPS][8][BN]
-    const unsigned bar_full = smem_u32(bars), bar_empty = smem_u32(bars + S);
+    T* As = reinterpret_cast<T*>(smem_raw + L::a_off);
+    T* Bs = reinterpret_cast<T*>(smem_raw + L::b_off);
+    RowState<T>* rs = row_state<T>();
+    const unsigned bar_full = smem_u32(smem_raw + L::bar_off), bar_empty = bar_full + 8 * S;
+    T* pj_s = reinterpret_cast<T*>(smem_raw + L::pj_off);                 // AUC only
+    unsigned* cj_s = reinterpret_cast<unsigned*>(smem_raw + L::cj_off);   // AUC only
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -441,11 +543,23 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
         rs->tau[r] = ranked ? -NumTraits<T>::inf() : NumTraits<T>::inf();
         rs->cnt[r] = 0;
         rs->nan[r] = 0;
-        int cur = 0, end = 0;
-        if (ranked) { cur = P.trp[P.user0 + ul]; end = P.trp[P.user0 + ul + 1]; }
+        int cur = 0, end = 0, tp0 = 0, npos = 0;
+        if (ranked) {
+            const int u = P.user0 + ul;
+            cur = P.trp[u]; end = P.trp[u + 1];
+            tp0 = P.tep[u]; npos = P.tep[u + 1] - tp0;
+        }
         rs->cur_train[r] = cur;
         rs->end_train[r] = end;
         rs->nxt_train[r] = cur < end ? P.tri[cur] : INT_MAX;
+        rs->tp0[r] = tp0;
+        rs->npos[r] = npos;
+        if (AUC) {
+            for (int j = 0; j < 16; j++) {
+                pj_s[r * 16 + j] = j < npos ? P.pos_sorted[tp0 + j] : NumTraits<T>::inf();
+                cj_s[r * 16 + j] = 0;
+            }
+        }
     }
     if (tid == 0) {
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, NCWARPS); }
@@ -477,26 +591,12 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
     // ===================== compute warps =====================
     const int ly = lane >> 4, lx = lane & 15;
     const int wrow0 = warp * 16;                    // first CTA row of this warp
-    T* blk = AUC ? (blk_all + (size_t)warp * 8 * BN) : nullptr;
+    T* blk = reinterpret_cast<T*>(smem_raw + L::blk_off) + (size_t)warp * 16 * BN;   // AUC only: [16][BN]
 
-    // AUC: held-out items owned by this lane (slot lx of rows wrow0 + 2*q + ly, q = 0..7)
-    T pj0[AUC ? 8 : 1];
-    unsigned cnt0[AUC ? 8 : 1];
-    T rowmin[AUC ? 8 : 1];
+    T rowmin[AUC ? 8 : 1];                          // AUC: smallest candidate score seen per thread row
     if (AUC) {
 #pragma unroll
-        for (int q = 0; q < 8; q++) {
-            const int row = wrow0 + 2 * q + ly;
-            const int ul = tile_u0 + row;
-            pj0[q] = NumTraits<T>::inf();
-            cnt0[q] = 0;
-            rowmin[q] = NumTraits<T>::inf();
-            if (rs->tau[row] != NumTraits<T>::inf()) {
-                const int u = P.user0 + ul;
-                const int tp0 = P.tep[u], npos = P.tep[u + 1] - tp0;
-                if (lx < npos) pj0[q] = P.pos_sorted[tp0 + lx];
-            }
-        }
+        for (int i = 0; i < 8; i++) rowmin[i] = NumTraits<T>::inf();
     }
 
     MicroTile<T> mt;
@@ -525,87 +625,109 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 #pragma unroll
             for (int c = 0; c < NC; c++) biasv[c] = P.bias[item0 + lx * 4 + (c & 3) + (c >> 2) * 64];
         }
+        const bool tile_has_padding = item0 + BN > P.n;
         bool inserted = false;
+        unsigned remask = 0;                         // AUC: thread rows whose minimum must be re-read after masking
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
+        for (int i = 0; i < 8; i++) {
+            const int row_l = ly * 4 + (i & 3) + (i >> 2) * 8;
+            const int row = wrow0 + row_l;
+            T s[NC];
+            mt.row(i, s);
+            if (P.bias != nullptr) {
 #pragma unroll
-            for (int i4 = 0; i4 < 4; i4++) {
-                const int i = h * 4 + i4;
-                const int row = wrow0 + ly * 4 + i4 + h * 8;
-                T s[NC];
-                mt.row(i, s);
-                if (P.bias != nullptr) {
-#pragma unroll
-                    for (int c = 0; c < NC; c++) s[c] += biasv[c];
-                }
-                const T tau = rs->tau[row];
-                T m = max_nan(max_nan(s[0], s[1]), max_nan(s[2], s[3]));
-                if (NC == 8) m = max_nan(m, max_nan(max_nan(s[NC - 4], s[NC - 3]), max_nan(s[NC - 2], s[NC - 1])));
-                if (!(m < tau) && tau != NumTraits<T>::inf()) {
-#pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        if (!(s[c] < tau)) {
-                            select_insert<T, C>(P, rs, s[c], row, tile_u0 + row, item0 + lx * 4 + (c & 3) + (c >> 2) * 64, item0 + BN);
-                            inserted = true;
-                        }
-                    }
-                }
-                if (AUC) {
-                    // mask what is not a candidate, track the smallest candidate score, stage the row
-                    const bool ranked = tau != NumTraits<T>::inf();
-                    const bool has_train = rs->nxt_train[row] < item0 + BN;
-                    T rmin = NumTraits<T>::inf();
-#pragma unroll
-                    for (int c = 0; c < NC; c++) {
-                        const int item = item0 + lx * 4 + (c & 3) + (c >> 2) * 64;
-                        bool drop = !ranked || item >= P.n || (s[c] != s[c]);
-                        if (!drop && has_train) drop = in_train_segment(P.tri, rs->cur_train[row], rs->end_train[row], item);
-                        s[c] = drop ? -NumTraits<T>::inf() : s[c];
-                        rmin = drop ? rmin : (s[c] < rmin ? s[c] : rmin);
-                    }
-                    rowmin[i] = rmin < rowmin[i] ? rmin : rowmin[i];
-                    T* dst = blk + (size_t)(ly * 4 + i4) * BN + lx * 4;
-                    sts4(dst, &s[0]);
-                    if (NC == 8) sts4(dst + 64, &s[NC - 4]);
-                }
+                for (int c = 0; c < NC; c++) s[c] += biasv[c];
+            }
+            const T tau = rs->tau[row];
+            T m = max_nan(max_nan(s[0], s[1]), max_nan(s[2], s[3]));
+            if (NC == 8) m = max_nan(m, max_nan(max_nan(s[NC - 4], s[NC - 3]), max_nan(s[NC - 2], s[NC - 1])));
+            if (!(m < tau) && tau != NumTraits<T>::inf()) {
+                row_slow<T, C>(P, tau, row, tile_u0 + row, item0 + lx * 4, item0 + BN, s[0], s[1], s[2], s[3]);
+                if (NC == 8)
+                    row_slow<T, C>(P, tau, row, tile_u0 + row, item0 + 64 + lx * 4, item0 + BN, s[NC - 4], s[NC - 3], s[NC - 2], s[NC - 1]);
+                inserted = true;
             }
             if (AUC) {
-                // count: rows wrow0 + 8h + b, b = 2*q4 + ly; this lane owns held-out slots lx, lx+16, ...
-                __syncwarp();
-#pragma unroll
-                for (int q4 = 0; q4 < 4; q4++) {
-                    const int b = 2 * q4 + ly;
-                    const int q = h * 4 + q4;                  // index into pj0 / cnt0 (row wrow0 + 8h + b)
-                    const T* src = blk + (size_t)b * BN;
-                    const T pj = pj0[q];
-                    unsigned c0 = 0;
-#pragma unroll 8
-                    for (int x = 0; x < BN; x += VEC) {
-                        T v[VEC];
-                        lds_vec(src + x, v);
-#pragma unroll
-                        for (int e = 0; e < VEC; e++) c0 += (v[e] > pj) ? 1u : 0u;
-                    }
-                    cnt0[q] += c0;
-                    // rows with more than 16 held-out items: remaining slots straight to global counters
-                    const int row = wrow0 + 8 * h + b;
-                    if (rs->tau[row] != NumTraits<T>::inf()) {
-                        const int u = P.user0 + tile_u0 + row;
-                        const int tp0 = P.tep[u], npos = P.tep[u + 1] - tp0;
-                        for (int j = lx + 16; j < npos; j += 16) {
-                            const T pjj = P.pos_sorted[tp0 + j];
-                            unsigned cj = 0;
-                            for (int x = 0; x < BN; x++) cj += (src[x] > pjj) ? 1u : 0u;
-                            if (cj) atomicAdd(&P.auc_cnt[(size_t)tp0 + j], cj);
-                        }
+                if (tile_has_padding || rs->nxt_train[row] < item0 + BN) {
+                    remask |= 1u << i;               // some of these are not candidates: exact minimum below
+                } else {
+                    T mn = fmin(fmin(s[0], s[1]), fmin(s[2], s[3]));      // fmin ignores NaN
+                    if (NC == 8) mn = fmin(mn, fmin(fmin(s[NC - 4], s[NC - 3]), fmin(s[NC - 2], s[NC - 1])));
+                    rowmin[i] = fmin(rowmin[i], mn);
+                }
+                T* dst = blk + (size_t)row_l * BN + lx * 4;
+                sts4(dst, &s[0]);
+                if (NC == 8) sts4(dst + 64, &s[NC - 4]);
+            }
+        }
+        __syncwarp();
+
+        if (AUC) {
+            // mask (with NaN: never above a threshold, ignored by fmin) what is not a candidate in the
+            // staged block: train items of rows whose train row intersects this tile, and the padding
+            // columns of the last tile (lane r <-> row r)
+            if (lane < 16) {
+                const int row = wrow0 + lane;
+                T* dst = blk + (size_t)lane * BN;
+                if (rs->nxt_train[row] < item0 + BN) {
+                    const int end = rs->end_train[row];
+                    for (int c = rs->cur_train[row]; c < end; c++) {
+                        const int item = P.tri[c];
+                        if (item >= item0 + BN) break;
+                        dst[item - item0] = NumTraits<T>::nan();
                     }
                 }
-                __syncwarp();
+                if (tile_has_padding)
+                    for (int x = (P.n > item0 ? P.n - item0 : 0); x < BN; x++) dst[x] = NumTraits<T>::nan();
             }
+            __syncwarp();
+            if (__any_sync(FULL, remask != 0)) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (remask & (1u << i)) {
+                        const int row_l = ly * 4 + (i & 3) + (i >> 2) * 8;
+                        const T* src = blk + (size_t)row_l * BN + lx * 4;
+                        T mn = NumTraits<T>::inf();
+#pragma unroll
+                        for (int c = 0; c < NC; c++) {
+                            const T v = src[(c & 3) + (c >> 2) * 64];
+                            mn = fmin(mn, v);                             // masked entries are NaN: ignored
+                        }
+                        rowmin[i] = fmin(rowmin[i], mn);
+                    }
+                }
+            }
+            // count: lane (ly, lx) owns held-out slots lx, lx+16, ... of rows 2*rp + ly
+            for (int rp = 0; rp < 8; rp++) {
+                const int row_l = 2 * rp + ly;
+                const int row = wrow0 + row_l;
+                const T* src = blk + (size_t)row_l * BN;
+                {
+                    const T thr[1] = {pj_s[row * 16 + lx]};
+                    unsigned c[1] = {0};
+                    count_above<T, 1>(src, thr, c);
+                    cj_s[row * 16 + lx] += c[0];
+                }
+                // rows with more than 16 held-out items: further slots, 4 at a time, counters in global memory
+                const int npos = rs->npos[row];
+                if (npos > 16) {
+                    const int tp0 = rs->tp0[row];
+                    for (int j0 = 16 + lx; j0 < npos; j0 += 64) {
+                        T thr[4];
+                        unsigned c[4] = {0, 0, 0, 0};
+#pragma unroll
+                        for (int q = 0; q < 4; q++) thr[q] = (j0 + 16 * q < npos) ? P.pos_sorted[tp0 + j0 + 16 * q] : NumTraits<T>::inf();
+                        count_above<T, 4>(src, thr, c);
+#pragma unroll
+                        for (int q = 0; q < 4; q++)
+                            if (c[q]) P.auc_cnt[(size_t)tp0 + j0 + 16 * q] += c[q];     // single owner: plain read-modify-write
+                    }
+                }
+            }
+            __syncwarp();
         }
 
         // advance the train cursors of the warp's rows past this tile (lanes 0..15, rare)
-        __syncwarp();
         if (lane < 16) {
             const int row = wrow0 + lane;
             int nxt = rs->nxt_train[row];
@@ -617,9 +739,8 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
                 rs->nxt_train[row] = cur < end ? nxt : INT_MAX;
             }
         }
-        // re-sort the buffers of this warp that passed the trigger (rare after the first few tiles)
+        // cut back the buffers of this warp that passed the trigger (rare after the first few tiles)
         if (__any_sync(FULL, inserted)) {
-            __syncwarp();
             const int nv_l = lane < 16 ? rs->cnt[wrow0 + lane] : 0;
             unsigned need = __ballot_sync(FULL, nv_l > C - BN);
             while (need) {
@@ -633,7 +754,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
         __syncwarp();
     }
 
-    // ---- final ranking of the warp's users ----
+    // ---- leave the best min(cnt, K) candidates of every user at the head of its buffer ----
     for (int r = 0; r < 16; r++) {
         const int row = wrow0 + r;
         const int ul = tile_u0 + row;
@@ -647,25 +768,46 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
         }
     }
     if (AUC) {
-#pragma unroll
-        for (int q = 0; q < 8; q++) {
-            // counters: row wrow0 + 8*(q>>2) + 2*(q&3) + ly, slot lx
-            const int row = wrow0 + 8 * (q >> 2) + 2 * (q & 3) + ly;
-            const int ul = tile_u0 + row;
-            if (ul < P.mb && P.ustatus[P.user0 + ul] == 0) {
-                const int u = P.user0 + ul;
-                const int tp0 = P.tep[u], npos = P.tep[u + 1] - tp0;
-                if (lx < npos) P.auc_cnt[(size_t)tp0 + lx] = cnt0[q];
-            }
+        for (int e = lane; e < 16 * 16; e += 32) {
+            const int row = wrow0 + (e >> 4), j = e & 15;
+            if (j < rs->npos[row]) P.auc_cnt[(size_t)rs->tp0[row] + j] = cj_s[row * 16 + j];
         }
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-            // smallest candidate score: thread row i = CTA row wrow0 + ly*4 + (i&3) + (i>>2)*8
             const int row = wrow0 + ly * 4 + (i & 3) + (i >> 2) * 8;
             const int ul = tile_u0 + row;
-            if (ul < P.mb && rowmin[i] != NumTraits<T>::inf())
+            if (ul < P.mb && rs->npos[row] > 0 && rowmin[i] != NumTraits<T>::inf())
                 atomicMin(&P.umin[P.user0 + ul], NumTraits<T>::orderable(rowmin[i]));
         }
+    }
+}
+
+// One warp per user: order the (<= K <= 32*E) candidates score_select_kernel left at the head of the
+// user's buffer (score descending, ties by ascending item id).
+template <typename T, int E>
+__global__ void rank_topk_kernel(T* __restrict__ cand_score, int* __restrict__ cand_item, const int* __restrict__ cand_count,
+                                 const int C, const int mb)
+{
+    const int lane = threadIdx.x & 31;
+    const int ul = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ul >= mb) return;
+    const int nv = cand_count[ul];
+    T* cs = cand_score + (size_t)ul * C;
+    int* ci = cand_item + (size_t)ul * C;
+    T s[E];
+    int it[E];
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int idx = e * 32 + lane;
+        const bool v = idx < nv;
+        s[e] = v ? cs[idx] : -NumTraits<T>::inf();
+        it[e] = v ? ci[idx] : INT_MAX;
+    }
+    warp_sort_ranked<T, E>(s, it, lane);
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int idx = e * 32 + lane;
+        if (idx < nv) { cs[idx] = s[e]; ci[idx] = it[e]; }
     }
 }
 

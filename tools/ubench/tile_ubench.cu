@@ -88,6 +88,45 @@ __global__ void __launch_bounds__(256, MINB) k_tile(float* out, const float* in,
     if (s == 123456789.f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
+
+// 16 warps x (4 users x 8 items) per thread: warp owns 8 rows x 128 cols
+template <int MINB>
+__global__ void __launch_bounds__(512, MINB) k_tile48(float* out, const float* in, int iters)
+{
+    __shared__ __align__(16) float As[BK * BM];
+    __shared__ __align__(16) float Bs[BK * BN];
+    for (int i = threadIdx.x; i < BK * BM; i += 512) { As[i] = in[i]; Bs[i] = in[BK * BM + i]; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int row_base = warp * 8 + (lane >> 4) * 4;
+    const int col_base = (lane & 15) * 4;
+    u64 acc[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = 0ull;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int kk = 0; kk < BK; kk++) {
+            const float4 a4 = *(const float4*)&As[kk * BM + row_base];
+            const ulonglong2 b0 = *(const ulonglong2*)&Bs[kk * BN + col_base];
+            const ulonglong2 b1 = *(const ulonglong2*)&Bs[kk * BN + col_base + 64];
+            const float a[4] = {a4.x, a4.y, a4.z, a4.w};
+            const u64 b2[4] = {b0.x, b0.y, b1.x, b1.y};
+#pragma unroll
+            for (int c = 0; c < 4; c++)
+#pragma unroll
+                for (int r = 0; r < 4; r++) fma2(acc[r][c], pack2(a[r], a[r]), b2[c]);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) { float lo, hi; unpack2(acc[r][c], lo, hi); s += lo + hi; }
+    if (s == 123456789.f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 template <typename F>
 double time_ms(F launch)
 {
@@ -127,5 +166,11 @@ int main()
     run<1, 2>("FFMA2 8x8 pairs along c, r outer", out, in, nsm);
     run<2, 1>("FFMA2 8x8 pairs along c, c outer", out, in, nsm);
     run<2, 2>("FFMA2 8x8 pairs along c, c outer", out, in, nsm);
+    {
+        const int iters = 4000;
+        double ms = time_ms([&] { k_tile48<1><<<nsm, 512>>>(out, in, iters); });
+        CHECK(cudaGetLastError());
+        printf("%-44s CTAs/SM=%d : %7.2f TFLOP/s\n", "FFMA2 4x8 per thread, 16 warps", 1, (double)nsm * 512 * iters * BK * 32 * 2 / ms / 1e9);
+    }
     return 0;
 }
