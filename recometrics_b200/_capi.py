@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librecometrics_b200.so")
+# RMB200_LIB: developer override used by tools/variants.sh to time alternative builds of the same library
+LIB_PATH = os.environ.get("RMB200_LIB") or os.path.join(_HERE, "librecometrics_b200.so")
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_INTERRUPTED, ERR_UNSUPPORTED = range(7)
 MAX_K = 384

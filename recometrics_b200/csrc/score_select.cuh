@@ -40,6 +40,17 @@
 #include <limits.h>
 #include <string.h>
 
+// build-time tuning knobs of the FMA loop (tools/variants.sh times the alternatives)
+#ifndef RMB_SWPIPE
+#define RMB_SWPIPE 0        // 1: explicit register double buffering of the operand fragments
+#endif
+#ifndef RMB_UNROLL
+#define RMB_UNROLL 8        // factors per unrolled block of the FMA loop (multiple of KPAD)
+#endif
+#ifndef RMB_EARLYTRY
+#define RMB_EARLYTRY 0      // 1: probe the next stage's mbarrier one block before it is needed
+#endif
+
 namespace rmb {
 
 constexpr int BM = 128;             // users per CTA tile (items per tile: NumTraits<T>::BN)
@@ -208,6 +219,17 @@ __device__ __forceinline__ void mbar_wait(const unsigned bar, const unsigned par
             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
     } while (!ok);
 }
+// non-blocking probe (the result arrives ~90 cycles later: issue it early, test it late)
+__device__ __forceinline__ unsigned mbar_try(const unsigned bar, const unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok;
+}
 // global -> shared bulk copy executed by the TMA unit, completion counted on an mbarrier
 __device__ __forceinline__ void tma_bulk_g2s(const unsigned dst, const void* src, const unsigned bytes, const unsigned bar)
 {
@@ -277,19 +299,24 @@ template <> struct MicroTile<float> {
 #pragma unroll
             for (int q = 0; q < 4; q++) acc[i][q] = 0ull;
     }
+    struct Frag { float a[8]; u64 b[4]; };
     // sA: the warp's 16 user values of factor k; sB: the tile's 128 item values of factor k
-    __device__ __forceinline__ void step(const float* __restrict__ sA, const float* __restrict__ sB, const int ly, const int lx)
+    __device__ __forceinline__ static void load(Frag& f, const float* __restrict__ sA, const float* __restrict__ sB, const int ly, const int lx)
     {
         const float4 a0 = *reinterpret_cast<const float4*>(sA + ly * 4);
         const float4 a1 = *reinterpret_cast<const float4*>(sA + 8 + ly * 4);
         const ulonglong2 b0 = *reinterpret_cast<const ulonglong2*>(sB + lx * 4);
         const ulonglong2 b1 = *reinterpret_cast<const ulonglong2*>(sB + 64 + lx * 4);
-        const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-        const u64 b[4] = {b0.x, b0.y, b1.x, b1.y};
+        f.a[0] = a0.x; f.a[1] = a0.y; f.a[2] = a0.z; f.a[3] = a0.w;
+        f.a[4] = a1.x; f.a[5] = a1.y; f.a[6] = a1.z; f.a[7] = a1.w;
+        f.b[0] = b0.x; f.b[1] = b0.y; f.b[2] = b1.x; f.b[3] = b1.y;
+    }
+    __device__ __forceinline__ void compute(const Frag& f)
+    {
 #pragma unroll
         for (int q = 0; q < 4; q++)
 #pragma unroll
-            for (int i = 0; i < 8; i++) fma2(acc[i][q], pack2(a[i], a[i]), b[q]);
+            for (int i = 0; i < 8; i++) fma2(acc[i][q], pack2(f.a[i], f.a[i]), f.b[q]);
     }
     __device__ __forceinline__ void row(const int i, float (&s)[8]) const
     {
@@ -308,25 +335,28 @@ template <> struct MicroTile<double> {
 #pragma unroll
             for (int c = 0; c < 4; c++) acc[i][c] = 0.;
     }
-    __device__ __forceinline__ void step(const double* __restrict__ sA, const double* __restrict__ sB, const int ly, const int lx)
+    struct Frag { double a[8]; double b[4]; };
+    __device__ __forceinline__ static void load(Frag& f, const double* __restrict__ sA, const double* __restrict__ sB, const int ly, const int lx)
     {
-        double a[8], b[4];
 #pragma unroll
         for (int g = 0; g < 2; g++)
 #pragma unroll
             for (int h = 0; h < 2; h++) {
                 const double2 va = *reinterpret_cast<const double2*>(sA + g * 8 + ly * 4 + h * 2);
-                a[g * 4 + h * 2] = va.x; a[g * 4 + h * 2 + 1] = va.y;
+                f.a[g * 4 + h * 2] = va.x; f.a[g * 4 + h * 2 + 1] = va.y;
             }
 #pragma unroll
         for (int h = 0; h < 2; h++) {
             const double2 vb = *reinterpret_cast<const double2*>(sB + lx * 4 + h * 2);
-            b[h * 2] = vb.x; b[h * 2 + 1] = vb.y;
+            f.b[h * 2] = vb.x; f.b[h * 2 + 1] = vb.y;
         }
+    }
+    __device__ __forceinline__ void compute(const Frag& f)
+    {
 #pragma unroll
         for (int c = 0; c < 4; c++)
 #pragma unroll
-            for (int i = 0; i < 8; i++) acc[i][c] = ::fma(a[i], b[c], acc[i][c]);
+            for (int i = 0; i < 8; i++) acc[i][c] = ::fma(f.a[i], f.b[c], acc[i][c]);
     }
     __device__ __forceinline__ void row(const int i, double (&s)[4]) const
     {
@@ -451,34 +481,36 @@ __device__ __forceinline__ bool in_train_segment(const int* __restrict__ tri, in
 }
 
 // Slow path of the selection filter (taken by ~K ln(n/K) scores per user): candidate checks, then
-// append to the user's buffer.
-template <typename T, int C>
-__device__ __forceinline__ void insert_candidate(const ScoreSelectParams<T>& P, RowState<T>* rs, const T s, const int row,
-                                                 const int ulocal, const int item, const int item_end)
+// append to the user's buffer (cs / ci = the row's candidate buffer).  Everything arrives by value:
+// the kernel parameters live in constant memory, which an out-of-line function could only reach
+// through a generic pointer.
+template <typename T>
+__device__ __forceinline__ void insert_candidate(RowState<T>* rs, T* cs, int* ci, const int* __restrict__ tri, const int n,
+                                                 const T s, const int row, const int item, const int item_end)
 {
-    if (item >= P.n) return;                                    // padding column
+    if (item >= n) return;                                      // padding column
     if (rs->nxt_train[row] < item_end &&                        // the train row intersects this tile
-        in_train_segment(P.tri, rs->cur_train[row], rs->end_train[row], item)) return;   // not a candidate
+        in_train_segment(tri, rs->cur_train[row], rs->end_train[row], item)) return;   // not a candidate
     if (s != s) { rs->nan[row] = 1; return; }                   // NaN candidate score => NaN row
     const int slot = atomicAdd(&rs->cnt[row], 1);
     // slot < C always: the buffer holds <= C-BN entries when a tile starts and a tile adds <= BN
-    const size_t base = (size_t)ulocal * C;
-    P.cand_score[base + slot] = s;
-    P.cand_item[base + slot] = item;
+    cs[slot] = s;
+    ci[slot] = item;
 }
 
 // A thread's scores of one user row in one item tile, at least one of which is not below tau.
-// item_lo = id of the thread's first column; columns c >= 4 sit 64 items further.
-template <typename T, int C>
-__device__ __noinline__ void row_slow(const ScoreSelectParams<T>& P, const T tau, const int row, const int ulocal,
+// item_lo = id of the first of the four columns.
+template <typename T>
+__device__ __noinline__ void row_slow(T* cs, int* ci, const int* __restrict__ tri, const int n, const T tau, const int row,
                                       const int item_lo, const int item_end,
                                       const T s0, const T s1, const T s2, const T s3)
 {
     RowState<T>* rs = row_state<T>();
-    if (!(s0 < tau)) insert_candidate<T, C>(P, rs, s0, row, ulocal, item_lo, item_end);
-    if (!(s1 < tau)) insert_candidate<T, C>(P, rs, s1, row, ulocal, item_lo + 1, item_end);
-    if (!(s2 < tau)) insert_candidate<T, C>(P, rs, s2, row, ulocal, item_lo + 2, item_end);
-    if (!(s3 < tau)) insert_candidate<T, C>(P, rs, s3, row, ulocal, item_lo + 3, item_end);
+    if (tau == NumTraits<T>::inf()) return;                     // row is not ranked (padding / NaN-row user)
+    if (!(s0 < tau)) insert_candidate<T>(rs, cs, ci, tri, n, s0, row, item_lo, item_end);
+    if (!(s1 < tau)) insert_candidate<T>(rs, cs, ci, tri, n, s1, row, item_lo + 1, item_end);
+    if (!(s2 < tau)) insert_candidate<T>(rs, cs, ci, tri, n, s2, row, item_lo + 2, item_end);
+    if (!(s3 < tau)) insert_candidate<T>(rs, cs, ci, tri, n, s3, row, item_lo + 3, item_end);
 }
 
 // number of a / b / c / d strictly above p, subtracted as 0 / -1 masks (SASS: FSET + IADD3)
@@ -600,21 +632,48 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
     }
 
     MicroTile<T> mt;
+    typename MicroTile<T>::Frag frag[2];            // operand registers, double buffered across k
     int it = 0;
+    unsigned ready = mbar_try(bar_full, 0);         // probe of the stage about to be consumed
     for (int tile = 0; tile < NT; tile++) {
         const int item0 = tile * BN;
         mt.zero();
         for (int kc = 0; kc < KC; kc++, it++) {
             const int s = it % S;
-            mbar_wait(bar_full + 8 * s, (it / S) & 1);
+            if (!ready) mbar_wait(bar_full + 8 * s, (it / S) & 1);
             const int k0 = kc * BK;
             const int kcount = (P.p_pad - k0) < BK ? (P.p_pad - k0) : BK;
             const T* sA = As + (size_t)s * BK * BM + wrow0;
             const T* sB = Bs + (size_t)s * BK * BN;
+#if RMB_SWPIPE
+            MicroTile<T>::load(frag[0], sA, sB, ly, lx);
             for (int kk0 = 0; kk0 < kcount; kk0 += KPAD) {
+                if (kk0 + KPAD >= kcount) {          // last block of the stage: probe the next stage now
+                    const int nit = it + 1;
+                    ready = (nit < total) ? mbar_try(bar_full + 8 * (nit % S), (nit / S) & 1) : 1u;
+                }
 #pragma unroll
-                for (int kk = 0; kk < KPAD; kk++) mt.step(sA + (kk0 + kk) * BM, sB + (kk0 + kk) * BN, ly, lx);
+                for (int kk = 0; kk < KPAD; kk++) {
+                    if (kk + 1 < KPAD || kk0 + KPAD < kcount)
+                        MicroTile<T>::load(frag[(kk + 1) & 1], sA + (kk0 + kk + 1) * BM, sB + (kk0 + kk + 1) * BN, ly, lx);
+                    mt.compute(frag[kk & 1]);
+                }
             }
+#else
+            for (int kk0 = 0; kk0 < kcount; kk0 += RMB_UNROLL) {
+                if (RMB_EARLYTRY && kk0 + RMB_UNROLL >= kcount) {   // last block of the stage: probe the next stage now
+                    const int nit = it + 1;
+                    ready = (nit < total) ? mbar_try(bar_full + 8 * (nit % S), (nit / S) & 1) : 1u;
+                }
+#pragma unroll
+                for (int kk = 0; kk < RMB_UNROLL; kk++) {
+                    if (RMB_UNROLL > KPAD && kk0 + kk >= kcount) break;     // only the tail chunk of a k that is not a multiple of the unroll
+                    MicroTile<T>::load(frag[0], sA + (kk0 + kk) * BM, sB + (kk0 + kk) * BN, ly, lx);
+                    mt.compute(frag[0]);
+                }
+            }
+            if (!RMB_EARLYTRY) ready = 0;
+#endif
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_empty + 8 * s);
         }
@@ -641,10 +700,12 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
             const T tau = rs->tau[row];
             T m = max_nan(max_nan(s[0], s[1]), max_nan(s[2], s[3]));
             if (NC == 8) m = max_nan(m, max_nan(max_nan(s[NC - 4], s[NC - 3]), max_nan(s[NC - 2], s[NC - 1])));
-            if (!(m < tau) && tau != NumTraits<T>::inf()) {
-                row_slow<T, C>(P, tau, row, tile_u0 + row, item0 + lx * 4, item0 + BN, s[0], s[1], s[2], s[3]);
+            if (!(m < tau)) {
+                T* cs = P.cand_score + (size_t)(tile_u0 + row) * C;
+                int* ci = P.cand_item + (size_t)(tile_u0 + row) * C;
+                row_slow<T>(cs, ci, P.tri, P.n, tau, row, item0 + lx * 4, item0 + BN, s[0], s[1], s[2], s[3]);
                 if (NC == 8)
-                    row_slow<T, C>(P, tau, row, tile_u0 + row, item0 + 64 + lx * 4, item0 + BN, s[NC - 4], s[NC - 3], s[NC - 2], s[NC - 1]);
+                    row_slow<T>(cs, ci, P.tri, P.n, tau, row, item0 + 64 + lx * 4, item0 + BN, s[NC - 4], s[NC - 3], s[NC - 2], s[NC - 1]);
                 inserted = true;
             }
             if (AUC) {
