@@ -67,6 +67,7 @@ typedef struct rmb200_timing {
     double d2h_ms;          /* device->host result copies                                       */
     int64_t kernel_launches;/* kernels of this library launched by the call                     */
     int64_t h2d_bytes, d2h_bytes;
+    int64_t scoring_path;   /* which scoring kernel ran: 1 = FMA tiles, 2 = tensor-core filter + exact re-score */
 } rmb200_timing_t;
 
 /* Optional extension block (pass NULL for reference behaviour).  Zero-initialise, then set
@@ -88,6 +89,11 @@ typedef struct rmb200_extra {
     int32_t *status;            /* optional out [m]: 0 computed, 1 not eligible (hpp:439-448),         */
                                 /* 2 NaN by the cand<=K rule (hpp:485-486), 3 NaN by score validity     */
     rmb200_timing_t *timing;    /* optional out                                                        */
+    int32_t scoring_path;       /* 0 = automatic; 1 = FP32/FP64 FMA tiles for every score; 2 = tensor-core     */
+                                /* (bf16 tcgen05) candidate filter + exact FMA re-scoring of the survivors:    */
+                                /* same top-K, same scores; not available with ROC/PR-AUC (rank counting).     */
+                                /* Env RMB200_PATH=fma|tensor overrides 0.                                     */
+    int32_t reserved_;
 } rmb200_extra_t;
 
 /* Drop-in for calc_metrics_float (src/recometrics_signatures.hpp:73-98).  Returns rmb200_status. */

@@ -32,6 +32,7 @@ class Timing(ctypes.Structure):
         ("total_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double), ("prep_ms", ctypes.c_double),
         ("score_select_ms", ctypes.c_double), ("metrics_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
         ("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+        ("scoring_path", ctypes.c_int64),
     ]
 
     def as_dict(self):
@@ -46,6 +47,7 @@ class Extra(ctypes.Structure):
         ("topk_items", ctypes.c_void_p), ("topk_scores", ctypes.c_void_p),
         ("pos_rank", ctypes.c_void_p), ("status", ctypes.c_void_p),
         ("timing", ctypes.POINTER(Timing)),
+        ("scoring_path", ctypes.c_int32), ("reserved_", ctypes.c_int32),
     ]
 
 
@@ -151,7 +153,7 @@ def calc_metrics(dtype, A, lda, B, ldb, m, n, k, trp, tri, tep, tei, tev, k_metr
 
 
 def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, strict_min_pos_test=False,
-               topk_items=None, topk_scores=None, pos_rank=None, status=None, timing=None):
+               topk_items=None, topk_scores=None, pos_rank=None, status=None, timing=None, scoring_path=0):
     ex = Extra()
     ex.struct_size = ctypes.sizeof(Extra)
     ex.device = int(device)
@@ -159,6 +161,7 @@ def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, stri
     ex.user_end = int(user_end)
     ex.inputs_on_device = int(bool(inputs_on_device))
     ex.strict_min_pos_test = int(bool(strict_min_pos_test))
+    ex.scoring_path = {"auto": 0, "fma": 1, "tensor": 2}.get(scoring_path, scoring_path)
     ex.topk_items = _vp(topk_items)
     ex.topk_scores = _vp(topk_scores)
     ex.pos_rank = _vp(pos_rank)

@@ -22,6 +22,7 @@
 #include "metrics.cuh"
 #include "prep.cuh"
 #include "score_select.cuh"
+#include "filter_select.cuh"
 
 namespace {
 
@@ -139,6 +140,25 @@ cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool 
                : launch_score_select_inst<T, 1024, false>(P, n_user_tiles, st);
 }
 
+template <typename T, int C>
+cudaError_t launch_filter_inst(const rmb::FilterParams<T>& P, int n_user_tiles, cudaStream_t st)
+{
+    auto kern = rmb::filter_select_kernel<T, C>;
+    const size_t smem = rmb::filter_smem_bytes(P.KB, P.stages, P.p_pad, sizeof(T));
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    kern<<<n_user_tiles, rmb::F_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
+}
+
+template <typename T>
+cudaError_t launch_filter_select(const rmb::FilterParams<T>& P, int C, int n_user_tiles, cudaStream_t st)
+{
+    if (C == 256) return launch_filter_inst<T, 256>(P, n_user_tiles, st);
+    if (C == 512) return launch_filter_inst<T, 512>(P, n_user_tiles, st);
+    return launch_filter_inst<T, 1024>(P, n_user_tiles, st);
+}
+
 // order the <= K survivors of every user (warp per user, bitonic network sized to K)
 template <typename T>
 cudaError_t launch_rank_topk(T* cs, int* ci, const int* cc, int C, int nb, int K, cudaStream_t st)
@@ -232,6 +252,23 @@ int run_call(const CallArgs<T>& a)
     const int n_pad = round_up(a.n, BN);
     const size_t rs = a.cumulative ? (size_t)K : 1;
 
+    // ---- which scoring path: tensor-core filter + exact re-scoring (top-K only), or FMA tiles ----
+    int path_req = ex ? ex->scoring_path : 0;                       // 0 auto, 1 fma, 2 tensor
+    if (path_req == 0) if (const char* env = std::getenv("RMB200_PATH")) {
+        if (!std::strcmp(env, "fma")) path_req = 1; else if (!std::strcmp(env, "tensor")) path_req = 2;
+    }
+    const int KB = round_up(a.k + (a.bias ? 1 : 0), 16);            // bf16 factors per row (bias = one more factor)
+    int f_stages = 0;
+    {
+        const long long tile = (long long)KB * 256, budget = 225 * 1024 - (long long)F_EPI_WARPS * p_pad * (long long)sizeof(T) - 2048;
+        f_stages = (int)(budget / tile) - 1;
+        if (f_stages > F_MAX_STAGES) f_stages = F_MAX_STAGES;
+    }
+    const bool tensor_ok = !count_ranks && f_stages >= 2;
+    if (path_req == 2 && !tensor_ok) { set_err("unsupported", "scoring_path=tensor needs no ROC/PR-AUC (rank counting) and k <= ~256"); return RMB200_ERR_UNSUPPORTED; }
+    const bool use_tensor = tensor_ok && path_req != 1;
+    tm.scoring_path = use_tensor ? 2 : 1;
+
     // ---- CSR slices of users [ub, ue), index pointers re-based to the slice ----
     int lo_hi[4];   // trp[ub], trp[ue], tep[ub], tep[ue]
     if (!on_dev) {
@@ -283,25 +320,25 @@ int run_call(const CallArgs<T>& a)
     const int* trp_d = d_trp.as<int>();
     const int* tep_d = d_tep.as<int>();
 
-    // ---- item factors: k-major, zero padded (+ biases) ----
-    DevBuf d_Bt, d_bias;
-    CK(d_Bt.alloc((size_t)p_pad * n_pad * sizeof(T)));
-    {
-        DevBuf d_Brow;
-        const T* Bsrc = nullptr; size_t Bld = 0;
-        if (!on_dev) {
-            CK(d_Brow.alloc((size_t)a.n * a.k * sizeof(T)));
-            pt.start();
-            int rc = stage_rows<T>(a.B, a.ldb, a.n, a.k, false, d_Brow, &Bsrc, &Bld, st, tm);
-            if (rc) return rc;
-            pt.stop(tm.h2d_ms);
-        } else { Bsrc = a.B; Bld = a.ldb; }
+    // ---- item factors: row-major staging copy, then the operand image of the chosen path ----
+    DevBuf d_Bt, d_bias, d_Brow, d_Bb, d_maxbn;
+    const T* Bsrc = nullptr; size_t Bld = 0;
+    if (!on_dev) {
+        CK(d_Brow.alloc((size_t)a.n * a.k * sizeof(T)));
+        pt.start();
+        int rc = stage_rows<T>(a.B, a.ldb, a.n, a.k, false, d_Brow, &Bsrc, &Bld, st, tm);
+        if (rc) return rc;
+        pt.stop(tm.h2d_ms);
+    } else { Bsrc = a.B; Bld = a.ldb; }
+    if (!use_tensor) {
+        CK(d_Bt.alloc((size_t)p_pad * n_pad * sizeof(T)));
         pt.start();
         dim3 grid(n_pad / 32, (p_pad + 31) / 32), block(32, 8);
         pack_tiles_kernel<T, BN><<<grid, block, 0, st>>>(Bsrc, Bld, a.n, a.k, d_Bt.as<T>(), n_pad, p_pad);
         CK(cudaGetLastError());
         tm.kernel_launches++;
-        pt.stop(tm.prep_ms);   // (synchronises: d_Brow may now be freed)
+        pt.stop(tm.prep_ms);   // (synchronises)
+        d_Brow.release();      // the FMA path reads only the tiled copy
     }
     const T* bias_d = nullptr;
     if (a.bias) {
@@ -322,6 +359,21 @@ int run_call(const CallArgs<T>& a)
         tm.kernel_launches++;
         pt.stop(tm.prep_ms);
         bias_d = d_bias.as<T>();
+    }
+    const int n_pad128 = round_up(a.n, 128);
+    if (use_tensor) {
+        CK(d_Bb.alloc((size_t)n_pad128 * KB * sizeof(__nv_bfloat16)));
+        CK(d_maxbn.alloc(sizeof(unsigned)));
+        pt.start();
+        CK(cudaMemsetAsync(d_maxbn.p, 0, sizeof(unsigned), st));
+        const long long total = (long long)n_pad128 * (KB / 8);
+        pack_bf16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0,
+                                                                             d_Bb.as<__nv_bfloat16>(), n_pad128, KB);
+        CK(cudaGetLastError());
+        row_norm_kernel<T><<<(a.n + 7) / 8, 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0, nullptr, d_maxbn.as<unsigned>());
+        CK(cudaGetLastError());
+        tm.kernel_launches += 2;
+        pt.stop(tm.prep_ms);
     }
 
     // ---- per-user state ----
@@ -373,8 +425,12 @@ int run_call(const CallArgs<T>& a)
     if (const char* env = std::getenv("RMB200_BATCH_USERS")) { const int v = std::atoi(env); if (v > 0) UB = round_up(v, BM); }
     if (UB > round_up(mr, BM)) UB = round_up(mr, BM);
 
-    DevBuf d_At, d_Arow, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out;
+    DevBuf d_At, d_Arow, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
     CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
+    if (use_tensor) {
+        CK(d_Ab.alloc((size_t)UB * KB * sizeof(__nv_bfloat16)));
+        CK(d_anorm.alloc((size_t)UB * sizeof(float)));
+    }
     if (!on_dev) CK(d_Arow.alloc((size_t)UB * a.k * sizeof(T)));
     CK(d_cs.alloc((size_t)UB * C * sizeof(T)));
     CK(d_ci.alloc((size_t)UB * C * sizeof(int)));
@@ -419,6 +475,31 @@ int run_call(const CallArgs<T>& a)
         }
         pt.stop(tm.prep_ms);
 
+        if (use_tensor) {
+            // bf16 operand image + norms of the batch's users, then the tensor-core filter
+            pt.start();
+            const long long total = (long long)nb_pad * (KB / 8);
+            pack_bf16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
+                                                                                 d_Ab.as<__nv_bfloat16>(), nb_pad, KB);
+            CK(cudaGetLastError());
+            row_norm_kernel<T><<<(nb + 7) / 8, 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0, d_anorm.as<float>(), nullptr);
+            CK(cudaGetLastError());
+            tm.kernel_launches += 2;
+            pt.stop(tm.prep_ms);
+            pt.start();
+            FilterParams<T> fp;
+            fp.Ab = d_Ab.as<__nv_bfloat16>(); fp.Bb = d_Bb.as<__nv_bfloat16>(); fp.KB = KB; fp.stages = f_stages;
+            fp.n = a.n; fp.mb = nb; fp.user0 = b0;
+            fp.At = d_At.as<T>(); fp.p_pad = p_pad; fp.p = a.k; fp.Brow = Bsrc; fp.ldb = Bld; fp.bias = bias_d;
+            fp.anorm = d_anorm.as<float>(); fp.maxbn = d_maxbn.as<unsigned>();
+            fp.trp = trp_d; fp.tri = tri_d; fp.ustatus = d_status.as<int>();
+            fp.cand_score = d_cs.as<T>(); fp.cand_item = d_ci.as<int>(); fp.cand_count = d_cc.as<int>();
+            fp.uflags = d_flags.as<int>(); fp.K = K;
+            CK(launch_filter_select<T>(fp, C, nb_pad / BM, st));
+            CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
+            tm.kernel_launches += 2;
+            pt.stop(tm.score_select_ms);
+        } else {
         // fused score / exclude / select (/ rank counting)
         pt.start();
         {
@@ -436,6 +517,7 @@ int run_call(const CallArgs<T>& a)
             tm.kernel_launches += 2;
         }
         pt.stop(tm.score_select_ms);
+        }
 
         // per-user metrics
         pt.start();

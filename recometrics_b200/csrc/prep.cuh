@@ -5,6 +5,7 @@
 //   score_entries_kernel   scores of the held-out (test) items, same FMA order as the tile kernel
 //   sort_positives_kernel  per-user ascending order of those scores (rank by counting)
 #pragma once
+#include <cuda_bf16.h>
 #include "score_select.cuh"
 
 namespace rmb {
@@ -119,6 +120,60 @@ __global__ void sort_positives_kernel(const int user0, const int mb, const int* 
             pos_sorted[e0 + rank] = v;
             pos_perm[e0 + rank] = e;
         }
+    }
+}
+
+
+// bf16 operand image for the tensor-core filter (filter_select.cuh): 128-row tiles, [tile][k/8][row][8 bf16],
+// KB factors per row (multiple of 16).  Column `cols` holds extra[row] (the item bias) or, for the user side,
+// 1.0 (ones_col) -- the bias travels as one more factor, as in recometrics/__init__.py:548-551; the rest is 0.
+// One thread per (row, 8-factor chunk): consecutive threads write consecutive 16-byte rows of a chunk.
+template <typename T>
+__global__ void pack_bf16_kernel(const T* __restrict__ src, const size_t ld, const int rows, const int cols,
+                                 const T* __restrict__ extra, const int ones_col,
+                                 __nv_bfloat16* __restrict__ dst, const int rows_pad, const int KB)
+{
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int chunks = KB / 8;
+    const long long total = (long long)rows_pad * chunks;
+    if (idx >= total) return;
+    const int tile = (int)(idx / ((long long)chunks * 128));
+    const int rem = (int)(idx % ((long long)chunks * 128));
+    const int c = rem / 128, rl = rem % 128;
+    const int r = tile * 128 + rl;
+    __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const int k = c * 8 + e;
+        float x = 0.f;
+        if (r < rows) {
+            if (k < cols) x = (float)src[(size_t)r * ld + k];
+            else if (k == cols) x = extra != nullptr ? (float)extra[r] : (ones_col ? 1.f : 0.f);
+        }
+        v[e] = __float2bfloat16_rn(x);
+    }
+    *reinterpret_cast<uint4*>(dst + (size_t)idx * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
+// One warp per row: Euclidean norm of the row (with the extra bias / 1.0 component), rounded up a little;
+// optionally the maximum over rows (float bits compare like unsigned ints for non-negative values; NaN wins).
+template <typename T>
+__global__ void row_norm_kernel(const T* __restrict__ src, const size_t ld, const int rows, const int cols,
+                                const T* __restrict__ extra, const int ones_col,
+                                float* __restrict__ norm_out, unsigned* __restrict__ max_bits)
+{
+    const int lane = threadIdx.x & 31;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (r >= rows) return;
+    float acc = 0.f;
+    for (int k = lane; k < cols; k += 32) { const float x = (float)src[(size_t)r * ld + k]; acc = fmaf(x, x, acc); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+    if (lane == 0) {
+        float e = extra != nullptr ? (float)extra[r] : (ones_col ? 1.f : 0.f);
+        const float nrm = sqrtf(fmaf(e, e, acc)) * 1.001f;
+        if (norm_out) norm_out[r] = nrm;
+        if (max_bits) atomicMax(max_bits, __float_as_uint(nrm));
     }
 }
 

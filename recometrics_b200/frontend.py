@@ -174,11 +174,13 @@ def calc_reco_metrics_ex(
         all_metrics=False, break_ties_with_noise=True, min_pos_test=1, min_items_pool=2,
         consider_cold_start=True, cumulative=False, nthreads=-1, seed=1,
         device=-1, user_range=None, strict_min_pos_test=False,
-        return_topk=False, return_ranks=False, return_status=False):
+        return_topk=False, return_ranks=False, return_status=False, scoring_path="auto"):
     """Same evaluation as :func:`calc_reco_metrics`, returning an :class:`EvalResult` with the
     reference-style dict plus timing and the optional extras (top-K ids/scores, held-out ranks,
     per-user status).  ``user_range=(begin, end)`` evaluates only those rows (the sharding unit);
-    rows outside it are left as NaN in the returned arrays."""
+    rows outside it are left as NaN in the returned arrays.  ``scoring_path``: "auto" | "fma" (every score on
+    the FP32/FP64 FMA pipe) | "tensor" (bf16 tensor-core candidate filter + exact FMA re-scoring of the
+    survivors: identical top-K and scores, top-K metrics only)."""
     flags = dict(p=precision, tp=trunc_precision, r=recall, ap=average_precision, tap=trunc_average_precision,
                  ndcg=ndcg, hit=hit, rr=rr, roc=roc_auc, pr=pr_auc)
     flags = {q: bool(v) or bool(all_metrics) for q, v in flags.items()}
@@ -202,7 +204,7 @@ def calc_reco_metrics_ex(
     ub, ue = (0, 0) if user_range is None else (int(user_range[0]), int(user_range[1]))
     extra = _capi.make_extra(device=device, user_begin=ub, user_end=ue, strict_min_pos_test=strict_min_pos_test,
                              topk_items=topk_items, topk_scores=topk_scores, pos_rank=pos_rank, status=status,
-                             timing=timing)
+                             timing=timing, scoring_path=scoring_path)
     rc = _capi.calc_metrics(dtype, prep["A"], prep["lda"], prep["B"], prep["ldb"], m, prep["n"], prep["p"],
                             prep["trp"], prep["tri"], prep["tep"], prep["tei"], prep["tev"], K, cumulative,
                             bool(break_ties_with_noise), outs, prep["consider_cold_start"], prep["min_items_pool"],

@@ -17,6 +17,17 @@ from tools import synth
 
 pytestmark = pytest.mark.gpu
 
+
+@pytest.fixture(autouse=True, params=["auto", "fma"])
+def scoring_path(request, monkeypatch):
+    """Every parity case runs twice: with the library's automatic choice (tensor-core filter + exact
+    re-scoring wherever only top-K metrics are requested) and with every score on the FMA pipe."""
+    if request.param == "auto":
+        monkeypatch.delenv("RMB200_PATH", raising=False)
+    else:
+        monkeypatch.setenv("RMB200_PATH", request.param)
+    return request.param
+
 REPORT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "parity_report.jsonl")
 
 
@@ -318,3 +329,30 @@ def test_unsupported_requests_fail_loudly(rb):
         rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=500, break_ties_with_noise=False)
     with pytest.raises(NotImplementedError):
         rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=5, break_ties_with_noise=True)
+
+
+def test_tensor_filter_path_equals_fma_path_bit_for_bit(rb):
+    """The tensor-core path only decides which scores get looked at: ranked ids and scores must be the FMA path's."""
+    for cfg_id, m, n, k, dtype in ((4, 700, 30000, 100, np.float32), (2, 900, 9000, 10, np.float32), (5, 600, 8000, 50, np.float64)):
+        d = synth.make(cfg_id, m=m, n=n)
+        A, B = d["A"].astype(dtype), d["B"].astype(dtype)
+        out = {}
+        for path in ("fma", "tensor"):
+            r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=k, item_biases=d["item_biases"], precision=True,
+                                        average_precision=True, ndcg=True, break_ties_with_noise=False, return_topk=True,
+                                        return_status=True, scoring_path=path)
+            assert r.timing["scoring_path"] == (1 if path == "fma" else 2)
+            out[path] = r
+        a, b = out["fma"], out["tensor"]
+        assert np.array_equal(a.status, b.status)
+        assert np.array_equal(a.topk_items, b.topk_items)
+        assert np.array_equal(a.topk_scores, b.topk_scores, equal_nan=True)
+        for key in ("P@K", "AP@K", "NDCG@K"):
+            assert np.array_equal(a.metrics[key], b.metrics[key], equal_nan=True)
+
+
+def test_tensor_path_refuses_rank_counting(rb):
+    d = synth.make(1, m=200, n=500)
+    with pytest.raises(NotImplementedError):
+        rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, roc_auc=True, break_ties_with_noise=False,
+                                scoring_path="tensor")
