@@ -68,6 +68,7 @@ typedef struct rmb200_timing {
     int64_t kernel_launches;/* kernels of this library launched by the call                     */
     int64_t h2d_bytes, d2h_bytes;
     int64_t scoring_path;   /* which scoring kernel ran: 1 = FMA tiles, 2 = tensor-core filter + exact re-score */
+    int64_t filter_fallback_batches; /* user batches the tensor-core filter handed back to the FMA path         */
 } rmb200_timing_t;
 
 /* Optional extension block (pass NULL for reference behaviour).  Zero-initialise, then set

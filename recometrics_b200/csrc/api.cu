@@ -140,23 +140,33 @@ cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool 
                : launch_score_select_inst<T, 1024, false>(P, n_user_tiles, st);
 }
 
-template <typename T, int C>
-cudaError_t launch_filter_inst(const rmb::FilterParams<T>& P, int n_user_tiles, cudaStream_t st)
+template <int C>
+cudaError_t launch_filter_inst(const rmb::FilterParams& P, int n_user_tiles, cudaStream_t st)
 {
-    auto kern = rmb::filter_select_kernel<T, C>;
-    const size_t smem = rmb::filter_smem_bytes(P.KB, P.stages, P.p_pad, sizeof(T));
+    auto kern = rmb::filter_select_kernel<C>;
+    const size_t smem = rmb::filter_smem_bytes(P.KB, P.stages);
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     kern<<<n_user_tiles, rmb::F_THREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
 
-template <typename T>
-cudaError_t launch_filter_select(const rmb::FilterParams<T>& P, int C, int n_user_tiles, cudaStream_t st)
+inline cudaError_t launch_filter_select(const rmb::FilterParams& P, int C, int n_user_tiles, cudaStream_t st)
 {
-    if (C == 256) return launch_filter_inst<T, 256>(P, n_user_tiles, st);
-    if (C == 512) return launch_filter_inst<T, 512>(P, n_user_tiles, st);
-    return launch_filter_inst<T, 1024>(P, n_user_tiles, st);
+    if (C == 256) return launch_filter_inst<256>(P, n_user_tiles, st);
+    if (C == 512) return launch_filter_inst<512>(P, n_user_tiles, st);
+    return launch_filter_inst<1024>(P, n_user_tiles, st);
+}
+
+template <typename T>
+cudaError_t launch_exact_topk(const float* capx, T* cs, int* ci, int* cc, int C, int nb, int user0, const T* At, int p_pad, int p,
+                              const T* Brow, size_t ldb, const T* bias, int* uflags, int K, cudaStream_t st)
+{
+    const int blocks = (nb + 3) / 4;
+    if (C == 256) rmb::exact_topk_kernel<T, 256><<<blocks, 128, 0, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
+    else if (C == 512) rmb::exact_topk_kernel<T, 512><<<blocks, 128, 0, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
+    else rmb::exact_topk_kernel<T, 1024><<<blocks, 128, 0, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
+    return cudaGetLastError();
 }
 
 // order the <= K survivors of every user (warp per user, bitonic network sized to K)
@@ -243,8 +253,9 @@ int run_call(const CallArgs<T>& a)
     if (!(ex && ex->strict_min_pos_test)) mpt = mpt < 1 ? mpt : 1;   // std::min(min_pos_test, 1): quirk Q1
 
     const int K = a.K;
-    // candidate buffer: K kept + 128 appended per tile + head-room between two re-sorts
-    const int C = (K <= 64) ? 256 : (K <= 192 ? 512 : 1024);
+    // candidate buffer: K kept + 128 appended per tile + head-room between two cuts (the tensor-core filter keeps
+    // the slack band below the K-th best as well: about 2.5 K entries on Gaussian scores, so it gets more room)
+    int C = (K <= 64) ? 256 : (K <= 192 ? 512 : 1024);
     const bool want_roc = a.out[8] != nullptr, want_pr = a.out[9] != nullptr;
     const bool count_ranks = want_roc || want_pr || (ex && ex->pos_rank);
     const int p_pad = round_up(a.k, KPAD);
@@ -260,14 +271,15 @@ int run_call(const CallArgs<T>& a)
     const int KB = round_up(a.k + (a.bias ? 1 : 0), 16);            // bf16 factors per row (bias = one more factor)
     int f_stages = 0;
     {
-        const long long tile = (long long)KB * 256, budget = 225 * 1024 - (long long)F_EPI_WARPS * p_pad * (long long)sizeof(T) - 2048;
+        const long long tile = (long long)KB * 256, budget = 225 * 1024;
         f_stages = (int)(budget / tile) - 1;
         if (f_stages > F_MAX_STAGES) f_stages = F_MAX_STAGES;
     }
-    const bool tensor_ok = !count_ranks && f_stages >= 2;
-    if (path_req == 2 && !tensor_ok) { set_err("unsupported", "scoring_path=tensor needs no ROC/PR-AUC (rank counting) and k <= ~256"); return RMB200_ERR_UNSUPPORTED; }
+    const bool tensor_ok = !count_ranks && f_stages >= 2 && K <= 256;
+    if (path_req == 2 && !tensor_ok) { set_err("unsupported", "scoring_path=tensor needs no ROC/PR-AUC (rank counting), k <= ~400 and k_metrics <= 256"); return RMB200_ERR_UNSUPPORTED; }
     const bool use_tensor = tensor_ok && path_req != 1;
     tm.scoring_path = use_tensor ? 2 : 1;
+    if (use_tensor) C = (K <= 32) ? 256 : (K <= 128 ? 512 : 1024);
 
     // ---- CSR slices of users [ub, ue), index pointers re-based to the slice ----
     int lo_hi[4];   // trp[ub], trp[ue], tep[ub], tep[ue]
@@ -330,7 +342,9 @@ int run_call(const CallArgs<T>& a)
         if (rc) return rc;
         pt.stop(tm.h2d_ms);
     } else { Bsrc = a.B; Bld = a.ldb; }
-    if (!use_tensor) {
+    bool have_Bt = false;
+    auto pack_Bt = [&]() -> int {          // operand image of the FMA path (the tensor path needs it only as a fall-back)
+        if (have_Bt) return RMB200_OK;
         CK(d_Bt.alloc((size_t)p_pad * n_pad * sizeof(T)));
         pt.start();
         dim3 grid(n_pad / 32, (p_pad + 31) / 32), block(32, 8);
@@ -338,7 +352,14 @@ int run_call(const CallArgs<T>& a)
         CK(cudaGetLastError());
         tm.kernel_launches++;
         pt.stop(tm.prep_ms);   // (synchronises)
+        have_Bt = true;
+        return RMB200_OK;
+    };
+    if (!use_tensor) {
+        int rc = pack_Bt();
+        if (rc) return rc;
         d_Brow.release();      // the FMA path reads only the tiled copy
+        if (!on_dev) Bsrc = nullptr;
     }
     const T* bias_d = nullptr;
     if (a.bias) {
@@ -427,9 +448,12 @@ int run_call(const CallArgs<T>& a)
 
     DevBuf d_At, d_Arow, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
     CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
+    DevBuf d_capx, d_overflow;
     if (use_tensor) {
         CK(d_Ab.alloc((size_t)UB * KB * sizeof(__nv_bfloat16)));
         CK(d_anorm.alloc((size_t)UB * sizeof(float)));
+        CK(d_capx.alloc((size_t)UB * C * sizeof(float)));
+        CK(d_overflow.alloc(sizeof(int)));
     }
     if (!on_dev) CK(d_Arow.alloc((size_t)UB * a.k * sizeof(T)));
     CK(d_cs.alloc((size_t)UB * C * sizeof(T)));
@@ -475,34 +499,8 @@ int run_call(const CallArgs<T>& a)
         }
         pt.stop(tm.prep_ms);
 
-        if (use_tensor) {
-            // bf16 operand image + norms of the batch's users, then the tensor-core filter
-            pt.start();
-            const long long total = (long long)nb_pad * (KB / 8);
-            pack_bf16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
-                                                                                 d_Ab.as<__nv_bfloat16>(), nb_pad, KB);
-            CK(cudaGetLastError());
-            row_norm_kernel<T><<<(nb + 7) / 8, 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0, d_anorm.as<float>(), nullptr);
-            CK(cudaGetLastError());
-            tm.kernel_launches += 2;
-            pt.stop(tm.prep_ms);
-            pt.start();
-            FilterParams<T> fp;
-            fp.Ab = d_Ab.as<__nv_bfloat16>(); fp.Bb = d_Bb.as<__nv_bfloat16>(); fp.KB = KB; fp.stages = f_stages;
-            fp.n = a.n; fp.mb = nb; fp.user0 = b0;
-            fp.At = d_At.as<T>(); fp.p_pad = p_pad; fp.p = a.k; fp.Brow = Bsrc; fp.ldb = Bld; fp.bias = bias_d;
-            fp.anorm = d_anorm.as<float>(); fp.maxbn = d_maxbn.as<unsigned>();
-            fp.trp = trp_d; fp.tri = tri_d; fp.ustatus = d_status.as<int>();
-            fp.cand_score = d_cs.as<T>(); fp.cand_item = d_ci.as<int>(); fp.cand_count = d_cc.as<int>();
-            fp.uflags = d_flags.as<int>(); fp.K = K;
-            CK(launch_filter_select<T>(fp, C, nb_pad / BM, st));
-            CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
-            tm.kernel_launches += 2;
-            pt.stop(tm.score_select_ms);
-        } else {
-        // fused score / exclude / select (/ rank counting)
-        pt.start();
-        {
+        auto run_fma_batch = [&]() -> int {
+            // fused score / exclude / select (/ rank counting) on the FMA pipe
             ScoreSelectParams<T> sp;
             sp.At = d_At.as<T>(); sp.Bt = d_Bt.as<T>(); sp.bias = bias_d;
             sp.p_pad = p_pad; sp.n = a.n; sp.mb = nb; sp.user0 = b0;
@@ -513,11 +511,60 @@ int run_call(const CallArgs<T>& a)
             sp.auc_cnt = count_ranks ? d_auc.as<unsigned int>() : nullptr;
             sp.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
             CK(launch_score_select<T>(sp, C, count_ranks, nb_pad / BM, st));
-            CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
+            tm.kernel_launches++;
+            return RMB200_OK;
+        };
+        bool batch_on_tensor = use_tensor;
+        if (use_tensor) {
+            // bf16 operand image + norms of the batch's users, then the tensor-core filter and the exact re-scoring
+            pt.start();
+            const long long total = (long long)nb_pad * (KB / 8);
+            pack_bf16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
+                                                                                 d_Ab.as<__nv_bfloat16>(), nb_pad, KB);
+            CK(cudaGetLastError());
+            row_norm_kernel<T><<<(nb + 7) / 8, 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0, d_anorm.as<float>(), nullptr);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(d_overflow.p, 0, sizeof(int), st));
             tm.kernel_launches += 2;
+            pt.stop(tm.prep_ms);
+            pt.start();
+            FilterParams fp;
+            fp.Ab = d_Ab.as<__nv_bfloat16>(); fp.Bb = d_Bb.as<__nv_bfloat16>(); fp.KB = KB; fp.stages = f_stages;
+            fp.n = a.n; fp.mb = nb; fp.user0 = b0;
+            fp.anorm = d_anorm.as<float>(); fp.maxbn = d_maxbn.as<unsigned>();
+            fp.trp = trp_d; fp.tri = tri_d; fp.ustatus = d_status.as<int>();
+            fp.cand_approx = d_capx.as<float>(); fp.cand_item = d_ci.as<int>(); fp.cand_count = d_cc.as<int>();
+            fp.overflow = d_overflow.as<int>(); fp.uflags = d_flags.as<int>(); fp.K = K;
+            CK(launch_filter_select(fp, C, nb_pad / BM, st));
+            tm.kernel_launches++;
+            int n_over = 0;
+            CK(cudaMemcpyAsync(&n_over, d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (n_over > 0) {
+                // some user's slack band did not fit its candidate buffer (near-constant scores): the whole batch
+                // goes through the FMA path instead -- slower, same results
+                batch_on_tensor = false;
+                tm.filter_fallback_batches++;
+                pt.stop(tm.score_select_ms);
+                int rc = pack_Bt();
+                if (rc) return rc;
+                pt.start();
+                rc = run_fma_batch();
+                if (rc) return rc;
+            } else {
+                CK(launch_exact_topk<T>(d_capx.as<float>(), d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, b0, d_At.as<T>(), p_pad, a.k,
+                                        Bsrc, Bld, bias_d, d_flags.as<int>(), K, st));
+                tm.kernel_launches++;
+            }
+        } else {
+            pt.start();
+            int rc = run_fma_batch();
+            if (rc) return rc;
         }
+        CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
+        tm.kernel_launches++;
         pt.stop(tm.score_select_ms);
-        }
+        (void)batch_on_tensor;
 
         // per-user metrics
         pt.start();

@@ -4,23 +4,28 @@
 // Same job as score_select.cuh (reference: candidate list /root/reference/src/recometrics.hpp:491-497,
 // dot1 scoring :84-112/:499-512, partial_sort :537-548) with the work split differently:
 //
-//   1. FILTER  -- every (user, item) score is computed APPROXIMATELY on the 5th-generation tensor cores:
-//      bf16 copies of the factors (item bias folded in as one more factor, as the reference's front-end
-//      does, recometrics/__init__.py:548-551), fp32 accumulation in TMEM.  A CTA keeps a 128-user A tile
-//      resident in shared memory and streams 128-item B tiles through a TMA ring; one elected thread
-//      issues tcgen05.mma (M=128, N=128, K=16 per instruction) into one of two TMEM accumulator
-//      buffers; four epilogue warps read the other buffer with tcgen05.ld -- thread t owns user row t
-//      (TMEM lane t), so tau, counters and the candidate buffer of a user are private to one thread.
-//      |approx - exact| <= margin_u = c * ||a_u|| * max_j ||b_j||  (bf16 rounding of both operands,
-//      Cauchy-Schwarz; prep.cuh), so an item can only belong to the user's top K if
-//      approx >= tau_u - margin_u, where tau_u is the EXACT K-th best score seen so far.  Everything
-//      else (>= 99.9 % of the catalogue) is rejected with one compare on the approximate score.
-//   2. EXACT   -- survivors are appended to the user's candidate buffer; when it fills, the warp
-//      re-scores the new entries exactly (sequential fma chain over the original fp32 / fp64 factors:
-//      the same chain, hence bit-identical scores, as score_select_kernel and score_entries_kernel),
-//      drops train items / padding, and cuts the buffer back to the best K with the radix select of
-//      score_select.cuh.  The final top-K, their order and their scores are therefore exactly those
-//      of the FP32 (FP64) FMA path; the tensor cores only decide what is worth looking at.
+//   1. FILTER (filter_select_kernel) -- every (user, item) score is computed APPROXIMATELY on the
+//      5th-generation tensor cores: bf16 copies of the factors (item bias folded in as one more factor,
+//      as the reference's front-end does, recometrics/__init__.py:548-551), fp32 accumulation in TMEM.
+//      A CTA keeps a 128-user A tile resident in shared memory and streams 128-item B tiles through a
+//      TMA ring; one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction) into one of
+//      two TMEM accumulator buffers; four epilogue warps read the other buffer with tcgen05.ld --
+//      thread t owns user row t (TMEM lane t), so the threshold, the counters, the train-row cursor and
+//      the candidate buffer of a user are private to one thread (no atomics, no shared state).
+//      With m_u = c * ||a_u|| * max_j ||b_j|| >= |approx - exact| (bf16 rounding of both operands,
+//      Cauchy-Schwarz; prep.cuh) and tau~ = the K-th best APPROXIMATE candidate score seen so far, every
+//      member of the exact top K satisfies approx >= tau~ - 2 m_u (the K best approximate scores have
+//      exact scores >= tau~ - m_u, so the exact K-th best is >= tau~ - m_u, and a member's approximate
+//      score is within m_u of its exact one).  The kernel therefore keeps, per user, all candidates with
+//      approx >= tau~ - 2 m_u: train items and padding columns are dropped when appended, the buffer is
+//      cut back with a radix select on the approximate keys when it fills.  >= 99.9 % of the catalogue
+//      is rejected with one compare.
+//   2. EXACT (exact_topk_kernel) -- one warp per user re-scores the few hundred survivors exactly
+//      (sequential fma chain over the original fp32 / fp64 factors: the same chain, hence bit-identical
+//      scores, as score_select_kernel / score_entries_kernel) and keeps the best K.  The final top-K,
+//      their order and their scores are exactly those of the FP32 (FP64) FMA path; the tensor cores only
+//      decide what is worth looking at.  A user whose slack band does not fit the buffer is flagged and
+//      the host re-runs that batch on the FMA path.
 //
 // Shared-memory operand layout (no swizzle, K-major "interleaved"): [k/8][row][8 bf16] -- a core matrix
 // is 8 rows x 16 bytes contiguous; descriptor LBO = 128 rows * 16 B (next k chunk), SBO = 128 B (next 8
@@ -39,33 +44,28 @@ constexpr int F_TMEM_COLS = 2 * FN;      // two accumulator buffers
 constexpr int F_MAX_STAGES = 4;
 constexpr int F_CHUNK = 32;              // TMEM columns per tcgen05.ld
 
-template <typename T>
 struct FilterParams {
     const __nv_bfloat16* __restrict__ Ab;   // [user tiles][KB/8][128][8]  bf16 user factors (+1.0 bias column)
     const __nv_bfloat16* __restrict__ Bb;   // [item tiles][KB/8][128][8]  bf16 item factors (+bias column)
     int KB;                                 // bf16 factors per row, multiple of 16
     int stages;                             // depth of the B ring
     int n, mb, user0;
-    const T* __restrict__ At;               // exact user factors, tiled [user tile][p_pad][128]
-    int p_pad, p;
-    const T* __restrict__ Brow;             // exact item factors, row-major, leading dimension ldb
-    size_t ldb;
-    const T* __restrict__ bias;             // exact item biases or nullptr
     const float* __restrict__ anorm;        // [mb] ||a_u|| (with the 1.0 bias component), rounded up
     const unsigned* __restrict__ maxbn;     // float bits of max_j ||b_j|| (with the bias component)
     const int* __restrict__ trp;
     const int* __restrict__ tri;
     const int* __restrict__ ustatus;
-    T* cand_score;                          // [mb_pad][C]
-    int* cand_item;
-    int* cand_count;
-    int* uflags;
+    float* cand_approx;                     // [mb_pad][C] approximate scores of the kept candidates
+    int* cand_item;                         // [mb_pad][C]
+    int* cand_count;                        // [mb_pad] kept candidates; -1 = slack band overflowed the buffer
+    int* overflow;                          // number of users flagged -1
+    int* uflags;                            // [m] bit0: a candidate score was NaN
     int K;
 };
 
-inline size_t filter_smem_bytes(int KB, int stages, int p_pad, size_t elem)
+inline size_t filter_smem_bytes(int KB, int stages)
 {
-    return (size_t)(1 + stages) * KB * 128 * 2 + (size_t)F_EPI_WARPS * p_pad * elem + 256 + 1024;
+    return (size_t)(1 + stages) * KB * 128 * 2 + 256;
 }
 
 // ------------------------------------------------------------------ tcgen05 wrappers
@@ -101,114 +101,63 @@ __device__ __forceinline__ void tmem_ld32(const unsigned taddr, unsigned (&r)[32
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__device__ __forceinline__ float sub_down(const float tau, const float margin) { return __fsub_rd(tau, margin); }
-__device__ __forceinline__ float sub_down(const double tau, const float margin) { return __double2float_rd(tau - (double)margin); }
-
-// One warp: re-score the not yet exact entries [nproc, nv) of a user's candidate buffer, drop what is
-// not a candidate (padding columns, train items: hpp:494-495; NaN scores raise the row's NaN flag),
-// then cut the buffer back to the best K (score descending, ties by ascending item id).
-// Returns the new entry count (all exact); tau is updated when at least K entries remain.
-template <typename T, int C>
-__device__ __noinline__ int filter_compact(T* cs, int* ci, const int nv, const int nproc, const int K, const int lane,
-                                           T* a_sm, const T* __restrict__ At_user /* + k*128 */, const int p,
-                                           const T* __restrict__ Brow, const size_t ldb, const T* __restrict__ bias, const int n,
-                                           const int* __restrict__ tri, const int tr_lo, const int tr_hi,
-                                           T* tau_io, int* nan_io)
+// One warp: cut the nv (>= K) approximate entries of a user's buffer back to those that can still belong
+// to the exact top K: score >= (K-th best approximate score) - slack.  Returns the number kept (>= K,
+// unordered at the head) and the K-th best approximate score.
+template <int C>
+__device__ __noinline__ int approx_compact(float* cs, int* ci, const int nv, const int K, const float slack, const int lane,
+                                           float* tau_out)
 {
-    typedef typename NumTraits<T>::key_t key_t;
     constexpr int E = C / 32;
-    for (int k = lane; k < p; k += 32) a_sm[k] = At_user[(size_t)k * BM];
-    __syncwarp();
-    key_t key[E];
+    unsigned key[E];
     int it[E];
-    int nanflag = 0;
 #pragma unroll
     for (int e = 0; e < E; e++) {
         const int idx = e * 32 + lane;
-        key[e] = 0;                                             // 0 sorts below every score: "not an entry"
-        it[e] = INT_MAX;
-        if (idx < nv) {
-            const int item = ci[idx];
-            it[e] = item;
-            if (idx < nproc) {
-                key[e] = NumTraits<T>::key(cs[idx]);
-            } else if (item < n && !in_train_segment(tri, tr_lo, tr_hi, item)) {
-                const T* __restrict__ b = Brow + (size_t)item * ldb;
-                T acc = (T)0;
-#pragma unroll 8
-                for (int k = 0; k < p; k++) acc = NumTraits<T>::fma(a_sm[k], b[k], acc);
-                if (bias != nullptr) acc += bias[item];
-                if (acc != acc) nanflag = 1;
-                else key[e] = NumTraits<T>::key(acc);
-            }
-        }
-    }
-    nanflag = __any_sync(FULL, nanflag);
-    int nvalid = 0;
-#pragma unroll
-    for (int e = 0; e < E; e++) nvalid += (key[e] != 0) ? 1 : 0;
-    nvalid = __reduce_add_sync(FULL, nvalid);
-
-    key_t t = 0;                  // keep key > t, and key == t with item id <= id_cut
-    unsigned id_cut = 0x7fffffffu;
-    if (nvalid >= K) {
-        for (int b = NumTraits<T>::KEYBITS - 1; b >= 0; b--) {
-            const key_t cand = t | ((key_t)1 << b);
-            int c = 0;
-#pragma unroll
-            for (int e = 0; e < E; e++) c += (key[e] >= cand) ? 1 : 0;
-            c = __reduce_add_sync(FULL, c);
-            if (c >= K) t = cand;
-        }
-        int cgt = 0, cge = 0;
-#pragma unroll
-        for (int e = 0; e < E; e++) { cgt += (key[e] > t) ? 1 : 0; cge += (key[e] >= t) ? 1 : 0; }
-        cgt = __reduce_add_sync(FULL, cgt);
-        cge = __reduce_add_sync(FULL, cge);
-        if (cge > K) {
-            const int need = K - cgt;
-            unsigned x = 0;
-            for (int b = 30; b >= 0; b--) {
-                const unsigned cand = x | (1u << b);
-                int c = 0;
-#pragma unroll
-                for (int e = 0; e < E; e++) c += (key[e] == t && (unsigned)it[e] < cand) ? 1 : 0;
-                c = __reduce_add_sync(FULL, c);
-                if (c < need) x = cand;
-            }
-            id_cut = x;
-        }
+        const bool v = idx < nv;
+        key[e] = v ? NumTraits<float>::key(cs[idx]) : 0u;      // 0 sorts below every score
+        it[e] = v ? ci[idx] : INT_MAX;
     }
     __syncwarp();
+    unsigned t = 0;                                             // K-th largest key (NaN scores sort on top)
+    for (int b = 31; b >= 0; b--) {
+        const unsigned cand = t | (1u << b);
+        int c = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) c += (key[e] >= cand) ? 1 : 0;
+        c = __reduce_add_sync(FULL, c);
+        if (c >= K) t = cand;
+    }
+    const float tau = NumTraits<float>::from_orderable((u64)t);
+    const float cutf = __fsub_rd(tau, slack);                   // NaN (tau or slack not finite): keep everything
+    const unsigned cut = (cutf == cutf) ? NumTraits<float>::key(cutf) : 1u;
     int base = 0;
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        const bool keep = (key[e] != 0) && ((key[e] > t) || (key[e] == t && (unsigned)it[e] <= id_cut));
+        const bool keep = key[e] >= cut && key[e] != 0u;
         const unsigned mask = __ballot_sync(FULL, keep);
         if (keep) {
             const int pos = base + __popc(mask & ((1u << lane) - 1u));
-            cs[pos] = NumTraits<T>::from_orderable((u64)key[e]);
+            cs[pos] = NumTraits<float>::from_orderable((u64)key[e]);
             ci[pos] = it[e];
         }
         base += __popc(mask);
     }
-    if (nvalid >= K) *tau_io = NumTraits<T>::from_orderable((u64)t);
-    if (nanflag) *nan_io = 1;
+    *tau_out = tau;
     __syncwarp();
     return base;
 }
 
-template <typename T, int C>
+template <int C>
 __global__ void __launch_bounds__(F_THREADS, 1)
-filter_select_kernel(const __grid_constant__ FilterParams<T> P)
+filter_select_kernel(const __grid_constant__ FilterParams P)
 {
     const int KB = P.KB, S = P.stages;
     const unsigned tile_bytes = (unsigned)KB * 128u * 2u;          // one operand tile (A or B)
-    unsigned char* a_tile = smem_raw;                              // 1024-aligned dynamic shared memory
+    unsigned char* a_tile = smem_raw;
     unsigned char* b_ring = a_tile + tile_bytes;
-    T* a_scratch = reinterpret_cast<T*>(b_ring + (size_t)S * tile_bytes);          // [F_EPI_WARPS][p_pad]
-    u64* bars = reinterpret_cast<u64*>(reinterpret_cast<unsigned char*>(a_scratch) + (((size_t)F_EPI_WARPS * P.p_pad * sizeof(T) + 15) & ~size_t(15)));
-    // barriers: full[S], empty[S], acc_full[2], acc_empty[2], a_full
+    u64* bars = reinterpret_cast<u64*>(b_ring + (size_t)S * tile_bytes);
+    // barriers: full[4], empty[4], acc_full[2], acc_empty[2], a_full
     const unsigned bar_full = smem_u32(bars), bar_empty = bar_full + 8 * F_MAX_STAGES;
     const unsigned bar_accf = bar_empty + 8 * F_MAX_STAGES, bar_acce = bar_accf + 16, bar_a = bar_acce + 16;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * F_MAX_STAGES + 5);
@@ -267,39 +216,22 @@ filter_select_kernel(const __grid_constant__ FilterParams<T> P)
         const int row = warp * 32 + lane;
         const int ul = tile_u0 + row;
         const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0);
-        T tau = -NumTraits<T>::inf();
         // |approx - exact| <= (2^-7 (1 + 2^-9) + k 2^-22) sum|a_k b_k| <= 0.0084 ||a|| ||b||: bf16 rounding of both
         // operands (relative 2^-8 each), fp32 accumulation in the tensor core, fp32 rounding of the exact chain
-        const float margin = ranked ? 0.0084f * P.anorm[ul] * __uint_as_float(*P.maxbn) : 0.f;
-        float thr = ranked ? -CUDART_INF_F : CUDART_INF_F;
-        int cnt = 0, nproc = 0, nanrow = 0;
-        T* cs = P.cand_score + (size_t)ul * C;
+        const float slack = ranked ? 2.f * 0.0084f * P.anorm[ul] * __uint_as_float(*P.maxbn) : 0.f;
+        float thr = ranked ? -CUDART_INF_F : CUDART_INF_F;       // approx < thr: cannot be in the exact top K
+        int cnt = 0;
+        bool overflowed = false, nanrow = false;
+        float* cs = P.cand_approx + (size_t)ul * C;
         int* ci = P.cand_item + (size_t)ul * C;
-        int tr_lo = 0, tr_hi = 0;
-        if (ranked) { tr_lo = P.trp[P.user0 + ul]; tr_hi = P.trp[P.user0 + ul + 1]; }
-        T* a_sm = a_scratch + (size_t)warp * P.p_pad;
-
-        auto compact_rows = [&](unsigned need) {
-            while (need) {
-                const int r = __ffs(need) - 1;
-                need &= need - 1;
-                const int ul_r = tile_u0 + warp * 32 + r;
-                const int nv_r = __shfl_sync(FULL, cnt, r), np_r = __shfl_sync(FULL, nproc, r);
-                const int lo_r = __shfl_sync(FULL, tr_lo, r), hi_r = __shfl_sync(FULL, tr_hi, r);
-                T tau_r = __shfl_sync(FULL, tau, r);
-                int nan_r = 0;
-                const int kept = filter_compact<T, C>(P.cand_score + (size_t)ul_r * C, P.cand_item + (size_t)ul_r * C, nv_r, np_r, P.K, lane,
-                                                      a_sm, P.At + (size_t)(ul_r / BM) * P.p_pad * BM + (ul_r % BM), P.p,
-                                                      P.Brow, P.ldb, P.bias, P.n, P.tri, lo_r, hi_r, &tau_r, &nan_r);
-                if (lane == r) {
-                    cnt = kept; nproc = kept; tau = tau_r; nanrow |= nan_r;
-                    thr = sub_down(tau, margin);
-                }
-            }
-        };
+        // the row's sorted train items (hpp:494-495 takes them out of the pool): cursor = first one >= the current tile
+        int tr_cur = 0, tr_end = 0;
+        if (ranked) { tr_cur = P.trp[P.user0 + ul]; tr_end = P.trp[P.user0 + ul + 1]; }
+        int nxt_train = tr_cur < tr_end ? P.tri[tr_cur] : INT_MAX;
 
         for (int t = 0; t < NT; t++) {
             const int b = t & 1;
+            const int tile_end = (t + 1) * FN;
             mbar_wait(bar_accf + 8 * b, (t >> 1) & 1);
             tc_fence_after();
             for (int c = 0; c < FN / F_CHUNK; c++) {
@@ -319,21 +251,45 @@ filter_select_kernel(const __grid_constant__ FilterParams<T> P)
                     for (int j = 0; j < w; j++) mx[j] = max_nan(mx[j], mx[j + w]);
                 if (__any_sync(FULL, !(mx[0] < thr))) {
                     const int item_base = t * FN + c * F_CHUNK;
+                    const bool has_train = nxt_train < tile_end;
 #pragma unroll
                     for (int j = 0; j < 32; j++) {
                         const float s = __uint_as_float(v[j]);
-                        if (!(s < thr) && ranked) { cs[cnt] = (T)s; ci[cnt] = item_base + j; cnt++; }
+                        if (!(s < thr)) {
+                            const int item = item_base + j;
+                            if (item < P.n && !(has_train && in_train_segment(P.tri, tr_cur, tr_end, item))) {
+                                if (s != s) nanrow = true;             // NaN candidate score => NaN row (hpp:195-197)
+                                else { cs[cnt] = s; ci[cnt] = item; cnt++; }
+                            }
+                        }
                     }
-                    const unsigned need = __ballot_sync(FULL, cnt > C - F_CHUNK);
-                    if (need) compact_rows(need);
+                    unsigned need = __ballot_sync(FULL, cnt > C - F_CHUNK);
+                    while (need) {
+                        const int r = __ffs(need) - 1;
+                        need &= need - 1;
+                        const size_t base = (size_t)(tile_u0 + warp * 32 + r) * C;
+                        float tau_r;
+                        const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, __shfl_sync(FULL, cnt, r), P.K,
+                                                           __shfl_sync(FULL, slack, r), lane, &tau_r);
+                        if (lane == r) {
+                            cnt = kept;
+                            thr = __fsub_rd(tau_r, slack);
+                            if (!(thr == thr)) thr = -CUDART_INF_F;          // non-finite bound: keep everything
+                            if (kept > C - F_CHUNK) { overflowed = true; thr = CUDART_INF_F; cnt = 0; }   // slack band does not fit
+                        }
+                    }
                 }
             }
+            // move the train cursor past this tile (rare)
+            if (nxt_train < tile_end) {
+                while (tr_cur < tr_end && (nxt_train = P.tri[tr_cur]) < tile_end) tr_cur++;
+                if (tr_cur >= tr_end) nxt_train = INT_MAX;
+            }
         }
-        // exact scores for whatever is still pending, best K at the head of every buffer
-        compact_rows(__ballot_sync(FULL, ranked && cnt > 0));
         if (ul < P.mb) {
-            P.cand_count[ul] = ranked ? cnt : 0;
-            if (nanrow) atomicOr(&P.uflags[P.user0 + ul], 1);
+            P.cand_count[ul] = overflowed ? -1 : (ranked ? cnt : 0);
+            if (overflowed) atomicAdd(P.overflow, 1);
+            if (nanrow && ranked) atomicOr(&P.uflags[P.user0 + ul], 1);
         }
     }
 
@@ -341,6 +297,99 @@ filter_select_kernel(const __grid_constant__ FilterParams<T> P)
     __syncthreads();
     if (warp == F_EPI_WARPS + 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)F_TMEM_COLS));
+}
+
+// One warp per user: exact scores of the candidates the filter kept (sequential fma chain over the original
+// factors, + bias: the chain of score_select_kernel / score_entries_kernel, so the values are bit-identical
+// to the FMA path), NaN scores raise the user's NaN flag (hpp:195-197), best K (score descending, ties by
+// ascending item id) left unordered at the head of cand_score / cand_item.
+template <typename T, int C>
+__global__ void exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_score, int* __restrict__ cand_item,
+                                  int* __restrict__ cand_count, const int mb, const int user0,
+                                  const T* __restrict__ At, const int p_pad, const int p,
+                                  const T* __restrict__ Brow, const size_t ldb, const T* __restrict__ bias,
+                                  int* __restrict__ uflags, const int K)
+{
+    typedef typename NumTraits<T>::key_t key_t;
+    constexpr int E = C / 32;
+    const int lane = threadIdx.x & 31;
+    const int ul = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ul >= mb) return;
+    const int nv = cand_count[ul];
+    if (nv <= 0) return;
+    const T* __restrict__ a = At + (size_t)(ul / BM) * p_pad * BM + (ul % BM);      // + k * BM
+    const int* ci = cand_item + (size_t)ul * C;
+    key_t key[E];
+    int it[E];
+    int nanflag = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int idx = e * 32 + lane;
+        key[e] = 0;
+        it[e] = INT_MAX;
+        if (idx < nv) {
+            const int item = ci[idx];
+            it[e] = item;
+            const T* __restrict__ b = Brow + (size_t)item * ldb;
+            T acc = (T)0;
+#pragma unroll 8
+            for (int k = 0; k < p; k++) acc = NumTraits<T>::fma(a[(size_t)k * BM], b[k], acc);
+            if (bias != nullptr) acc += bias[item];
+            if (acc != acc) nanflag = 1;
+            else key[e] = NumTraits<T>::key(acc);
+        }
+    }
+    if (__any_sync(FULL, nanflag)) { if (lane == 0) atomicOr(&uflags[user0 + ul], 1); }
+    int nvalid = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) nvalid += (key[e] != 0) ? 1 : 0;
+    nvalid = __reduce_add_sync(FULL, nvalid);
+    key_t t = 0;                  // keep key > t, and key == t with item id <= id_cut
+    unsigned id_cut = 0x7fffffffu;
+    if (nvalid > K) {
+        for (int b = NumTraits<T>::KEYBITS - 1; b >= 0; b--) {
+            const key_t cand = t | ((key_t)1 << b);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < E; e++) c += (key[e] >= cand) ? 1 : 0;
+            c = __reduce_add_sync(FULL, c);
+            if (c >= K) t = cand;
+        }
+        int cgt = 0, cge = 0;
+#pragma unroll
+        for (int e = 0; e < E; e++) { cgt += (key[e] > t) ? 1 : 0; cge += (key[e] >= t) ? 1 : 0; }
+        cgt = __reduce_add_sync(FULL, cgt);
+        cge = __reduce_add_sync(FULL, cge);
+        if (cge > K) {
+            const int need = K - cgt;
+            unsigned x = 0;
+            for (int b = 30; b >= 0; b--) {
+                const unsigned cand = x | (1u << b);
+                int c = 0;
+#pragma unroll
+                for (int e = 0; e < E; e++) c += (key[e] == t && (unsigned)it[e] < cand) ? 1 : 0;
+                c = __reduce_add_sync(FULL, c);
+                if (c < need) x = cand;
+            }
+            id_cut = x;
+        }
+    }
+    T* cs = cand_score + (size_t)ul * C;
+    int* cio = cand_item + (size_t)ul * C;
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const bool keep = (key[e] != 0) && ((key[e] > t) || (key[e] == t && (unsigned)it[e] <= id_cut));
+        const unsigned mask = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+            cs[pos] = NumTraits<T>::from_orderable((u64)key[e]);
+            cio[pos] = it[e];
+        }
+        base += __popc(mask);
+    }
+    if (lane == 0) cand_count[ul] = base;
 }
 
 }  // namespace rmb
