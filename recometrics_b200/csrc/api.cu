@@ -158,15 +158,30 @@ inline cudaError_t launch_filter_select(const rmb::FilterParams& P, int C, int n
     return launch_filter_inst<1024>(P, n_user_tiles, st);
 }
 
+template <typename T, int C>
+cudaError_t launch_exact_topk_inst(const float* capx, T* cs, int* ci, int* cc, int nb, int user0, const T* At, int p_pad, int p,
+                                   const T* Brow, size_t ldb, const T* bias, int* uflags, int K, cudaStream_t st)
+{
+    const int blocks = (nb + rmb::EXACT_WARPS - 1) / rmb::EXACT_WARPS;
+    const size_t smem = rmb::exact_topk_smem_bytes(p_pad, sizeof(T));
+    if (smem <= 100 * 1024) {       // two blocks per SM
+        auto kern = rmb::exact_topk_kernel<T, C, true>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<blocks, rmb::EXACT_WARPS * 32, smem, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
+    } else {
+        rmb::exact_topk_kernel<T, C, false><<<blocks, rmb::EXACT_WARPS * 32, 0, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
+    }
+    return cudaGetLastError();
+}
+
 template <typename T>
 cudaError_t launch_exact_topk(const float* capx, T* cs, int* ci, int* cc, int C, int nb, int user0, const T* At, int p_pad, int p,
                               const T* Brow, size_t ldb, const T* bias, int* uflags, int K, cudaStream_t st)
 {
-    const int blocks = (nb + 3) / 4;
-    if (C == 256) rmb::exact_topk_kernel<T, 256><<<blocks, 128, 0, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
-    else if (C == 512) rmb::exact_topk_kernel<T, 512><<<blocks, 128, 0, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
-    else rmb::exact_topk_kernel<T, 1024><<<blocks, 128, 0, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
-    return cudaGetLastError();
+    if (C == 256) return launch_exact_topk_inst<T, 256>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, st);
+    if (C == 512) return launch_exact_topk_inst<T, 512>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, st);
+    return launch_exact_topk_inst<T, 1024>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, st);
 }
 
 // order the <= K survivors of every user (warp per user, bitonic network sized to K)

@@ -148,6 +148,27 @@ __device__ __noinline__ int approx_compact(float* cs, int* ci, const int nv, con
     return base;
 }
 
+// Slow path of the filter (a thread's group of 8 consecutive columns holds a score >= thr): drop padding columns and
+// train items (hpp:494-495), flag NaN scores (hpp:195-197), append the rest to the thread's own candidate buffer.
+__device__ __noinline__ int append_group(float* cs, int* ci, int cnt, const float thr, const int item0, const int n,
+                                         const bool has_train, const int* __restrict__ tri, const int tr_cur, const int tr_end, int* nanrow,
+                                         const float s0, const float s1, const float s2, const float s3,
+                                         const float s4, const float s5, const float s6, const float s7)
+{
+    const float s[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        if (!(s[j] < thr)) {
+            const int item = item0 + j;
+            if (item < n && !(has_train && in_train_segment(tri, tr_cur, tr_end, item))) {
+                if (s[j] != s[j]) *nanrow = 1;
+                else { cs[cnt] = s[j]; ci[cnt] = item; cnt++; }
+            }
+        }
+    }
+    return cnt;
+}
+
 template <int C>
 __global__ void __launch_bounds__(F_THREADS, 1)
 filter_select_kernel(const __grid_constant__ FilterParams P)
@@ -221,7 +242,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
         const float slack = ranked ? 2.f * 0.0084f * P.anorm[ul] * __uint_as_float(*P.maxbn) : 0.f;
         float thr = ranked ? -CUDART_INF_F : CUDART_INF_F;       // approx < thr: cannot be in the exact top K
         int cnt = 0;
-        bool overflowed = false, nanrow = false;
+        bool overflowed = false;
+        int nanrow = 0;
         float* cs = P.cand_approx + (size_t)ul * C;
         int* ci = P.cand_item + (size_t)ul * C;
         // the row's sorted train items (hpp:494-495 takes them out of the pool): cursor = first one >= the current tile
@@ -242,27 +264,26 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     __syncwarp();
                     if (lane == 0) mbar_arrive(bar_acce + 8 * b);
                 }
-                float mx[16];
+                // NaN-propagating max of each group of 8 columns; only groups holding a score >= thr are looked at
+                const int item_base = t * FN + c * F_CHUNK;
+                const bool has_train = nxt_train < tile_end;
+                bool any_pass = false;
 #pragma unroll
-                for (int j = 0; j < 16; j++) mx[j] = max_nan(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
-#pragma unroll
-                for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-                    for (int j = 0; j < w; j++) mx[j] = max_nan(mx[j], mx[j + w]);
-                if (__any_sync(FULL, !(mx[0] < thr))) {
-                    const int item_base = t * FN + c * F_CHUNK;
-                    const bool has_train = nxt_train < tile_end;
-#pragma unroll
-                    for (int j = 0; j < 32; j++) {
-                        const float s = __uint_as_float(v[j]);
-                        if (!(s < thr)) {
-                            const int item = item_base + j;
-                            if (item < P.n && !(has_train && in_train_segment(P.tri, tr_cur, tr_end, item))) {
-                                if (s != s) nanrow = true;             // NaN candidate score => NaN row (hpp:195-197)
-                                else { cs[cnt] = s; ci[cnt] = item; cnt++; }
-                            }
-                        }
+                for (int g = 0; g < 4; g++) {
+                    const float m01 = max_nan(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
+                    const float m23 = max_nan(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+                    const float m45 = max_nan(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+                    const float m67 = max_nan(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+                    const float m = max_nan(max_nan(m01, m23), max_nan(m45, m67));
+                    if (!(m < thr)) {
+                        cnt = append_group(cs, ci, cnt, thr, item_base + 8 * g, P.n, has_train, P.tri, tr_cur, tr_end, &nanrow,
+                                           __uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]),
+                                           __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]),
+                                           __uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+                        any_pass = true;
                     }
+                }
+                if (__any_sync(FULL, any_pass)) {
                     unsigned need = __ballot_sync(FULL, cnt > C - F_CHUNK);
                     while (need) {
                         const int r = __ffs(need) - 1;
@@ -303,22 +324,34 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 // factors, + bias: the chain of score_select_kernel / score_entries_kernel, so the values are bit-identical
 // to the FMA path), NaN scores raise the user's NaN flag (hpp:195-197), best K (score descending, ties by
 // ascending item id) left unordered at the head of cand_score / cand_item.
-template <typename T, int C>
-__global__ void exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_score, int* __restrict__ cand_item,
-                                  int* __restrict__ cand_count, const int mb, const int user0,
-                                  const T* __restrict__ At, const int p_pad, const int p,
-                                  const T* __restrict__ Brow, const size_t ldb, const T* __restrict__ bias,
-                                  int* __restrict__ uflags, const int K)
+// STAGED: the item-factor rows of 32 candidates at a time are fetched with coalesced loads into shared memory
+// (row stride p_pad + 1: conflict-free), then every lane runs the chain of its own candidate from there.
+constexpr int EXACT_WARPS = 4;
+inline size_t exact_topk_smem_bytes(int p_pad, size_t elem) { return (size_t)EXACT_WARPS * (32 * (size_t)(p_pad + 1) + p_pad) * elem; }
+
+template <typename T, int C, bool STAGED>
+__global__ void __launch_bounds__(EXACT_WARPS * 32)
+exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_score, int* __restrict__ cand_item,
+                  int* __restrict__ cand_count, const int mb, const int user0,
+                  const T* __restrict__ At, const int p_pad, const int p,
+                  const T* __restrict__ Brow, const size_t ldb, const T* __restrict__ bias,
+                  int* __restrict__ uflags, const int K)
 {
     typedef typename NumTraits<T>::key_t key_t;
     constexpr int E = C / 32;
-    const int lane = threadIdx.x & 31;
-    const int ul = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ul = blockIdx.x * EXACT_WARPS + warp;
     if (ul >= mb) return;
     const int nv = cand_count[ul];
     if (nv <= 0) return;
     const T* __restrict__ a = At + (size_t)(ul / BM) * p_pad * BM + (ul % BM);      // + k * BM
     const int* ci = cand_item + (size_t)ul * C;
+    T* rows = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (32 * (size_t)(p_pad + 1) + p_pad);   // [32][p_pad + 1]
+    T* a_sm = rows + 32 * (size_t)(p_pad + 1);                                                     // [p_pad]
+    if (STAGED) {
+        for (int k = lane; k < p; k += 32) a_sm[k] = a[(size_t)k * BM];
+        __syncwarp();
+    }
     key_t key[E];
     int it[E];
     int nanflag = 0;
@@ -327,16 +360,33 @@ __global__ void exact_topk_kernel(const float* __restrict__ cand_approx, T* __re
         const int idx = e * 32 + lane;
         key[e] = 0;
         it[e] = INT_MAX;
-        if (idx < nv) {
-            const int item = ci[idx];
-            it[e] = item;
-            const T* __restrict__ b = Brow + (size_t)item * ldb;
+        if (e * 32 < nv) {                       // warp-uniform
+            const bool valid = idx < nv;
+            const int item = valid ? ci[idx] : 0;
+            if (valid) it[e] = item;
             T acc = (T)0;
+            if (STAGED) {
+                for (int j = 0; j < 32; j++) {   // candidate j of this round: its factor row, 32 lanes wide
+                    const int item_j = __shfl_sync(FULL, item, j);
+                    const T* __restrict__ b = Brow + (size_t)item_j * ldb;
+                    T* dst = rows + (size_t)j * (p_pad + 1);
+                    for (int k = lane; k < p; k += 32) dst[k] = b[k];
+                }
+                __syncwarp();
+                const T* mine = rows + (size_t)lane * (p_pad + 1);
 #pragma unroll 8
-            for (int k = 0; k < p; k++) acc = NumTraits<T>::fma(a[(size_t)k * BM], b[k], acc);
-            if (bias != nullptr) acc += bias[item];
-            if (acc != acc) nanflag = 1;
-            else key[e] = NumTraits<T>::key(acc);
+                for (int k = 0; k < p; k++) acc = NumTraits<T>::fma(a_sm[k], mine[k], acc);
+                __syncwarp();
+            } else if (valid) {
+                const T* __restrict__ b = Brow + (size_t)item * ldb;
+#pragma unroll 8
+                for (int k = 0; k < p; k++) acc = NumTraits<T>::fma(a[(size_t)k * BM], b[k], acc);
+            }
+            if (valid) {
+                if (bias != nullptr) acc += bias[item];
+                if (acc != acc) nanflag = 1;
+                else key[e] = NumTraits<T>::key(acc);
+            }
         }
     }
     if (__any_sync(FULL, nanflag)) { if (lane == 0) atomicOr(&uflags[user0 + ul], 1); }
