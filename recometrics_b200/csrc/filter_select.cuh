@@ -9,9 +9,10 @@
 //      as the reference's front-end does, recometrics/__init__.py:548-551), fp32 accumulation in TMEM.
 //      A CTA keeps a 128-user A tile resident in shared memory and streams 128-item B tiles through a
 //      TMA ring; one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction) into one of
-//      two TMEM accumulator buffers; four epilogue warps read the other buffer with tcgen05.ld --
-//      thread t owns user row t (TMEM lane t), so the threshold, the counters, the train-row cursor and
-//      the candidate buffer of a user are private to one thread (no atomics, no shared state).
+//      two TMEM accumulator buffers; sixteen epilogue warps read the other buffer with tcgen05.ld: the four
+//      warps of a TMEM lane quarter (32 user rows) each take one 32-column chunk of the tile, so that four
+//      warps per scheduler hide each other's latencies; a quarter's per-row state (threshold, counter,
+//      train-row cursor) lives in shared memory and its warps meet at a named barrier once per tile.
 //      With m_u = c * ||a_u|| * max_j ||b_j|| >= |approx - exact| (bf16 rounding of both operands,
 //      Cauchy-Schwarz; prep.cuh) and tau~ = the K-th best APPROXIMATE candidate score seen so far, every
 //      member of the exact top K satisfies approx >= tau~ - 2 m_u (the K best approximate scores have
@@ -38,7 +39,7 @@
 namespace rmb {
 
 constexpr int FN = 128;                  // items per MMA tile = TMEM columns per accumulator buffer
-constexpr int F_EPI_WARPS = 4;           // 4 x 32 threads = 128 user rows = 128 TMEM lanes
+constexpr int F_EPI_WARPS = 16;          // warp w reads TMEM lanes (user rows) 32*(w%4)..+31, column chunk w/4 of every tile
 constexpr int F_THREADS = (F_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA warp
 constexpr int F_TMEM_COLS = 2 * FN;      // two accumulator buffers
 constexpr int F_MAX_STAGES = 4;
@@ -63,9 +64,15 @@ struct FilterParams {
     int K;
 };
 
+struct FilterRowState {      // per user row of the CTA, shared by the four epilogue warps of its TMEM lane quarter
+    float thr[BM], slack[BM];
+    int cnt[BM], flags[BM];          // flags: 1 = NaN candidate score, 2 = slack band overflowed the buffer
+    int nxt_train[BM], tr_cur[BM], tr_end[BM];
+};
+
 inline size_t filter_smem_bytes(int KB, int stages)
 {
-    return (size_t)(1 + stages) * KB * 128 * 2 + 256;
+    return (size_t)(1 + stages) * KB * 128 * 2 + 256 + sizeof(FilterRowState);
 }
 
 // ------------------------------------------------------------------ tcgen05 wrappers
@@ -148,25 +155,10 @@ __device__ __noinline__ int approx_compact(float* cs, int* ci, const int nv, con
     return base;
 }
 
-// Slow path of the filter (a thread's group of 8 consecutive columns holds a score >= thr): drop padding columns and
-// train items (hpp:494-495), flag NaN scores (hpp:195-197), append the rest to the thread's own candidate buffer.
-__device__ __noinline__ int append_group(float* cs, int* ci, int cnt, const float thr, const int item0, const int n,
-                                         const bool has_train, const int* __restrict__ tri, const int tr_cur, const int tr_end, int* nanrow,
-                                         const float s0, const float s1, const float s2, const float s3,
-                                         const float s4, const float s5, const float s6, const float s7)
+// train-row membership, out of line: only reached by a passing score in a tile the user's train row intersects
+__device__ __noinline__ bool train_hit(const int* __restrict__ tri, const int lo, const int hi, const int item)
 {
-    const float s[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        if (!(s[j] < thr)) {
-            const int item = item0 + j;
-            if (item < n && !(has_train && in_train_segment(tri, tr_cur, tr_end, item))) {
-                if (s[j] != s[j]) *nanrow = 1;
-                else { cs[cnt] = s[j]; ci[cnt] = item; cnt++; }
-            }
-        }
-    }
-    return cnt;
+    return in_train_segment(tri, lo, hi, item);
 }
 
 template <int C>
@@ -182,6 +174,7 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
     const unsigned bar_full = smem_u32(bars), bar_empty = bar_full + 8 * F_MAX_STAGES;
     const unsigned bar_accf = bar_empty + 8 * F_MAX_STAGES, bar_acce = bar_accf + 16, bar_a = bar_acce + 16;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * F_MAX_STAGES + 5);
+    FilterRowState* rs = reinterpret_cast<FilterRowState*>(reinterpret_cast<unsigned char*>(bars) + 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile_u0 = blockIdx.x * BM;
@@ -233,84 +226,105 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             }
         }
     } else {
-        // ===================== epilogue warps: thread <-> user row =====================
-        const int row = warp * 32 + lane;
+        // ===================== epilogue warps =====================
+        const int q = warp & 3, slot = warp >> 2;       // TMEM lane quarter, 32-column chunk of the tile
+        const int row = q * 32 + lane;                  // user row of this thread (shared with the 3 other slots)
         const int ul = tile_u0 + row;
-        const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0);
-        // |approx - exact| <= (2^-7 (1 + 2^-9) + k 2^-22) sum|a_k b_k| <= 0.0084 ||a|| ||b||: bf16 rounding of both
-        // operands (relative 2^-8 each), fp32 accumulation in the tensor core, fp32 rounding of the exact chain
-        const float slack = ranked ? 2.f * 0.0084f * P.anorm[ul] * __uint_as_float(*P.maxbn) : 0.f;
-        float thr = ranked ? -CUDART_INF_F : CUDART_INF_F;       // approx < thr: cannot be in the exact top K
-        int cnt = 0;
-        bool overflowed = false;
-        int nanrow = 0;
+        const unsigned qbar = 1 + q;                    // named barrier of the quarter's four warps
         float* cs = P.cand_approx + (size_t)ul * C;
         int* ci = P.cand_item + (size_t)ul * C;
-        // the row's sorted train items (hpp:494-495 takes them out of the pool): cursor = first one >= the current tile
-        int tr_cur = 0, tr_end = 0;
-        if (ranked) { tr_cur = P.trp[P.user0 + ul]; tr_end = P.trp[P.user0 + ul + 1]; }
-        int nxt_train = tr_cur < tr_end ? P.tri[tr_cur] : INT_MAX;
+        if (slot == 0) {
+            const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0);
+            // |approx - exact| <= (2^-7 (1 + 2^-9) + k 2^-22) sum|a_k b_k| <= 0.0084 ||a|| ||b||: bf16 rounding of both
+            // operands (relative 2^-8 each), fp32 accumulation in the tensor core, fp32 rounding of the exact chain
+            rs->slack[row] = ranked ? 2.f * 0.0084f * P.anorm[ul] * __uint_as_float(*P.maxbn) : 0.f;
+            rs->thr[row] = ranked ? -CUDART_INF_F : CUDART_INF_F;     // approx < thr: cannot be in the exact top K
+            rs->cnt[row] = 0;
+            rs->flags[row] = 0;
+            // the row's sorted train items (hpp:494-495 takes them out of the pool): cursor = first one >= the current tile
+            int cur = 0, end = 0;
+            if (ranked) { cur = P.trp[P.user0 + ul]; end = P.trp[P.user0 + ul + 1]; }
+            rs->tr_cur[row] = cur;
+            rs->tr_end[row] = end;
+            rs->nxt_train[row] = cur < end ? P.tri[cur] : INT_MAX;
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
 
         for (int t = 0; t < NT; t++) {
             const int b = t & 1;
             const int tile_end = (t + 1) * FN;
             mbar_wait(bar_accf + 8 * b, (t >> 1) & 1);
             tc_fence_after();
-            for (int c = 0; c < FN / F_CHUNK; c++) {
-                unsigned v[32];
-                tmem_ld32(tmem_base + ((unsigned)(warp * 32) << 16) + (unsigned)(b * FN + c * F_CHUNK), v);
-                if (c == FN / F_CHUNK - 1) {            // accumulator buffer fully read: hand it back to the MMA warp
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(bar_acce + 8 * b);
-                }
-                // NaN-propagating max of each group of 8 columns; only groups holding a score >= thr are looked at
-                const int item_base = t * FN + c * F_CHUNK;
-                const bool has_train = nxt_train < tile_end;
-                bool any_pass = false;
+            unsigned v[32];
+            tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(b * FN + slot * F_CHUNK), v);
+            tc_fence_before();                      // this warp's part of the accumulator is in registers
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_acce + 8 * b);
+
+            const float thr = rs->thr[row];
+            const int item_base = t * FN + slot * F_CHUNK;
+            const bool has_train = rs->nxt_train[row] < tile_end;
+            // NaN-propagating max of each group of 8 columns; only groups holding a score >= thr are looked at
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const float m01 = max_nan(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
-                    const float m23 = max_nan(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
-                    const float m45 = max_nan(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
-                    const float m67 = max_nan(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-                    const float m = max_nan(max_nan(m01, m23), max_nan(m45, m67));
-                    if (!(m < thr)) {
-                        cnt = append_group(cs, ci, cnt, thr, item_base + 8 * g, P.n, has_train, P.tri, tr_cur, tr_end, &nanrow,
-                                           __uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]),
-                                           __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]),
-                                           __uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-                        any_pass = true;
-                    }
-                }
-                if (__any_sync(FULL, any_pass)) {
-                    unsigned need = __ballot_sync(FULL, cnt > C - F_CHUNK);
-                    while (need) {
-                        const int r = __ffs(need) - 1;
-                        need &= need - 1;
-                        const size_t base = (size_t)(tile_u0 + warp * 32 + r) * C;
-                        float tau_r;
-                        const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, __shfl_sync(FULL, cnt, r), P.K,
-                                                           __shfl_sync(FULL, slack, r), lane, &tau_r);
-                        if (lane == r) {
-                            cnt = kept;
-                            thr = __fsub_rd(tau_r, slack);
-                            if (!(thr == thr)) thr = -CUDART_INF_F;          // non-finite bound: keep everything
-                            if (kept > C - F_CHUNK) { overflowed = true; thr = CUDART_INF_F; cnt = 0; }   // slack band does not fit
+            for (int g = 0; g < 4; g++) {
+                const float m01 = max_nan(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
+                const float m23 = max_nan(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+                const float m45 = max_nan(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+                const float m67 = max_nan(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+                const float m = max_nan(max_nan(m01, m23), max_nan(m45, m67));
+                if (!(m < thr)) {
+                    // slow path: drop padding columns and train items (hpp:494-495), flag NaN scores (hpp:195-197),
+                    // append the rest to the row's candidate buffer
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float s = __uint_as_float(v[8 * g + j]);
+                        if (!(s < thr)) {
+                            const int item = item_base + 8 * g + j;
+                            if (item < P.n && !(has_train && train_hit(P.tri, rs->tr_cur[row], rs->tr_end[row], item))) {
+                                if (s != s) rs->flags[row] = 1;
+                                else { const int at = atomicAdd(&rs->cnt[row], 1); cs[at] = s; ci[at] = item; }
+                            }
                         }
                     }
                 }
             }
-            // move the train cursor past this tile (rare)
-            if (nxt_train < tile_end) {
-                while (tr_cur < tr_end && (nxt_train = P.tri[tr_cur]) < tile_end) tr_cur++;
-                if (tr_cur >= tr_end) nxt_train = INT_MAX;
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");     // the quarter's four chunks of this tile are done
+            // rows whose buffer may not take another tile, rows whose train cursor has to move: the same masks in all four warps
+            unsigned need = __ballot_sync(FULL, rs->cnt[row] > C - FN);
+            const unsigned move = __ballot_sync(FULL, rs->nxt_train[row] < tile_end);
+            if (need | move) {
+                if (slot == 0 && rs->nxt_train[row] < tile_end) {
+                    int cur = rs->tr_cur[row], nxt = INT_MAX;
+                    const int end = rs->tr_end[row];
+                    while (cur < end && (nxt = P.tri[cur]) < tile_end) cur++;
+                    rs->tr_cur[row] = cur;
+                    rs->nxt_train[row] = cur < end ? nxt : INT_MAX;
+                }
+                while (need) {
+                    const int r = __ffs(need) - 1;
+                    need &= need - 1;
+                    if ((r & 3) != slot) continue;                         // the quarter's warps share the work
+                    const int rr = q * 32 + r;
+                    const size_t base = (size_t)(tile_u0 + rr) * C;
+                    float tau_r;
+                    const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, rs->cnt[rr], P.K, rs->slack[rr], lane, &tau_r);
+                    if (lane == 0) {
+                        float thr_r = __fsub_rd(tau_r, rs->slack[rr]);
+                        if (!(thr_r == thr_r)) thr_r = -CUDART_INF_F;       // non-finite bound: keep everything
+                        int cnt_r = kept;
+                        if (kept > C - FN) { rs->flags[rr] |= 2; thr_r = CUDART_INF_F; cnt_r = 0; }   // slack band does not fit
+                        rs->thr[rr] = thr_r;
+                        rs->cnt[rr] = cnt_r;
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
             }
         }
-        if (ul < P.mb) {
-            P.cand_count[ul] = overflowed ? -1 : (ranked ? cnt : 0);
-            if (overflowed) atomicAdd(P.overflow, 1);
-            if (nanrow && ranked) atomicOr(&P.uflags[P.user0 + ul], 1);
+        if (slot == 0 && ul < P.mb) {
+            const int fl = rs->flags[row];
+            P.cand_count[ul] = (fl & 2) ? -1 : rs->cnt[row];
+            if (fl & 2) atomicAdd(P.overflow, 1);
+            if (fl & 1) atomicOr(&P.uflags[P.user0 + ul], 1);
         }
     }
 
@@ -366,6 +380,7 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
             if (valid) it[e] = item;
             T acc = (T)0;
             if (STAGED) {
+#pragma unroll 8
                 for (int j = 0; j < 32; j++) {   // candidate j of this round: its factor row, 32 lanes wide
                     const int item_j = __shfl_sync(FULL, item, j);
                     const T* __restrict__ b = Brow + (size_t)item_j * ldb;
