@@ -236,12 +236,13 @@ def product_arm(args, cfg, rank, world, local_rank):
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches = 0.0, 0
+    kernel_ms, launches, path, fallbacks = 0.0, 0, 0, 0
     e0.record()
     for _ in range(args.steps):
         call(True, tm)
-        kernel_ms += tm.score_select_ms
+        kernel_ms += tm.dominant_kernel_ms
         launches += tm.kernel_launches
+        path, fallbacks = int(tm.scoring_path), fallbacks + int(tm.filter_fallback_batches)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -277,15 +278,32 @@ def product_arm(args, cfg, rank, world, local_rank):
             traffic = json.load(open(tpath)).get(str(cfg.cfg_id))
         except Exception:
             traffic = None
-    roofline = {
-        "bound": "fp32_fma" if T == np.float32 else "fp64_fma", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": ach / peak_tflops if peak_tflops > 0 else None, "traffic": traffic,
-        "kernel": "score_select_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
-        "kernel_share_of_step": kernel_ms / dev_ms if world == 1 else None,
-        "algorithmic_flops_per_step": flops, "launches_per_step": -(-m // (8 * 148 * 128)),
-        "peak_source": "FMA microbenchmark run live on this GPU (rmb200_measure_fma_peak): MEASURED_PEAKS.json holds "
-                       "HBM and bf16-tensor peaks only; nominal %s" % ("74.4 TFLOP/s FP32" if T == np.float32 else "37.2 TFLOP/s FP64"),
-    }
+    batches = -(-m // (8 * 148 * 128))
+    if path == 2:
+        # tensor-core filter: every (user, item) score is an MMA on bf16 copies of the factors; the measured
+        # denominator is the driver's cuBLAS bf16 figure (sustained: the kernel IS the long step)
+        try:
+            mp0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            tpeak, tsrc = float(mp0["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (of measured); burst %.1f" % mp0["bf16_tflops"]
+        except Exception:
+            tpeak, tsrc = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md; of fallback)"
+        roofline = {
+            "bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": traffic,
+            "kernel": "filter_select_kernel (tcgen05 bf16 candidate filter; survivors re-scored exactly in %s by exact_topk_kernel)" % ("fp32" if T == np.float32 else "fp64"),
+            "kernel_ms_per_step": kernel_ms / args.steps, "kernel_share_of_step": kernel_ms / dev_ms if world == 1 else None,
+            "algorithmic_flops_per_step": flops, "launches_per_step": batches, "peak_source": tsrc,
+            "fma_peak_tflops_live": peak_tflops, "filter_fallback_batches": fallbacks,
+        }
+    else:
+        roofline = {
+            "bound": "fp32_fma" if T == np.float32 else "fp64_fma", "achieved": ach, "peak": peak_tflops, "unit": "TFLOP/s",
+            "frac": ach / peak_tflops if peak_tflops > 0 else None, "traffic": traffic,
+            "kernel": "score_select_kernel", "kernel_ms_per_step": kernel_ms / args.steps,
+            "kernel_share_of_step": kernel_ms / dev_ms if world == 1 else None,
+            "algorithmic_flops_per_step": flops, "launches_per_step": batches,
+            "peak_source": "FMA microbenchmark run live on this GPU (rmb200_measure_fma_peak): MEASURED_PEAKS.json holds "
+                           "HBM and bf16-tensor peaks only; nominal %s" % ("74.4 TFLOP/s FP32" if T == np.float32 else "37.2 TFLOP/s FP64"),
+        }
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roofline["hbm_peak_gbs_measured"] = mp.get("hbm_gbs")
@@ -312,6 +330,7 @@ def product_arm(args, cfg, rank, world, local_rank):
                        "k_metrics": K, "metrics": list(cfg.metrics), "cumulative": bool(cfg.cumulative),
                        "l2": "inputs (A+B+CSR = %.0f MB) larger than the 126 MB L2; no flush" % (
                            (A.nbytes + B.nbytes + Xtr.indices.nbytes + Xte.indices.nbytes) / 1e6),
+                       "scoring_path": {1: "fma", 2: "tensor filter + exact re-score"}.get(path, "?"),
                        "parallelism": "users block-partitioned, B replicated, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),

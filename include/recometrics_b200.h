@@ -69,6 +69,7 @@ typedef struct rmb200_timing {
     int64_t h2d_bytes, d2h_bytes;
     int64_t scoring_path;   /* which scoring kernel ran: 1 = FMA tiles, 2 = tensor-core filter + exact re-score */
     int64_t filter_fallback_batches; /* user batches the tensor-core filter handed back to the FMA path         */
+    double dominant_kernel_ms; /* the scoring kernel alone (filter_select_kernel / score_select_kernel), all batches */
 } rmb200_timing_t;
 
 /* Optional extension block (pass NULL for reference behaviour).  Zero-initialise, then set

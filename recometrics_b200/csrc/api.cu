@@ -259,7 +259,7 @@ int run_call(const CallArgs<T>& a)
     std::lock_guard<std::mutex> lock(g_call_mutex);
     SignalLatch latch;
     cudaStream_t st = nullptr;   // legacy default stream: ordered after the caller's default-stream work
-    PhaseTimer pt(st);
+    PhaseTimer pt(st), pk(st);   // phases; the dominant scoring kernel alone
 
     // hpp:391-393
     int mip = a.min_items_pool < a.K ? a.K : a.min_items_pool;
@@ -294,7 +294,11 @@ int run_call(const CallArgs<T>& a)
     if (path_req == 2 && !tensor_ok) { set_err("unsupported", "scoring_path=tensor needs no ROC/PR-AUC (rank counting), k <= ~400 and k_metrics <= 256"); return RMB200_ERR_UNSUPPORTED; }
     const bool use_tensor = tensor_ok && path_req != 1;
     tm.scoring_path = use_tensor ? 2 : 1;
-    if (use_tensor) C = (K <= 32) ? 256 : (K <= 128 ? 512 : 1024);
+#ifndef RMB_F_CMID
+#define RMB_F_CMID 512
+#endif
+    if (use_tensor) C = (K <= 32) ? 256 : (K <= 128 ? RMB_F_CMID : 1024);
+    if (use_tensor && F_INTERVAL > 1) C = (K <= 32) ? 512 : 1024;
 
     // ---- CSR slices of users [ub, ue), index pointers re-based to the slice ----
     int lo_hi[4];   // trp[ub], trp[ue], tep[ub], tep[ue]
@@ -514,6 +518,7 @@ int run_call(const CallArgs<T>& a)
         }
         pt.stop(tm.prep_ms);
 
+        bool pk_pending = false;
         auto run_fma_batch = [&]() -> int {
             // fused score / exclude / select (/ rank counting) on the FMA pipe
             ScoreSelectParams<T> sp;
@@ -525,7 +530,10 @@ int run_call(const CallArgs<T>& a)
             sp.pos_sorted = count_ranks ? d_pos_sorted.as<T>() : nullptr;
             sp.auc_cnt = count_ranks ? d_auc.as<unsigned int>() : nullptr;
             sp.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
+            cudaEventRecord(pk.a, st);
             CK(launch_score_select<T>(sp, C, count_ranks, nb_pad / BM, st));
+            cudaEventRecord(pk.b, st);
+            pk_pending = true;
             tm.kernel_launches++;
             return RMB200_OK;
         };
@@ -550,7 +558,11 @@ int run_call(const CallArgs<T>& a)
             fp.trp = trp_d; fp.tri = tri_d; fp.ustatus = d_status.as<int>();
             fp.cand_approx = d_capx.as<float>(); fp.cand_item = d_ci.as<int>(); fp.cand_count = d_cc.as<int>();
             fp.overflow = d_overflow.as<int>(); fp.uflags = d_flags.as<int>(); fp.K = K;
+            fp.dbg = 0; if (const char* env = std::getenv("RMB200_DBG")) fp.dbg = std::atoi(env);
+            cudaEventRecord(pk.a, st);
             CK(launch_filter_select(fp, C, nb_pad / BM, st));
+            cudaEventRecord(pk.b, st);
+            pk_pending = true;
             tm.kernel_launches++;
             int n_over = 0;
             CK(cudaMemcpyAsync(&n_over, d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
@@ -579,6 +591,7 @@ int run_call(const CallArgs<T>& a)
         CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
         tm.kernel_launches++;
         pt.stop(tm.score_select_ms);
+        if (pk_pending) { float ms = 0; cudaEventElapsedTime(&ms, pk.a, pk.b); tm.dominant_kernel_ms += ms; }
         (void)batch_on_tensor;
 
         // per-user metrics

@@ -41,9 +41,18 @@ namespace rmb {
 constexpr int FN = 128;                  // items per MMA tile = TMEM columns per accumulator buffer
 constexpr int F_EPI_WARPS = 16;          // warp w reads TMEM lanes (user rows) 32*(w%4)..+31, column chunk w/4 of every tile
 constexpr int F_THREADS = (F_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA warp
-constexpr int F_TMEM_COLS = 2 * FN;      // two accumulator buffers
+#ifndef RMB_F_ACCBUFS
+#define RMB_F_ACCBUFS 4                  // TMEM accumulator buffers (2 or 4): slack between the MMA warp and the slowest epilogue warp
+#endif
+constexpr int F_ACCBUFS = RMB_F_ACCBUFS;
+constexpr int F_ACCSHIFT = F_ACCBUFS == 4 ? 2 : 1;
+constexpr int F_TMEM_COLS = F_ACCBUFS * FN;
 constexpr int F_MAX_STAGES = 4;
 constexpr int F_CHUNK = 32;              // TMEM columns per tcgen05.ld
+#ifndef RMB_F_INTERVAL
+#define RMB_F_INTERVAL 1                 // item tiles between two meetings of a quarter's warps (buffer check, train cursor)
+#endif
+constexpr int F_INTERVAL = RMB_F_INTERVAL;
 
 struct FilterParams {
     const __nv_bfloat16* __restrict__ Ab;   // [user tiles][KB/8][128][8]  bf16 user factors (+1.0 bias column)
@@ -62,6 +71,7 @@ struct FilterParams {
     int* overflow;                          // number of users flagged -1
     int* uflags;                            // [m] bit0: a candidate score was NaN
     int K;
+    int dbg;                                // developer switch (env RMB200_DBG): 1 = skip the scan (pipeline ceiling)
 };
 
 struct FilterRowState {      // per user row of the CTA, shared by the four epilogue warps of its TMEM lane quarter
@@ -155,10 +165,16 @@ __device__ __noinline__ int approx_compact(float* cs, int* ci, const int nv, con
     return base;
 }
 
-// train-row membership, out of line: only reached by a passing score in a tile the user's train row intersects
-__device__ __noinline__ bool train_hit(const int* __restrict__ tri, const int lo, const int hi, const int item)
+// train-row membership, out of line: only reached by a passing score in a tile the user's train row intersects.
+// tri[lo] is the first train item of the current tile: the few that follow inside the tile are scanned linearly.
+__device__ __noinline__ bool train_hit(const int* __restrict__ tri, int lo, const int hi, const int item)
 {
-    return in_train_segment(tri, lo, hi, item);
+    while (lo < hi) {
+        const int v = tri[lo];
+        if (v >= item) return v == item;
+        lo++;
+    }
+    return false;
 }
 
 template <int C>
@@ -170,10 +186,10 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
     unsigned char* a_tile = smem_raw;
     unsigned char* b_ring = a_tile + tile_bytes;
     u64* bars = reinterpret_cast<u64*>(b_ring + (size_t)S * tile_bytes);
-    // barriers: full[4], empty[4], acc_full[2], acc_empty[2], a_full
+    // barriers: full[4], empty[4], acc_full[4], acc_empty[4], a_full
     const unsigned bar_full = smem_u32(bars), bar_empty = bar_full + 8 * F_MAX_STAGES;
-    const unsigned bar_accf = bar_empty + 8 * F_MAX_STAGES, bar_acce = bar_accf + 16, bar_a = bar_acce + 16;
-    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * F_MAX_STAGES + 5);
+    const unsigned bar_accf = bar_empty + 8 * F_MAX_STAGES, bar_acce = bar_accf + 32, bar_a = bar_acce + 32;
+    unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * F_MAX_STAGES + 9);
     FilterRowState* rs = reinterpret_cast<FilterRowState*>(reinterpret_cast<unsigned char*>(bars) + 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -182,7 +198,7 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 
     if (tid == 0) {
         for (int s = 0; s < F_MAX_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < 2; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, F_EPI_WARPS); }
+        for (int b = 0; b < F_ACCBUFS; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, F_EPI_WARPS); }
         mbar_init(bar_a, 1);
         mbar_fence_init();
     }
@@ -214,8 +230,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(FN >> 3) << 17) | ((128u >> 4) << 24);
             mbar_wait(bar_a, 0);
             for (int t = 0; t < NT; t++) {
-                const int s = t % S, b = t & 1;
-                mbar_wait(bar_acce + 8 * b, ((t >> 1) & 1) ^ 1);          // accumulator buffer drained by the epilogue
+                const int s = t % S, b = t & (F_ACCBUFS - 1);
+                mbar_wait(bar_acce + 8 * b, ((t >> F_ACCSHIFT) & 1) ^ 1); // accumulator buffer drained by the epilogue
                 mbar_wait(bar_full + 8 * s, (t / S) & 1);                 // B tile landed
                 tc_fence_after();
                 const unsigned a0 = smem_u32(a_tile), b0 = smem_u32(b_ring + (size_t)s * tile_bytes);
@@ -251,9 +267,9 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
         asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
 
         for (int t = 0; t < NT; t++) {
-            const int b = t & 1;
-            const int tile_end = (t + 1) * FN;
-            mbar_wait(bar_accf + 8 * b, (t >> 1) & 1);
+            const int b = t & (F_ACCBUFS - 1);
+            const int tile_end = (t / F_INTERVAL + 1) * F_INTERVAL * FN;     // end of the interval this tile belongs to
+            mbar_wait(bar_accf + 8 * b, (t >> F_ACCSHIFT) & 1);
             tc_fence_after();
             unsigned v[32];
             tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(b * FN + slot * F_CHUNK), v);
@@ -261,6 +277,7 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_acce + 8 * b);
 
+            if (P.dbg & 1) continue;
             const float thr = rs->thr[row];
             const int item_base = t * FN + slot * F_CHUNK;
             const bool has_train = rs->nxt_train[row] < tile_end;
@@ -288,9 +305,10 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     }
                 }
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");     // the quarter's four chunks of this tile are done
-            // rows whose buffer may not take another tile, rows whose train cursor has to move: the same masks in all four warps
-            unsigned need = __ballot_sync(FULL, rs->cnt[row] > C - FN);
+            if ((t + 1) % F_INTERVAL != 0 && t + 1 < NT) continue;
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");     // the quarter's chunks of this interval are done
+            // rows whose buffer may not take another interval, rows whose train cursor has to move: the same masks in all four warps
+            unsigned need = __ballot_sync(FULL, rs->cnt[row] > C - F_INTERVAL * FN);
             const unsigned move = __ballot_sync(FULL, rs->nxt_train[row] < tile_end);
             if (need | move) {
                 if (slot == 0 && rs->nxt_train[row] < tile_end) {
@@ -312,7 +330,7 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                         float thr_r = __fsub_rd(tau_r, rs->slack[rr]);
                         if (!(thr_r == thr_r)) thr_r = -CUDART_INF_F;       // non-finite bound: keep everything
                         int cnt_r = kept;
-                        if (kept > C - FN) { rs->flags[rr] |= 2; thr_r = CUDART_INF_F; cnt_r = 0; }   // slack band does not fit
+                        if (kept > C - F_INTERVAL * FN) { rs->flags[rr] |= 2; thr_r = CUDART_INF_F; cnt_r = 0; }   // slack band does not fit
                         rs->thr[rr] = thr_r;
                         rs->cnt[rr] = cnt_r;
                     }
