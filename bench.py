@@ -237,11 +237,14 @@ def product_arm(args, cfg, rank, world, local_rank):
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, launches, path, fallbacks = 0.0, 0, 0, 0
+    phases = {}
     e0.record()
     for _ in range(args.steps):
         call(True, tm)
         kernel_ms += tm.dominant_kernel_ms
         launches += tm.kernel_launches
+        for f in ("total_ms", "prep_ms", "score_select_ms", "metrics_ms"):
+            phases[f] = phases.get(f, 0.0) + getattr(tm, f) / args.steps
         path, fallbacks = int(tm.scoring_path), fallbacks + int(tm.filter_fallback_batches)
     e1.record()
     barrier()
@@ -336,6 +339,7 @@ def product_arm(args, cfg, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_s * 1e3 / args.steps},
             "gpu_launches": int(launches), "clocks": clocks,
+            "phases_ms_per_step": {k: round(v, 3) for k, v in phases.items()},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -157,6 +157,9 @@ RMB200_API int rmb200_version(void);
 RMB200_API const char *rmb200_last_error(void);
 /* Ask a running call to stop at the next user-batch boundary (what SIGINT does). */
 RMB200_API void rmb200_request_interrupt(void);
+/* Device scratch (operand images, candidate buffers) is cached between calls; this returns it to the driver.
+ * RMB200_NO_POOL=1 in the environment disables the cache. */
+RMB200_API void rmb200_release_workspace(void);
 /* Measured FP32 / FP64 FMA throughput of `device` in TFLOP/s (register-resident FMA chains on all
  * SMs; the roofline denominator for the scoring kernel).  dtype_bytes = 4 or 8.  <0 on error. */
 RMB200_API double rmb200_measure_fma_peak(int device, int dtype_bytes, double *elapsed_ms);

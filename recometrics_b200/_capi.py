@@ -23,7 +23,7 @@ EXPORTS = (
     "rmb200_calc_metrics_f32", "rmb200_calc_metrics_f64",
     "rmb200_calc_metrics_ex_f32", "rmb200_calc_metrics_ex_f64",
     "rmb200_device_count", "rmb200_version", "rmb200_last_error",
-    "rmb200_request_interrupt", "rmb200_measure_fma_peak",
+    "rmb200_request_interrupt", "rmb200_measure_fma_peak", "rmb200_release_workspace",
 )
 
 
@@ -76,6 +76,7 @@ def load():
     lib.rmb200_version.restype = ctypes.c_int
     lib.rmb200_last_error.restype = ctypes.c_char_p
     lib.rmb200_request_interrupt.restype = None
+    lib.rmb200_release_workspace.restype = None
     lib.rmb200_measure_fma_peak.restype = ctypes.c_double
     lib.rmb200_measure_fma_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     for name in EXPORTS[:4]:
@@ -86,6 +87,11 @@ def load():
 
 def device_count():
     return int(load().rmb200_device_count())
+
+
+def release_workspace():
+    """Give the device scratch cached between calls back to the driver."""
+    load().rmb200_release_workspace()
 
 
 def last_error():

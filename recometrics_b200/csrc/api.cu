@@ -56,18 +56,74 @@ struct SignalLatch {
     ~SignalLatch() { restore(); }
 };
 
+// Device workspace cache: a call needs a few GB of scratch (operand images, candidate buffers); cudaMalloc / cudaFree
+// of those cost tens of milliseconds per call and synchronise the device, so released blocks are kept for the next
+// call (rmb200_release_workspace() or RMB200_NO_POOL=1 gives them back).
+struct PoolEntry { void* p; size_t bytes; int dev; bool in_use; };
+std::vector<PoolEntry> g_pool;
+std::mutex g_pool_mutex;
+
+bool pool_enabled()
+{
+    static const bool on = []() { const char* e = std::getenv("RMB200_NO_POOL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+void pool_trim_locked(int dev_only)
+{
+    for (size_t i = 0; i < g_pool.size();) {
+        if (!g_pool[i].in_use && (dev_only < 0 || g_pool[i].dev == dev_only)) {
+            cudaFree(g_pool[i].p);
+            g_pool[i] = g_pool.back();
+            g_pool.pop_back();
+        } else i++;
+    }
+}
+
+cudaError_t pool_alloc(void** out, size_t bytes)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    if (pool_enabled()) {
+        int best = -1;
+        for (size_t i = 0; i < g_pool.size(); i++) {
+            const PoolEntry& e = g_pool[i];
+            if (e.in_use || e.dev != dev || e.bytes < bytes || e.bytes > bytes + bytes / 4 + (1u << 20)) continue;
+            if (best < 0 || e.bytes < g_pool[best].bytes) best = (int)i;
+        }
+        if (best >= 0) { g_pool[best].in_use = true; *out = g_pool[best].p; return cudaSuccess; }
+    }
+    cudaError_t e = cudaMalloc(out, bytes);
+    if (e == cudaErrorMemoryAllocation) {           // give cached blocks back and try once more
+        cudaGetLastError();
+        pool_trim_locked(dev);
+        e = cudaMalloc(out, bytes);
+    }
+    if (e == cudaSuccess && pool_enabled()) g_pool.push_back(PoolEntry{*out, bytes, dev, true});
+    return e;
+}
+
+void pool_free(void* p)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    for (auto& e : g_pool)
+        if (e.p == p) { e.in_use = false; return; }
+    cudaFree(p);
+}
+
 struct DevBuf {
     void* p = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
     ~DevBuf() { release(); }
-    void release() { if (p) { cudaFree(p); p = nullptr; } }
+    void release() { if (p) { pool_free(p); p = nullptr; } }
     cudaError_t alloc(size_t bytes)
     {
         release();
         if (bytes == 0) bytes = 16;
-        return cudaMalloc(&p, bytes);
+        return pool_alloc(&p, bytes);
     }
     template <typename U> U* as() const { return reinterpret_cast<U*>(p); }
 };
@@ -772,6 +828,12 @@ int rmb200_version(void) { return RMB200_VERSION; }
 const char* rmb200_last_error(void) { return g_err.c_str(); }
 
 void rmb200_request_interrupt(void) { g_interrupt.store(1); }
+
+void rmb200_release_workspace(void)
+{
+    std::lock_guard<std::mutex> lk(g_pool_mutex);
+    pool_trim_locked(-1);
+}
 
 double rmb200_measure_fma_peak(int device, int dtype_bytes, double* elapsed_ms)
 {

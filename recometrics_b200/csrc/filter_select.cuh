@@ -338,6 +338,18 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
             }
         }
+        // last cut: hand the exact stage only what can still be in the top K
+        for (int r = slot; r < 32; r += 4) {
+            const int rr = q * 32 + r;
+            const int nv = rs->cnt[rr];
+            if (nv > P.K && !(rs->flags[rr] & 2)) {
+                const size_t base = (size_t)(tile_u0 + rr) * C;
+                float tau_r;
+                const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, nv, P.K, rs->slack[rr], lane, &tau_r);
+                if (lane == 0) rs->cnt[rr] = kept;
+            }
+        }
+        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
         if (slot == 0 && ul < P.mb) {
             const int fl = rs->flags[row];
             P.cand_count[ul] = (fl & 2) ? -1 : rs->cnt[row];
@@ -359,6 +371,14 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 // STAGED: the item-factor rows of 32 candidates at a time are fetched with coalesced loads into shared memory
 // (row stride p_pad + 1: conflict-free), then every lane runs the chain of its own candidate from there.
 constexpr int EXACT_WARPS = 4;
+__device__ __forceinline__ void cp_async_elem(float* dst, const float* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_elem(double* dst, const double* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
 inline size_t exact_topk_smem_bytes(int p_pad, size_t elem) { return (size_t)EXACT_WARPS * (32 * (size_t)(p_pad + 1) + p_pad) * elem; }
 
 template <typename T, int C, bool STAGED>
@@ -398,13 +418,15 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
             if (valid) it[e] = item;
             T acc = (T)0;
             if (STAGED) {
-#pragma unroll 8
-                for (int j = 0; j < 32; j++) {   // candidate j of this round: its factor row, 32 lanes wide
+                // candidate j of this round: its factor row, 32 lanes wide, straight into shared memory (cp.async: all
+                // 32 rows are in flight at once, no registers in between)
+                for (int j = 0; j < 32; j++) {
                     const int item_j = __shfl_sync(FULL, item, j);
                     const T* __restrict__ b = Brow + (size_t)item_j * ldb;
                     T* dst = rows + (size_t)j * (p_pad + 1);
-                    for (int k = lane; k < p; k += 32) dst[k] = b[k];
+                    for (int k = lane; k < p; k += 32) cp_async_elem(dst + k, b + k);
                 }
+                asm volatile("cp.async.wait_all;" ::: "memory");
                 __syncwarp();
                 const T* mine = rows + (size_t)lane * (p_pad + 1);
 #pragma unroll 8
