@@ -70,6 +70,7 @@ typedef struct rmb200_timing {
     int64_t scoring_path;   /* which scoring kernel ran: 1 = FMA tiles, 2 = tensor-core filter + exact re-score */
     int64_t filter_fallback_batches; /* user batches the tensor-core filter handed back to the FMA path         */
     double dominant_kernel_ms; /* the scoring kernel alone (filter_select_kernel / score_select_kernel), all batches */
+    int64_t filter_retry_rows; /* users whose sampled threshold guess failed its check (their CTA walked the catalogue twice) */
 } rmb200_timing_t;
 
 /* Optional extension block (pass NULL for reference behaviour).  Zero-initialise, then set

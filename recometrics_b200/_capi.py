@@ -33,7 +33,7 @@ class Timing(ctypes.Structure):
         ("score_select_ms", ctypes.c_double), ("metrics_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
         ("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
         ("scoring_path", ctypes.c_int64), ("filter_fallback_batches", ctypes.c_int64),
-        ("dominant_kernel_ms", ctypes.c_double),
+        ("dominant_kernel_ms", ctypes.c_double), ("filter_retry_rows", ctypes.c_int64),
     ]
 
     def as_dict(self):

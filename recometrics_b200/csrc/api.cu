@@ -339,7 +339,7 @@ int run_call(const CallArgs<T>& a)
     if (path_req == 0) if (const char* env = std::getenv("RMB200_PATH")) {
         if (!std::strcmp(env, "fma")) path_req = 1; else if (!std::strcmp(env, "tensor")) path_req = 2;
     }
-    const int KB = round_up(a.k + (a.bias ? 1 : 0), 16);            // bf16 factors per row (bias = one more factor)
+    const int KB = round_up(a.k + (a.bias ? 1 : 0), 16);            // fp16 factors per row (bias = one more factor)
     int f_stages = 0;
     {
         const long long tile = (long long)KB * 256, budget = 225 * 1024;
@@ -354,7 +354,6 @@ int run_call(const CallArgs<T>& a)
 #define RMB_F_CMID 512
 #endif
     if (use_tensor) C = (K <= 32) ? 256 : (K <= 128 ? RMB_F_CMID : 1024);
-    if (use_tensor && F_INTERVAL > 1) C = (K <= 32) ? 512 : 1024;
 
     // ---- CSR slices of users [ub, ue), index pointers re-based to the slice ----
     int lo_hi[4];   // trp[ub], trp[ue], tep[ub], tep[ue]
@@ -458,15 +457,15 @@ int run_call(const CallArgs<T>& a)
     }
     const int n_pad128 = round_up(a.n, 128);
     if (use_tensor) {
-        CK(d_Bb.alloc((size_t)n_pad128 * KB * sizeof(__nv_bfloat16)));
+        CK(d_Bb.alloc((size_t)n_pad128 * KB * sizeof(__half)));
         CK(d_maxbn.alloc(sizeof(unsigned)));
         pt.start();
         CK(cudaMemsetAsync(d_maxbn.p, 0, sizeof(unsigned), st));
         const long long total = (long long)n_pad128 * (KB / 8);
-        pack_bf16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0,
-                                                                             d_Bb.as<__nv_bfloat16>(), n_pad128, KB);
-        CK(cudaGetLastError());
         row_norm_kernel<T><<<(a.n + 7) / 8, 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0, nullptr, d_maxbn.as<unsigned>());
+        CK(cudaGetLastError());
+        pack_f16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0, nullptr, d_maxbn.as<unsigned>(),
+                                                                            d_Bb.as<__half>(), n_pad128, KB);
         CK(cudaGetLastError());
         tm.kernel_launches += 2;
         pt.stop(tm.prep_ms);
@@ -524,11 +523,35 @@ int run_call(const CallArgs<T>& a)
     DevBuf d_At, d_Arow, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
     CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
     DevBuf d_capx, d_overflow;
+    // sampled threshold guess of the filter (filter_select.cuh, pass 0): every stride-th item tile, about 7/K of the
+    // catalogue (1/16 .. 1/8); the guess is the r-th best of the sample with r = the smallest rank for which
+    // P(Poisson(K * sample / n) >= r) <= 1e-6, i.e. fewer than K items of the whole catalogue reach it about once
+    // in a million users (those users' CTAs walk the catalogue a second time; results never depend on the guess)
+    int f_sample_tiles = 0, f_sample_stride = 1, f_sample_rank = 0;
     if (use_tensor) {
-        CK(d_Ab.alloc((size_t)UB * KB * sizeof(__nv_bfloat16)));
+        const int NT = (a.n + 127) / 128;
+        bool on = NT >= 512;
+        if (const char* env = std::getenv("RMB200_SAMPLE")) on = on && std::atoi(env) != 0;
+        if (on) {
+            double frac = 7.0 / K;
+            if (frac < 1.0 / 16) frac = 1.0 / 16;
+            if (frac > 1.0 / 8) frac = 1.0 / 8;
+            int stride = (int)(1.0 / frac);
+            if (const char* env = std::getenv("RMB200_SAMPLE_STRIDE")) { const int v = std::atoi(env); if (v >= 2) stride = v; }
+            const int ns = NT / stride;                                  // tiles 0, stride, ..., (ns-1)*stride: all full tiles
+            const double lam = (double)K * ((double)ns * 128.0) / (double)a.n;
+            double term = std::exp(-lam), cdf = 0.0;                     // P(X <= r-1), X ~ Poisson(lam)
+            int r = 0;
+            while (r < 4096) { cdf += term; r++; term *= lam / r; if (1.0 - cdf <= 1e-6) break; }
+            if (const char* env = std::getenv("RMB200_SAMPLE_RANK")) { const int v = std::atoi(env); if (v >= 1) r = v; }
+            if (ns >= 8 && r + 128 <= C - 128) { f_sample_tiles = ns; f_sample_stride = stride; f_sample_rank = r; }
+        }
+    }
+    if (use_tensor) {
+        CK(d_Ab.alloc((size_t)UB * KB * sizeof(__half)));
         CK(d_anorm.alloc((size_t)UB * sizeof(float)));
         CK(d_capx.alloc((size_t)UB * C * sizeof(float)));
-        CK(d_overflow.alloc(sizeof(int)));
+        CK(d_overflow.alloc(8 * sizeof(int)));     // [0] users whose slack band overflowed, [1] users that took the retry pass
     }
     if (!on_dev) CK(d_Arow.alloc((size_t)UB * a.k * sizeof(T)));
     CK(d_cs.alloc((size_t)UB * C * sizeof(T)));
@@ -595,34 +618,43 @@ int run_call(const CallArgs<T>& a)
         };
         bool batch_on_tensor = use_tensor;
         if (use_tensor) {
-            // bf16 operand image + norms of the batch's users, then the tensor-core filter and the exact re-scoring
+            // norms + fp16 operand image of the batch's users, then the tensor-core filter and the exact re-scoring
             pt.start();
             const long long total = (long long)nb_pad * (KB / 8);
-            pack_bf16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
-                                                                                 d_Ab.as<__nv_bfloat16>(), nb_pad, KB);
-            CK(cudaGetLastError());
             row_norm_kernel<T><<<(nb + 7) / 8, 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0, d_anorm.as<float>(), nullptr);
             CK(cudaGetLastError());
-            CK(cudaMemsetAsync(d_overflow.p, 0, sizeof(int), st));
+            pack_f16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
+                                                                                d_anorm.as<float>(), nullptr, d_Ab.as<__half>(), nb_pad, KB);
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(d_overflow.p, 0, 8 * sizeof(int), st));
             tm.kernel_launches += 2;
             pt.stop(tm.prep_ms);
             pt.start();
             FilterParams fp;
-            fp.Ab = d_Ab.as<__nv_bfloat16>(); fp.Bb = d_Bb.as<__nv_bfloat16>(); fp.KB = KB; fp.stages = f_stages;
+            fp.Ab = d_Ab.as<__half>(); fp.Bb = d_Bb.as<__half>(); fp.KB = KB; fp.err_coef = filter_err_coef(KB); fp.stages = f_stages;
             fp.n = a.n; fp.mb = nb; fp.user0 = b0;
             fp.anorm = d_anorm.as<float>(); fp.maxbn = d_maxbn.as<unsigned>();
             fp.trp = trp_d; fp.tri = tri_d; fp.ustatus = d_status.as<int>();
             fp.cand_approx = d_capx.as<float>(); fp.cand_item = d_ci.as<int>(); fp.cand_count = d_cc.as<int>();
             fp.overflow = d_overflow.as<int>(); fp.uflags = d_flags.as<int>(); fp.K = K;
+            fp.sample_tiles = f_sample_tiles; fp.sample_stride = f_sample_stride; fp.sample_rank = f_sample_rank;
+            fp.retries = d_overflow.as<int>() + 1;
             fp.dbg = 0; if (const char* env = std::getenv("RMB200_DBG")) fp.dbg = std::atoi(env);
             cudaEventRecord(pk.a, st);
             CK(launch_filter_select(fp, C, nb_pad / BM, st));
             cudaEventRecord(pk.b, st);
             pk_pending = true;
             tm.kernel_launches++;
-            int n_over = 0;
-            CK(cudaMemcpyAsync(&n_over, d_overflow.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            int over_retry[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            CK(cudaMemcpyAsync(over_retry, d_overflow.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
+#if RMB_F_STATS
+            std::fprintf(stderr, "[rmb200 stats] users %d: appends/user %.1f cuts/user %.2f slow-path entries/user %.1f cursor moves/user %.1f retries %d (sample tiles %d stride %d rank %d)\n",
+                         nb, over_retry[2] / (double)nb, over_retry[3] / (double)nb, over_retry[4] / (double)nb, over_retry[5] / (double)nb,
+                         over_retry[1], f_sample_tiles, f_sample_stride, f_sample_rank);
+#endif
+            const int n_over = over_retry[0];
+            tm.filter_retry_rows += over_retry[1];
             if (n_over > 0) {
                 // some user's slack band did not fit its candidate buffer (near-constant scores): the whole batch
                 // goes through the FMA path instead -- slower, same results

@@ -33,7 +33,8 @@
 // rows).  The pack kernel writes tiles in exactly this image, so one bulk copy per tile lands it.
 // Encodings pinned on hardware by tools/ubench/umma_probe.cu.
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include "prep.cuh"
 #include "score_select.cuh"
 
 namespace rmb {
@@ -49,15 +50,21 @@ constexpr int F_ACCSHIFT = F_ACCBUFS == 4 ? 2 : 1;
 constexpr int F_TMEM_COLS = F_ACCBUFS * FN;
 constexpr int F_MAX_STAGES = 4;
 constexpr int F_CHUNK = 32;              // TMEM columns per tcgen05.ld
-#ifndef RMB_F_INTERVAL
-#define RMB_F_INTERVAL 1                 // item tiles between two meetings of a quarter's warps (buffer check, train cursor)
+
+#ifndef RMB_F_STATS
+#define RMB_F_STATS 0                    // developer build: count appends / cuts / slow-path entries / cursor moves into FilterParams::retries[1..4]
 #endif
-constexpr int F_INTERVAL = RMB_F_INTERVAL;
+#if RMB_F_STATS
+#define F_STAT(i, v) atomicAdd(&rs->stat[i], (v))
+#else
+#define F_STAT(i, v) do { } while (0)
+#endif
 
 struct FilterParams {
-    const __nv_bfloat16* __restrict__ Ab;   // [user tiles][KB/8][128][8]  bf16 user factors (+1.0 bias column)
-    const __nv_bfloat16* __restrict__ Bb;   // [item tiles][KB/8][128][8]  bf16 item factors (+bias column)
-    int KB;                                 // bf16 factors per row, multiple of 16
+    const __half* __restrict__ Ab;          // [user tiles][KB/8][128][8]  fp16 user factors (+1.0 bias column), each row scaled by pow2_scale_for(||a_u||)
+    const __half* __restrict__ Bb;          // [item tiles][KB/8][128][8]  fp16 item factors (+bias column), all scaled by pow2_scale_for(max_j ||b_j||)
+    int KB;                                 // fp16 factors per row, multiple of 16
+    float err_coef;                         // c: |approx - exact| <= c ||a|| max||b|| (host: filter_err_coef)
     int stages;                             // depth of the B ring
     int n, mb, user0;
     const float* __restrict__ anorm;        // [mb] ||a_u|| (with the 1.0 bias component), rounded up
@@ -71,14 +78,31 @@ struct FilterParams {
     int* overflow;                          // number of users flagged -1
     int* uflags;                            // [m] bit0: a candidate score was NaN
     int K;
-    int dbg;                                // developer switch (env RMB200_DBG): 1 = skip the scan (pipeline ceiling)
+    int sample_tiles, sample_stride, sample_rank;   // pass 0 (see filter_pass_tile); sample_tiles == 0: no sampling
+    int* retries;                           // rows that needed the retry pass (statistics; may be nullptr)
+    int dbg;                                // developer switch (env RMB200_DBG): 1 = skip the scan (pipeline ceiling), 2 = no row is ranked (fast path only), 4 = no per-tile meeting, 8 = no tcgen05.ld
 };
 
 struct FilterRowState {      // per user row of the CTA, shared by the four epilogue warps of its TMEM lane quarter
-    float thr[BM], slack[BM];
-    int cnt[BM], flags[BM];          // flags: 1 = NaN candidate score, 2 = slack band overflowed the buffer
-    int nxt_train[BM], tr_cur[BM], tr_end[BM];
+    float thr[BM], slack[BM], guess[BM];
+    int cnt[BM], flags[BM];          // flags: 1 = NaN candidate score, 2 = slack band overflowed the buffer, 4 = guess failed (retry pass)
+    int retry;                       // some row of the CTA needs the retry pass
+    int stat[4];                     // RMB_F_STATS: appends, cuts, slow-path entries (8-column groups), cursor moves
+    int nxt_train[BM], nxt2_train[BM], tr_cur[BM], tr_end[BM];   // next train item id, the one after it (prefetched), cursor, row end
+    unsigned hist[F_EPI_WARPS][32];  // bucket counters of approx_compact_hist, one set per epilogue warp
 };
+
+// Error bound of the filter's approximate scores, as a multiple of ||a_u|| max_j ||b_j||:
+//   fp16 rounding of both operands (scaled so that |x| <= 1; relative 2^-11 each, absolute 2^-25 below 6e-5):
+//       sum_k |a_k b_k| (2^-10 + 2^-22) + 2^-25 sqrt(k) (||a|| + ||b||)   <=  (2^-10 (1 + 2^-10) + 4 sqrt(k) 2^-24) ||a|| ||b||
+//       (Cauchy-Schwarz; the scaled norms are >= 0.5, hence the factor 4 on the absolute term)
+//   fp32 accumulation inside the tensor core plus the rounding of the exact fp32 fma chain it is compared with: k 2^-22
+// and 1 % on top.
+inline float filter_err_coef(int KB)
+{
+    const double c = std::ldexp(1.0, -10) * (1.0 + std::ldexp(1.0, -10)) + 4.0 * std::sqrt((double)KB) * std::ldexp(1.0, -24) + KB * std::ldexp(1.0, -22);
+    return (float)(1.01 * c);
+}
 
 inline size_t filter_smem_bytes(int KB, int stages)
 {
@@ -91,7 +115,10 @@ __device__ __forceinline__ uint64_t umma_desc(const unsigned saddr)
     // K-major, no swizzle: LBO = 128 rows * 16 B = 2048 (>>4 = 128), SBO = 128 B (>>4 = 8), version 1
     return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)128 << 16) | ((uint64_t)8 << 32) | (1ull << 46);
 }
-__device__ __forceinline__ void umma_bf16(const unsigned tmem_d, const uint64_t adesc, const uint64_t bdesc,
+// the same descriptor `bytes` further into the tile: only the 14-bit address field (bytes >> 4) of the low word moves
+// (shared-memory addresses stay below 2^18, so the field cannot carry into the LBO field)
+__device__ __forceinline__ uint64_t umma_desc_advance(const uint64_t desc, const unsigned bytes) { return desc + (uint64_t)(bytes >> 4); }
+__device__ __forceinline__ void umma_f16(const unsigned tmem_d, const uint64_t adesc, const uint64_t bdesc,
                                           const unsigned idesc, const unsigned accumulate)
 {
     asm volatile(
@@ -102,6 +129,13 @@ __device__ __forceinline__ void umma_bf16(const unsigned tmem_d, const uint64_t 
 __device__ __forceinline__ void umma_commit(const unsigned bar)
 {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// one lane of a converged warp (elect.sync): the compiler keeps what the elected lane computes in uniform registers
+__device__ __forceinline__ bool elect_one()
+{
+    unsigned pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -165,6 +199,80 @@ __device__ __noinline__ int approx_compact(float* cs, int* ci, const int nv, con
     return base;
 }
 
+// The same cut, cheaper: instead of the K-th best key bit by bit (32 dependent warp reductions), ROUNDS rounds of a
+// 32-bucket histogram (shared-memory counters, one bucket per lane, suffix sums by shuffles) narrow a window of the
+// key range that holds it.  The window's lower edge `lo` always satisfies #(key >= lo) >= K, so it is a valid (slightly
+// low: window width = key range / 32^ROUNDS) stand-in for the K-th best approximate score; ROUNDS = 7 makes it exact.
+#ifndef RMB_F_HIST_ROUNDS
+#define RMB_F_HIST_ROUNDS 2
+#endif
+template <int C, int ROUNDS>
+__device__ __noinline__ int approx_compact_hist(float* cs, int* ci, const int nv, const int K, const float slack, const int lane,
+                                                unsigned* hist, float* tau_out)
+{
+    constexpr int E = C / 32;
+    unsigned key[E];
+    int it[E];
+    unsigned kmax = 0u, kmin = 0xffffffffu;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const int idx = e * 32 + lane;
+        const bool v = idx < nv;
+        key[e] = v ? NumTraits<float>::key(cs[idx]) : 0u;      // 0 sorts below every score
+        it[e] = v ? ci[idx] : INT_MAX;
+        if (v) { kmax = max(kmax, key[e]); kmin = min(kmin, key[e]); }
+    }
+    kmax = __reduce_max_sync(FULL, kmax);
+    kmin = __reduce_min_sync(FULL, kmin);
+    unsigned lo = kmin, span = kmax - kmin;     // window [lo, lo + span]; the need-th largest key inside it is wanted
+    int need = K;
+#pragma unroll 1
+    for (int round = 0; round < ROUNDS; round++) {
+        const int sh = max(0, 27 - __clz(span));               // (key - lo) >> sh < 32 inside the window
+        hist[lane] = 0u;
+        __syncwarp();
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            const unsigned d = key[e] - lo;
+            if (key[e] >= lo && d <= span) atomicAdd(&hist[d >> sh], 1u);
+        }
+        __syncwarp();
+        unsigned suf = hist[lane];                             // -> number of window keys in buckets >= lane
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_down_sync(FULL, suf, o);
+            if (lane + o < 32) suf += t;
+        }
+        const unsigned mask = __ballot_sync(FULL, (int)suf >= need);   // lane 0 always votes: the window holds >= need keys
+        const int b = 31 - __clz(mask);
+        const unsigned above = __shfl_sync(FULL, suf, (b + 1) & 31);
+        if (b < 31) need -= (int)above;
+        const unsigned off = (unsigned)b << sh;
+        lo += off;
+        span = min(span - off, (1u << sh) - 1u);
+        if (sh == 0) break;
+    }
+    const float tau = NumTraits<float>::from_orderable((u64)lo);
+    const float cutf = __fsub_rd(tau, slack);                   // NaN (tau or slack not finite): keep everything
+    const unsigned cut = (cutf == cutf) ? NumTraits<float>::key(cutf) : 1u;
+    int base = 0;
+    __syncwarp();
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const bool keep = key[e] >= cut && key[e] != 0u;
+        const unsigned mask = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+            cs[pos] = NumTraits<float>::from_orderable((u64)key[e]);
+            ci[pos] = it[e];
+        }
+        base += __popc(mask);
+    }
+    *tau_out = tau;
+    __syncwarp();
+    return base;
+}
+
 // train-row membership, out of line: only reached by a passing score in a tile the user's train row intersects.
 // tri[lo] is the first train item of the current tile: the few that follow inside the tile are scanned linearly.
 __device__ __noinline__ bool train_hit(const int* __restrict__ tri, int lo, const int hi, const int item)
@@ -176,6 +284,21 @@ __device__ __noinline__ bool train_hit(const int* __restrict__ tri, int lo, cons
     }
     return false;
 }
+
+// The item tiles a CTA walks, pass by pass (all roles -- TMA producer, MMA issuer, epilogue -- step through the same list):
+//   pass 0  SAMPLE  every sample_stride-th tile (sample_tiles of them, ~1/16 of the catalogue; skipped when sample_tiles == 0).
+//                   The rows run the same streaming selection with K = sample_rank and no slack; the sample_rank-th best
+//                   approximate score of the sample becomes the row's GUESS g: with sample_rank chosen by the host so that
+//                   P(fewer than K of ALL items reach the sample's sample_rank-th best) <= 1e-6 per row.
+//   pass 1  MAIN    every tile, thresholds start at g - slack instead of -inf.  A streaming top-K appends K' (1 + ln(n / K'))
+//                   candidates per row, more than half of them in the first percent of the catalogue while the threshold is
+//                   still loose; starting from the guess leaves about (items >= g - slack) appends, 3x fewer at 1M items.
+//                   The guess is VERIFIED: the pass is valid for a row iff at least K of its kept candidates reach g
+//                   (then the K-th best approximate score tau~ >= g and everything >= tau~ - slack was kept).
+//   pass 2  RETRY   only if some row of the CTA failed the check (or had too few sample candidates): every tile again,
+//                   failed rows from -inf, the others closed.  Costs the CTA a second walk; never changes a result.
+__device__ __forceinline__ int filter_pass_tiles(const FilterParams& P, const int pass, const int NT) { return pass == 0 ? P.sample_tiles : NT; }
+__device__ __forceinline__ int filter_pass_tile(const FilterParams& P, const int pass, const int j) { return pass == 0 ? j * P.sample_stride : j; }
 
 template <int C>
 __global__ void __launch_bounds__(F_THREADS, 1)
@@ -201,6 +324,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
         for (int b = 0; b < F_ACCBUFS; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, F_EPI_WARPS); }
         mbar_init(bar_a, 1);
         mbar_fence_init();
+        rs->retry = 0;
+        for (int i = 0; i < 4; i++) rs->stat[i] = 0;
     }
     if (warp == F_EPI_WARPS + 1) {      // the MMA warp owns the tensor-memory allocation
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((unsigned)F_TMEM_COLS));
@@ -211,155 +336,232 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
 
-    if (warp == F_EPI_WARPS) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            mbar_arrive_expect_tx(bar_a, tile_bytes);
-            tma_bulk_g2s(smem_u32(a_tile), P.Ab + (size_t)blockIdx.x * KB * 128, tile_bytes, bar_a);
-            for (int t = 0; t < NT; t++) {
-                const int s = t % S;
-                mbar_wait(bar_empty + 8 * s, ((t / S) & 1) ^ 1);          // first round passes immediately
-                mbar_arrive_expect_tx(bar_full + 8 * s, tile_bytes);
-                tma_bulk_g2s(smem_u32(b_ring + (size_t)s * tile_bytes), P.Bb + (size_t)t * KB * 128, tile_bytes, bar_full + 8 * s);
+    if (warp == F_EPI_WARPS && elect_one()) {
+        mbar_arrive_expect_tx(bar_a, tile_bytes);
+        tma_bulk_g2s(smem_u32(a_tile), P.Ab + (size_t)blockIdx.x * KB * 128, tile_bytes, bar_a);
+    }
+
+    int it0 = 0;                         // pipeline iterations before this pass (ring stage / accumulator buffer / parities follow it)
+    for (int pass = P.sample_tiles > 0 ? 0 : 1; pass < 3; pass++) {
+        const int ntiles = filter_pass_tiles(P, pass, NT);
+        if (warp == F_EPI_WARPS) {
+            // ===================== TMA producer (the warp stays converged, one elected lane issues) =====================
+            int s = it0 % S, ph = (it0 / S) & 1;                             // ring stage and its phase parity
+            for (int j = 0; j < ntiles; j++) {
+                mbar_wait(bar_empty + 8 * s, ph ^ 1);                         // first round passes immediately
+                if (elect_one()) {
+                    mbar_arrive_expect_tx(bar_full + 8 * s, tile_bytes);
+                    tma_bulk_g2s(smem_u32(b_ring) + (unsigned)s * tile_bytes, P.Bb + (size_t)filter_pass_tile(P, pass, j) * KB * 128, tile_bytes,
+                                 bar_full + 8 * s);
+                }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1; }
             }
-        }
-    } else if (warp == F_EPI_WARPS + 1) {
-        // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
-            // D fp32 (bit 4), A bf16 (bit 7), B bf16 (bit 10), both K-major, N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
-            const unsigned idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((unsigned)(FN >> 3) << 17) | ((128u >> 4) << 24);
-            mbar_wait(bar_a, 0);
-            for (int t = 0; t < NT; t++) {
-                const int s = t % S, b = t & (F_ACCBUFS - 1);
-                mbar_wait(bar_acce + 8 * b, ((t >> F_ACCSHIFT) & 1) ^ 1); // accumulator buffer drained by the epilogue
-                mbar_wait(bar_full + 8 * s, (t / S) & 1);                 // B tile landed
+        } else if (warp == F_EPI_WARPS + 1) {
+            // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+            // D fp32 (bit 4), A and B fp16 (format 0 at bits 7 and 10), both K-major, N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
+            const unsigned idesc = (1u << 4) | ((unsigned)(FN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t adesc0 = umma_desc(smem_u32(a_tile)), bdesc0 = umma_desc(smem_u32(b_ring));
+            const int ksteps = KB / 16;                                       // K=16 per MMA = two 16-byte k chunks of 2048 B
+            if (it0 == 0) mbar_wait(bar_a, 0);
+            int s = it0 % S, ph = (it0 / S) & 1;
+            for (int j = 0; j < ntiles; j++) {
+                const int it = it0 + j, b = it & (F_ACCBUFS - 1);
+                mbar_wait(bar_acce + 8 * b, ((it >> F_ACCSHIFT) & 1) ^ 1);     // accumulator buffer drained by the epilogue
+                mbar_wait(bar_full + 8 * s, ph);                              // B tile landed
                 tc_fence_after();
-                const unsigned a0 = smem_u32(a_tile), b0 = smem_u32(b_ring + (size_t)s * tile_bytes);
-                for (int ks = 0; ks < KB / 16; ks++)                      // K=16 per MMA = two 16-byte k chunks of 2048 B
-                    umma_bf16(tmem_base + (unsigned)(b * FN), umma_desc(a0 + ks * 4096), umma_desc(b0 + ks * 4096), idesc, ks > 0 ? 1u : 0u);
-                umma_commit(bar_empty + 8 * s);                           // stage reusable once these MMAs have read it
-                umma_commit(bar_accf + 8 * b);                            // accumulator complete
+                if (elect_one()) {
+                    const uint64_t bdesc = umma_desc_advance(bdesc0, (unsigned)s * tile_bytes);
+                    const unsigned d = tmem_base + (unsigned)(b * FN);
+                    umma_f16(d, adesc0, bdesc, idesc, 0u);
+#pragma unroll 7
+                    for (int ks = 1; ks < ksteps; ks++)
+                        umma_f16(d, umma_desc_advance(adesc0, ks * 4096), umma_desc_advance(bdesc, ks * 4096), idesc, 1u);
+                    umma_commit(bar_empty + 8 * s);                           // stage reusable once these MMAs have read it
+                    umma_commit(bar_accf + 8 * b);                            // accumulator complete
+                }
+                __syncwarp();
+                if (++s == S) { s = 0; ph ^= 1; }
             }
-        }
-    } else {
-        // ===================== epilogue warps =====================
-        const int q = warp & 3, slot = warp >> 2;       // TMEM lane quarter, 32-column chunk of the tile
-        const int row = q * 32 + lane;                  // user row of this thread (shared with the 3 other slots)
-        const int ul = tile_u0 + row;
-        const unsigned qbar = 1 + q;                    // named barrier of the quarter's four warps
-        float* cs = P.cand_approx + (size_t)ul * C;
-        int* ci = P.cand_item + (size_t)ul * C;
-        if (slot == 0) {
-            const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0);
-            // |approx - exact| <= (2^-7 (1 + 2^-9) + k 2^-22) sum|a_k b_k| <= 0.0084 ||a|| ||b||: bf16 rounding of both
-            // operands (relative 2^-8 each), fp32 accumulation in the tensor core, fp32 rounding of the exact chain
-            rs->slack[row] = ranked ? 2.f * 0.0084f * P.anorm[ul] * __uint_as_float(*P.maxbn) : 0.f;
-            rs->thr[row] = ranked ? -CUDART_INF_F : CUDART_INF_F;     // approx < thr: cannot be in the exact top K
-            rs->cnt[row] = 0;
-            rs->flags[row] = 0;
-            // the row's sorted train items (hpp:494-495 takes them out of the pool): cursor = first one >= the current tile
-            int cur = 0, end = 0;
-            if (ranked) { cur = P.trp[P.user0 + ul]; end = P.trp[P.user0 + ul + 1]; }
-            rs->tr_cur[row] = cur;
-            rs->tr_end[row] = end;
-            rs->nxt_train[row] = cur < end ? P.tri[cur] : INT_MAX;
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+        } else {
+            // ===================== epilogue warps =====================
+            const int q = warp & 3, slot = warp >> 2;       // TMEM lane quarter, 32-column chunk of the tile
+            const int row = q * 32 + lane;                  // user row of this thread (shared with the 3 other slots)
+            const int ul = tile_u0 + row;
+            const unsigned qbar = 1 + q;                    // named barrier of the quarter's four warps
+            const int Kp = pass == 0 ? P.sample_rank : P.K; // how many best candidates the pass keeps track of
+            float* cs = P.cand_approx + (size_t)ul * C;
+            int* ci = P.cand_item + (size_t)ul * C;
+            if (slot == 0) {
+                const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0) && !(P.dbg & 2);
+                // |approx - exact| <= c ||a|| max||b|| (c = P.err_coef, see filter_err_coef); the approximate scores live in the
+                // scaled units of the operand image (row scale x matrix scale, both powers of two), and so does the slack
+                float slack = 0.f;
+                if (ranked) {
+                    const float an = P.anorm[ul], bn = __uint_as_float(*P.maxbn);
+                    slack = 2.f * P.err_coef * (an * pow2_scale_for(an)) * (bn * pow2_scale_for(bn));
+                }
+                float thr0 = CUDART_INF_F;                  // approx < thr: cannot be in the exact top K; +inf: the row is closed
+                if (pass == 0) {
+                    rs->flags[row] = 0;
+                    rs->guess[row] = -CUDART_INF_F;
+                    if (ranked) thr0 = -CUDART_INF_F;
+                } else if (pass == 1) {
+                    if (P.sample_tiles == 0) { rs->flags[row] = 0; rs->guess[row] = -CUDART_INF_F; }
+                    if (ranked) { thr0 = __fsub_rd(rs->guess[row], slack); if (!(thr0 == thr0)) thr0 = -CUDART_INF_F; }
+                } else {
+                    if (rs->flags[row] & 4) thr0 = -CUDART_INF_F;
+                }
+                rs->slack[row] = pass == 0 ? 0.f : slack;
+                rs->thr[row] = thr0;
+                if (thr0 != CUDART_INF_F) rs->cnt[row] = 0;  // (a closed row keeps what pass 1 found for it)
+                else if (pass < 2) rs->cnt[row] = 0;
+                // the row's sorted train items (hpp:494-495 takes them out of the pool): cursor = first one >= the current tile
+                int cur = 0, end = 0;
+                if (thr0 != CUDART_INF_F) { cur = P.trp[P.user0 + ul]; end = P.trp[P.user0 + ul + 1]; }
+                rs->tr_cur[row] = cur;
+                rs->tr_end[row] = end;
+                rs->nxt_train[row] = cur < end ? P.tri[cur] : INT_MAX;
+                rs->nxt2_train[row] = cur + 1 < end ? P.tri[cur + 1] : INT_MAX;
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
 
-        for (int t = 0; t < NT; t++) {
-            const int b = t & (F_ACCBUFS - 1);
-            const int tile_end = (t / F_INTERVAL + 1) * F_INTERVAL * FN;     // end of the interval this tile belongs to
-            mbar_wait(bar_accf + 8 * b, (t >> F_ACCSHIFT) & 1);
-            tc_fence_after();
-            unsigned v[32];
-            tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(b * FN + slot * F_CHUNK), v);
-            tc_fence_before();                      // this warp's part of the accumulator is in registers
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_acce + 8 * b);
+            for (int j = 0; j < ntiles; j++) {
+                const int it = it0 + j, b = it & (F_ACCBUFS - 1);
+                const int t = filter_pass_tile(P, pass, j);
+                const int tile_end = (t + 1) * FN;
+                mbar_wait(bar_accf + 8 * b, (it >> F_ACCSHIFT) & 1);
+                tc_fence_after();
+                unsigned v[32];
+                if (!(P.dbg & 8)) tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(b * FN + slot * F_CHUNK), v);
+                tc_fence_before();                      // this warp's part of the accumulator is in registers
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_acce + 8 * b);
 
-            if (P.dbg & 1) continue;
-            const float thr = rs->thr[row];
-            const int item_base = t * FN + slot * F_CHUNK;
-            const bool has_train = rs->nxt_train[row] < tile_end;
-            // NaN-propagating max of each group of 8 columns; only groups holding a score >= thr are looked at
+                if (P.dbg & 1) continue;
+                const float thr = rs->thr[row];
+                const int item_base = t * FN + slot * F_CHUNK;
+                const bool has_train = rs->nxt_train[row] < tile_end;
+                // NaN-propagating max of each group of 8 columns; only groups holding a score >= thr are looked at
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
-                const float m01 = max_nan(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
-                const float m23 = max_nan(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
-                const float m45 = max_nan(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
-                const float m67 = max_nan(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-                const float m = max_nan(max_nan(m01, m23), max_nan(m45, m67));
-                if (!(m < thr)) {
-                    // slow path: drop padding columns and train items (hpp:494-495), flag NaN scores (hpp:195-197),
-                    // append the rest to the row's candidate buffer
+                for (int g = 0; g < 4; g++) {
+                    const float m01 = max_nan(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
+                    const float m23 = max_nan(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
+                    const float m45 = max_nan(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
+                    const float m67 = max_nan(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
+                    const float m = max_nan(max_nan(m01, m23), max_nan(m45, m67));
+                    if (!(m < thr)) {
+                        F_STAT(2, 1);
+                        // slow path: drop padding columns and train items (hpp:494-495), flag NaN scores (hpp:195-197),
+                        // append the rest to the row's candidate buffer
 #pragma unroll
-                    for (int j = 0; j < 8; j++) {
-                        const float s = __uint_as_float(v[8 * g + j]);
-                        if (!(s < thr)) {
-                            const int item = item_base + 8 * g + j;
-                            if (item < P.n && !(has_train && train_hit(P.tri, rs->tr_cur[row], rs->tr_end[row], item))) {
-                                if (s != s) rs->flags[row] = 1;
-                                else { const int at = atomicAdd(&rs->cnt[row], 1); cs[at] = s; ci[at] = item; }
+                        for (int jj = 0; jj < 8; jj++) {
+                            const float s = __uint_as_float(v[8 * g + jj]);
+                            if (!(s < thr)) {
+                                const int item = item_base + 8 * g + jj;
+                                if (item < P.n && !(has_train && train_hit(P.tri, rs->tr_cur[row], rs->tr_end[row], item))) {
+                                    if (s != s) rs->flags[row] |= 1;
+                                    else { const int at = atomicAdd(&rs->cnt[row], 1); cs[at] = s; ci[at] = item; F_STAT(0, 1); }
+                                }
                             }
                         }
                     }
                 }
-            }
-            if ((t + 1) % F_INTERVAL != 0 && t + 1 < NT) continue;
-            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");     // the quarter's chunks of this interval are done
-            // rows whose buffer may not take another interval, rows whose train cursor has to move: the same masks in all four warps
-            unsigned need = __ballot_sync(FULL, rs->cnt[row] > C - F_INTERVAL * FN);
-            const unsigned move = __ballot_sync(FULL, rs->nxt_train[row] < tile_end);
-            if (need | move) {
-                if (slot == 0 && rs->nxt_train[row] < tile_end) {
-                    int cur = rs->tr_cur[row], nxt = INT_MAX;
-                    const int end = rs->tr_end[row];
-                    while (cur < end && (nxt = P.tri[cur]) < tile_end) cur++;
-                    rs->tr_cur[row] = cur;
-                    rs->nxt_train[row] = cur < end ? nxt : INT_MAX;
+                if (P.dbg & 4) continue;
+                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");     // the quarter's chunks of this tile are done
+                // rows whose buffer may not take another tile, rows whose train cursor has to move: the same masks in all four warps
+                unsigned need = __ballot_sync(FULL, rs->cnt[row] > C - FN);
+                const unsigned move = __ballot_sync(FULL, rs->nxt_train[row] < tile_end);
+                if (need | move) {
+                    if (slot == 0 && rs->nxt_train[row] < tile_end) {
+                        // the id after the current one was prefetched into shared memory when the cursor last moved (cp.async:
+                        // the three sibling warps wait at the barrier below, a global-memory round trip here would stall them all)
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        F_STAT(3, 1);
+                        int cur = rs->tr_cur[row] + 1, nxt = rs->nxt2_train[row];
+                        const int end = rs->tr_end[row];
+                        while (nxt < tile_end) { cur++; nxt = cur < end ? P.tri[cur] : INT_MAX; }    // several train items in one tile
+                        rs->tr_cur[row] = cur;
+                        rs->nxt_train[row] = nxt;
+                        if (cur + 1 < end)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&rs->nxt2_train[row])), "l"(P.tri + cur + 1) : "memory");
+                        else rs->nxt2_train[row] = INT_MAX;
+                    }
+                    while (need) {
+                        const int r = __ffs(need) - 1;
+                        need &= need - 1;
+                        if ((r & 3) != slot) continue;                         // the quarter's warps share the work
+                        const int rr = q * 32 + r;
+                        const size_t base = (size_t)(tile_u0 + rr) * C;
+                        float tau_r;
+#if RMB_F_HIST_ROUNDS > 0
+                        const int kept = approx_compact_hist<C, RMB_F_HIST_ROUNDS>(P.cand_approx + base, P.cand_item + base, rs->cnt[rr], Kp, rs->slack[rr],
+                                                                                   lane, rs->hist[warp], &tau_r);
+#else
+                        const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, rs->cnt[rr], Kp, rs->slack[rr], lane, &tau_r);
+#endif
+                        if (lane == 0) {
+                            F_STAT(1, 1);
+                            float thr_r = __fsub_rd(tau_r, rs->slack[rr]);
+                            if (!(thr_r == thr_r)) thr_r = -CUDART_INF_F;       // non-finite bound: keep everything
+                            thr_r = fmaxf(thr_r, rs->thr[rr]);                  // an earlier (valid) bound may be the sharper one
+                            int cnt_r = kept;
+                            if (kept > C - FN) { rs->flags[rr] |= 2; thr_r = CUDART_INF_F; cnt_r = 0; }   // slack band does not fit
+                            rs->thr[rr] = thr_r;
+                            rs->cnt[rr] = cnt_r;
+                        }
+                    }
+                    asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
                 }
-                while (need) {
-                    const int r = __ffs(need) - 1;
-                    need &= need - 1;
-                    if ((r & 3) != slot) continue;                         // the quarter's warps share the work
-                    const int rr = q * 32 + r;
+            }
+            // end of the pass: the exact Kp-th best approximate score of what each row kept
+            for (int r = slot; r < 32; r += 4) {
+                const int rr = q * 32 + r;
+                if (rs->thr[rr] == CUDART_INF_F && !(rs->flags[rr] & 2)) continue;    // closed row (not ranked / settled in pass 1)
+                const int nv = rs->cnt[rr];
+                float tau_r = -CUDART_INF_F;
+                bool have_k = false;
+                if (nv >= Kp && !(rs->flags[rr] & 2)) {
                     const size_t base = (size_t)(tile_u0 + rr) * C;
-                    float tau_r;
-                    const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, rs->cnt[rr], P.K, rs->slack[rr], lane, &tau_r);
-                    if (lane == 0) {
-                        float thr_r = __fsub_rd(tau_r, rs->slack[rr]);
-                        if (!(thr_r == thr_r)) thr_r = -CUDART_INF_F;       // non-finite bound: keep everything
-                        int cnt_r = kept;
-                        if (kept > C - F_INTERVAL * FN) { rs->flags[rr] |= 2; thr_r = CUDART_INF_F; cnt_r = 0; }   // slack band does not fit
-                        rs->thr[rr] = thr_r;
-                        rs->cnt[rr] = cnt_r;
+                    const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, nv, Kp, rs->slack[rr], lane, &tau_r);
+                    have_k = true;
+                    if (lane == 0 && pass > 0) rs->cnt[rr] = kept;      // last cut: the exact stage gets only what can still be in the top K
+                }
+                if (lane == 0) {
+                    if (pass == 0) {
+                        rs->guess[rr] = have_k ? tau_r : -CUDART_INF_F;                 // too small a sample / overflow: no guess
+                        rs->flags[rr] &= ~2;
+                    } else if (pass == 1 && !(rs->flags[rr] & 2)) {
+                        const float g = rs->guess[rr];
+                        const bool ok = (g == -CUDART_INF_F) || (have_k && tau_r >= g);  // >= K kept candidates reach the guess
+                        if (!ok) { rs->flags[rr] |= 4; rs->retry = 1; }
                     }
                 }
-                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
             }
+            asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
         }
-        // last cut: hand the exact stage only what can still be in the top K
-        for (int r = slot; r < 32; r += 4) {
-            const int rr = q * 32 + r;
-            const int nv = rs->cnt[rr];
-            if (nv > P.K && !(rs->flags[rr] & 2)) {
-                const size_t base = (size_t)(tile_u0 + rr) * C;
-                float tau_r;
-                const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, nv, P.K, rs->slack[rr], lane, &tau_r);
-                if (lane == 0) rs->cnt[rr] = kept;
-            }
-        }
-        asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
-        if (slot == 0 && ul < P.mb) {
+        it0 += ntiles;
+        if (pass == 0) continue;         // the sample's result is consumed by the epilogue warps alone
+        __syncthreads();
+        if (pass == 2 || !__any_sync(FULL, rs->retry != 0)) break;      // (a vote: the compiler keeps the pass loop warp-uniform)
+    }
+
+    if (warp < F_EPI_WARPS && (warp >> 2) == 0) {
+        const int row = (warp & 3) * 32 + lane, ul = tile_u0 + row;
+        if (ul < P.mb) {
             const int fl = rs->flags[row];
             P.cand_count[ul] = (fl & 2) ? -1 : rs->cnt[row];
             if (fl & 2) atomicAdd(P.overflow, 1);
             if (fl & 1) atomicOr(&P.uflags[P.user0 + ul], 1);
+            if ((fl & 4) && P.retries) atomicAdd(P.retries, 1);
         }
     }
 
     tc_fence_before();
     __syncthreads();
+#if RMB_F_STATS
+    if (tid < 4 && P.retries) atomicAdd(P.retries + 1 + tid, rs->stat[tid]);
+#endif
     if (warp == F_EPI_WARPS + 1)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)F_TMEM_COLS));
 }

@@ -5,7 +5,7 @@
 //   score_entries_kernel   scores of the held-out (test) items, same FMA order as the tile kernel
 //   sort_positives_kernel  per-user ascending order of those scores (rank by counting)
 #pragma once
-#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include "score_select.cuh"
 
 namespace rmb {
@@ -124,14 +124,29 @@ __global__ void sort_positives_kernel(const int user0, const int mb, const int* 
 }
 
 
-// bf16 operand image for the tensor-core filter (filter_select.cuh): 128-row tiles, [tile][k/8][row][8 bf16],
+// Power-of-two scale that brings a positive norm into [0.5, 1): 2^-e with nrm = f * 2^e (frexp).  Scaling by it is
+// exact; 1 for zero / non-finite norms (such rows produce non-finite scores and are handled as NaN rows).
+__device__ __forceinline__ float pow2_scale_for(const float nrm)
+{
+    if (!(nrm > 0.f) || nrm == CUDART_INF_F) return 1.f;
+    int e;
+    frexpf(nrm, &e);
+    e = e < -100 ? -100 : (e > 100 ? 100 : e);
+    return ldexpf(1.f, -e);
+}
+
+// fp16 operand image for the tensor-core filter (filter_select.cuh): 128-row tiles, [tile][k/8][row][8 halves],
 // KB factors per row (multiple of 16).  Column `cols` holds extra[row] (the item bias) or, for the user side,
 // 1.0 (ones_col) -- the bias travels as one more factor, as in recometrics/__init__.py:548-551; the rest is 0.
+// Rows are scaled by a power of two so that every element is at most 1 in magnitude (fp16 keeps 11 significant bits
+// from 6e-5 up): the user side by its own row norm (row_norm[r]), the item side by ONE scale for the whole matrix
+// (*global_norm_bits = max_j ||b_j||), so that a user's approximate scores stay comparable across items.
 // One thread per (row, 8-factor chunk): consecutive threads write consecutive 16-byte rows of a chunk.
 template <typename T>
-__global__ void pack_bf16_kernel(const T* __restrict__ src, const size_t ld, const int rows, const int cols,
-                                 const T* __restrict__ extra, const int ones_col,
-                                 __nv_bfloat16* __restrict__ dst, const int rows_pad, const int KB)
+__global__ void pack_f16_kernel(const T* __restrict__ src, const size_t ld, const int rows, const int cols,
+                                const T* __restrict__ extra, const int ones_col,
+                                const float* __restrict__ row_norm, const unsigned* __restrict__ global_norm_bits,
+                                __half* __restrict__ dst, const int rows_pad, const int KB)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int chunks = KB / 8;
@@ -141,7 +156,9 @@ __global__ void pack_bf16_kernel(const T* __restrict__ src, const size_t ld, con
     const int rem = (int)(idx % ((long long)chunks * 128));
     const int c = rem / 128, rl = rem % 128;
     const int r = tile * 128 + rl;
-    __align__(16) __nv_bfloat16 v[8];
+    float scale = 1.f;
+    if (r < rows) scale = pow2_scale_for(row_norm != nullptr ? row_norm[r] : __uint_as_float(*global_norm_bits));
+    __align__(16) __half v[8];
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         const int k = c * 8 + e;
@@ -150,7 +167,7 @@ __global__ void pack_bf16_kernel(const T* __restrict__ src, const size_t ld, con
             if (k < cols) x = (float)src[(size_t)r * ld + k];
             else if (k == cols) x = extra != nullptr ? (float)extra[r] : (ones_col ? 1.f : 0.f);
         }
-        v[e] = __float2bfloat16_rn(x);
+        v[e] = __float2half_rn(x * scale);
     }
     *reinterpret_cast<uint4*>(dst + (size_t)idx * 8) = *reinterpret_cast<const uint4*>(v);
 }

@@ -27,6 +27,7 @@ for i in range(a.reps):
     r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=cfg.k, item_biases=d["item_biases"],
                                 cumulative=cfg.cumulative, break_ties_with_noise=False, min_pos_test=cfg.min_pos_test, **kw)
     t = r.timing
-    print(json.dumps({"rep": i, "users": a.users, "kernel_ms": t["score_select_ms"], "tflops": F / t["score_select_ms"] / 1e9,
+    print(json.dumps({"rep": i, "dom_ms": round(t["dominant_kernel_ms"], 3), "users": a.users, "kernel_ms": t["score_select_ms"], "tflops": F / t["score_select_ms"] / 1e9,
                       "prep_ms": t["prep_ms"], "metrics_ms": t["metrics_ms"], "h2d_ms": t["h2d_ms"], "d2h_ms": t["d2h_ms"],
-                      "total_ms": t["total_ms"], "users_per_s_kernel": a.users / t["score_select_ms"] * 1e3}))
+                      "total_ms": t["total_ms"], "users_per_s_kernel": a.users / t["score_select_ms"] * 1e3,
+                      "dom_ms": t["dominant_kernel_ms"], "retry_rows": t.get("filter_retry_rows"), "fallback": t.get("filter_fallback_batches")}))
