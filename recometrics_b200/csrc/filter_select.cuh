@@ -5,21 +5,26 @@
 // dot1 scoring :84-112/:499-512, partial_sort :537-548) with the work split differently:
 //
 //   1. FILTER (filter_select_kernel) -- every (user, item) score is computed APPROXIMATELY on the
-//      5th-generation tensor cores: bf16 copies of the factors (item bias folded in as one more factor,
-//      as the reference's front-end does, recometrics/__init__.py:548-551), fp32 accumulation in TMEM.
+//      5th-generation tensor cores: fp16 copies of the factors, scaled by powers of two so that every element
+//      is at most 1 (prep.cuh; item bias folded in as one more factor, as the reference's front-end does,
+//      recometrics/__init__.py:548-551), fp32 accumulation in TMEM.
 //      A CTA keeps a 128-user A tile resident in shared memory and streams 128-item B tiles through a
-//      TMA ring; one elected thread issues tcgen05.mma (M=128, N=128, K=16 per instruction) into one of
-//      two TMEM accumulator buffers; sixteen epilogue warps read the other buffer with tcgen05.ld: the four
-//      warps of a TMEM lane quarter (32 user rows) each take one 32-column chunk of the tile, so that four
-//      warps per scheduler hide each other's latencies; a quarter's per-row state (threshold, counter,
-//      train-row cursor) lives in shared memory and its warps meet at a named barrier once per tile.
-//      With m_u = c * ||a_u|| * max_j ||b_j|| >= |approx - exact| (bf16 rounding of both operands,
-//      Cauchy-Schwarz; prep.cuh) and tau~ = the K-th best APPROXIMATE candidate score seen so far, every
+//      TMA ring; one elected lane issues tcgen05.mma (M=128, N=128, K=16 per instruction) into one of
+//      four TMEM accumulator buffers; sixteen epilogue warps read them back with tcgen05.ld: the four
+//      warps of a TMEM lane quarter (32 user rows; they also share a warp scheduler) each take one
+//      32-column chunk of every tile.  Everything a warp needs per row is PRIVATE to it -- its own region
+//      of the row's candidate buffer with the counter in a register, its own cursor into the row's train
+//      items -- so the four warps never wait for each other inside a tile: while one of them appends
+//      candidates, the others run ahead (up to the four accumulator buffers).  They meet at a named
+//      barrier only every 1..16 tiles (the distance adapts to the append rate) to cut the row's four
+//      regions back together and raise the row's shared threshold.
+//      With m_u = c * ||a_u|| * max_j ||b_j|| >= |approx - exact| (fp16 rounding of both operands,
+//      Cauchy-Schwarz; filter_err_coef) and tau~ = the K-th best APPROXIMATE candidate score seen so far, every
 //      member of the exact top K satisfies approx >= tau~ - 2 m_u (the K best approximate scores have
 //      exact scores >= tau~ - m_u, so the exact K-th best is >= tau~ - m_u, and a member's approximate
 //      score is within m_u of its exact one).  The kernel therefore keeps, per user, all candidates with
-//      approx >= tau~ - 2 m_u: train items and padding columns are dropped when appended, the buffer is
-//      cut back with a radix select on the approximate keys when it fills.  >= 99.9 % of the catalogue
+//      approx >= tau~ - 2 m_u: train items and padding columns are dropped when appended, the regions are
+//      cut back with a histogram select on the approximate keys.  >= 99.9 % of the catalogue
 //      is rejected with one compare.
 //   2. EXACT (exact_topk_kernel) -- one warp per user re-scores the few hundred survivors exactly
 //      (sequential fma chain over the original fp32 / fp64 factors: the same chain, hence bit-identical
@@ -28,7 +33,7 @@
 //      decide what is worth looking at.  A user whose slack band does not fit the buffer is flagged and
 //      the host re-runs that batch on the FMA path.
 //
-// Shared-memory operand layout (no swizzle, K-major "interleaved"): [k/8][row][8 bf16] -- a core matrix
+// Shared-memory operand layout (no swizzle, K-major "interleaved"): [k/8][row][8 halves] -- a core matrix
 // is 8 rows x 16 bytes contiguous; descriptor LBO = 128 rows * 16 B (next k chunk), SBO = 128 B (next 8
 // rows).  The pack kernel writes tiles in exactly this image, so one bulk copy per tile lands it.
 // Encodings pinned on hardware by tools/ubench/umma_probe.cu.
@@ -50,7 +55,18 @@ constexpr int F_ACCSHIFT = F_ACCBUFS == 4 ? 2 : 1;
 constexpr int F_TMEM_COLS = F_ACCBUFS * FN;
 constexpr int F_MAX_STAGES = 4;
 constexpr int F_CHUNK = 32;              // TMEM columns per tcgen05.ld
+#ifndef RMB_F_CUT_MARGIN
+#define RMB_F_CUT_MARGIN 48               // a row's regions are cut back together once they hold this many more than the last cut kept
+#endif
+constexpr int F_CUT_MARGIN = RMB_F_CUT_MARGIN;
+#ifndef RMB_F_MAX_MEET
+#define RMB_F_MAX_MEET 16                 // most item tiles between two meetings of a quarter's warps
+#endif
+constexpr int F_MAX_MEET = RMB_F_MAX_MEET;
 
+#ifndef RMB_F_DBG
+#define RMB_F_DBG 0                      // developer build: honour FilterParams::dbg (env RMB200_DBG) inside the tile loop
+#endif
 #ifndef RMB_F_STATS
 #define RMB_F_STATS 0                    // developer build: count appends / cuts / slow-path entries / cursor moves into FilterParams::retries[1..4]
 #endif
@@ -85,12 +101,16 @@ struct FilterParams {
 
 struct FilterRowState {      // per user row of the CTA, shared by the four epilogue warps of its TMEM lane quarter
     float thr[BM], slack[BM], guess[BM];
-    int cnt[BM], flags[BM];          // flags: 1 = NaN candidate score, 2 = slack band overflowed the buffer, 4 = guess failed (retry pass)
+    int cnt[BM];                     // candidates left contiguous at the head of the row's buffer when a pass ends
+    int cnt4[4][BM];                 // candidates in each warp's region of the buffer, published at the meeting points
+    int trig[BM];                    // total above which the regions are cut back together
+    int flags[BM];                   // 1 = NaN candidate score, 2 = buffer overflow (slack band / burst), 4 = guess failed (retry pass)
+    int nxt2_train[4][BM];           // per warp: the train item id after the cursor's next one (prefetched with cp.async)
     int retry;                       // some row of the CTA needs the retry pass
     int stat[4];                     // RMB_F_STATS: appends, cuts, slow-path entries (8-column groups), cursor moves
-    int nxt_train[BM], nxt2_train[BM], tr_cur[BM], tr_end[BM];   // next train item id, the one after it (prefetched), cursor, row end
-    unsigned hist[F_EPI_WARPS][32];  // bucket counters of approx_compact_hist, one set per epilogue warp
+    unsigned hist[F_EPI_WARPS][32];  // bucket counters of cut_regions, one set per epilogue warp
 };
+
 
 // Error bound of the filter's approximate scores, as a multiple of ||a_u|| max_j ||b_j||:
 //   fp16 rounding of both operands (scaled so that |x| <= 1; relative 2^-11 each, absolute 2^-25 below 6e-5):
@@ -152,72 +172,32 @@ __device__ __forceinline__ void tmem_ld32(const unsigned taddr, unsigned (&r)[32
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// One warp: cut the nv (>= K) approximate entries of a user's buffer back to those that can still belong
-// to the exact top K: score >= (K-th best approximate score) - slack.  Returns the number kept (>= K,
-// unordered at the head) and the K-th best approximate score.
-template <int C>
-__device__ __noinline__ int approx_compact(float* cs, int* ci, const int nv, const int K, const float slack, const int lane,
-                                           float* tau_out)
-{
-    constexpr int E = C / 32;
-    unsigned key[E];
-    int it[E];
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const int idx = e * 32 + lane;
-        const bool v = idx < nv;
-        key[e] = v ? NumTraits<float>::key(cs[idx]) : 0u;      // 0 sorts below every score
-        it[e] = v ? ci[idx] : INT_MAX;
-    }
-    __syncwarp();
-    unsigned t = 0;                                             // K-th largest key (NaN scores sort on top)
-    for (int b = 31; b >= 0; b--) {
-        const unsigned cand = t | (1u << b);
-        int c = 0;
-#pragma unroll
-        for (int e = 0; e < E; e++) c += (key[e] >= cand) ? 1 : 0;
-        c = __reduce_add_sync(FULL, c);
-        if (c >= K) t = cand;
-    }
-    const float tau = NumTraits<float>::from_orderable((u64)t);
-    const float cutf = __fsub_rd(tau, slack);                   // NaN (tau or slack not finite): keep everything
-    const unsigned cut = (cutf == cutf) ? NumTraits<float>::key(cutf) : 1u;
-    int base = 0;
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const bool keep = key[e] >= cut && key[e] != 0u;
-        const unsigned mask = __ballot_sync(FULL, keep);
-        if (keep) {
-            const int pos = base + __popc(mask & ((1u << lane) - 1u));
-            cs[pos] = NumTraits<float>::from_orderable((u64)key[e]);
-            ci[pos] = it[e];
-        }
-        base += __popc(mask);
-    }
-    *tau_out = tau;
-    __syncwarp();
-    return base;
-}
-
-// The same cut, cheaper: instead of the K-th best key bit by bit (32 dependent warp reductions), ROUNDS rounds of a
-// 32-bucket histogram (shared-memory counters, one bucket per lane, suffix sums by shuffles) narrow a window of the
-// key range that holds it.  The window's lower edge `lo` always satisfies #(key >= lo) >= K, so it is a valid (slightly
-// low: window width = key range / 32^ROUNDS) stand-in for the K-th best approximate score; ROUNDS = 7 makes it exact.
+// One warp: cut a row's candidates back to those that can still belong to the exact top K: approximate score >=
+// (K-th best approximate score) - slack.  The row's buffer is four regions of C/4 entries (one per epilogue warp of the
+// quarter), region s holding cnt4[s] entries; all of them are read into registers first, so the survivors can be written
+// back in place: CONTIG ? packed at the head of the buffer : dealt round-robin over the four regions.
+// The K-th best key is found by ROUNDS rounds of a 32-bucket histogram (shared-memory counters, one bucket per lane,
+// suffix sums by shuffles) that narrow a window [lo, lo + span] of the key range around it.  The window's lower edge
+// always satisfies #(key >= lo) >= K, so it is a valid (slightly low: window width = key range / 32^ROUNDS) stand-in
+// for the K-th best approximate score; ROUNDS = 7 exhausts 32-bit keys and makes it exact.
+// K <= total entries is required.  Returns the number kept; *tau_out = the (stand-in for the) K-th best score.
 #ifndef RMB_F_HIST_ROUNDS
 #define RMB_F_HIST_ROUNDS 2
 #endif
-template <int C, int ROUNDS>
-__device__ __noinline__ int approx_compact_hist(float* cs, int* ci, const int nv, const int K, const float slack, const int lane,
-                                                unsigned* hist, float* tau_out)
+template <int C, int ROUNDS, bool CONTIG>
+__device__ __noinline__ int cut_regions(float* cs, int* ci, const int c0, const int c1, const int c2, const int c3, const int K,
+                                        const float slack, const int lane, unsigned* hist, float* tau_out)
 {
-    constexpr int E = C / 32;
+    constexpr int E = C / 32, RC = C / 4, EPR = E / 4;      // entries per lane, region capacity, per-lane entries per region
     unsigned key[E];
     int it[E];
     unsigned kmax = 0u, kmin = 0xffffffffu;
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        const int idx = e * 32 + lane;
-        const bool v = idx < nv;
+        const int region = e / EPR, pos = (e % EPR) * 32 + lane;
+        const int cr = region == 0 ? c0 : (region == 1 ? c1 : (region == 2 ? c2 : c3));
+        const bool v = pos < cr;
+        const int idx = region * RC + pos;
         key[e] = v ? NumTraits<float>::key(cs[idx]) : 0u;      // 0 sorts below every score
         it[e] = v ? ci[idx] : INT_MAX;
         if (v) { kmax = max(kmax, key[e]); kmin = min(kmin, key[e]); }
@@ -262,7 +242,8 @@ __device__ __noinline__ int approx_compact_hist(float* cs, int* ci, const int nv
         const bool keep = key[e] >= cut && key[e] != 0u;
         const unsigned mask = __ballot_sync(FULL, keep);
         if (keep) {
-            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+            const int k = base + __popc(mask & ((1u << lane) - 1u));
+            const int pos = CONTIG ? k : (k & 3) * RC + (k >> 2);
             cs[pos] = NumTraits<float>::from_orderable((u64)key[e]);
             ci[pos] = it[e];
         }
@@ -273,16 +254,37 @@ __device__ __noinline__ int approx_compact_hist(float* cs, int* ci, const int nv
     return base;
 }
 
-// train-row membership, out of line: only reached by a passing score in a tile the user's train row intersects.
-// tri[lo] is the first train item of the current tile: the few that follow inside the tile are scanned linearly.
-__device__ __noinline__ bool train_hit(const int* __restrict__ tri, int lo, const int hi, const int item)
+// Slow path of the filter, out of line and in ONE copy (the tile loop must stay small: sixteen warps share the
+// instruction cache): the 8 scores of a column group of which at least one is not below the row's threshold.
+// Padding columns and train items are dropped (hpp:494-495; [t_lo, t_hi) = the part of the row's sorted train items
+// that can intersect this tile, empty when none does: the few inside the tile are scanned linearly), NaN scores raise
+// flag 1 (hpp:195-197), the rest is appended to this warp's region of the row's candidate buffer (flag 2 when it is full).
+// Returns the new fill of the region.
+template <int RC>
+__device__ __noinline__ int filter_append_group(const float s0, const float s1, const float s2, const float s3,
+                                                const float s4, const float s5, const float s6, const float s7,
+                                                const float thr, const int item0, const int n,
+                                                const int* __restrict__ tri, const int t_lo, const int t_hi,
+                                                float* cs, int* ci, int mycnt, int* flagp)
 {
-    while (lo < hi) {
-        const int v = tri[lo];
-        if (v >= item) return v == item;
-        lo++;
+    const float sv[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
+#pragma unroll
+    for (int jj = 0; jj < 8; jj++) {
+        const float s = sv[jj];
+        if (s < thr) continue;
+        const int item = item0 + jj;
+        if (item >= n) continue;
+        bool in_train = false;
+        for (int lo = t_lo; lo < t_hi; lo++) {
+            const int v = tri[lo];
+            if (v >= item) { in_train = (v == item); break; }
+        }
+        if (in_train) continue;
+        if (s != s) atomicOr(flagp, 1);
+        else if (mycnt < RC) { cs[mycnt] = s; ci[mycnt] = item; mycnt++; }
+        else atomicOr(flagp, 2);
     }
-    return false;
+    return mycnt;
 }
 
 // The item tiles a CTA walks, pass by pass (all roles -- TMA producer, MMA issuer, epilogue -- step through the same list):
@@ -385,15 +387,16 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             }
         } else {
             // ===================== epilogue warps =====================
+            constexpr int RC = C / 4;                       // capacity of a warp's region of the row's candidate buffer
             const int q = warp & 3, slot = warp >> 2;       // TMEM lane quarter, 32-column chunk of the tile
             const int row = q * 32 + lane;                  // user row of this thread (shared with the 3 other slots)
             const int ul = tile_u0 + row;
             const unsigned qbar = 1 + q;                    // named barrier of the quarter's four warps
             const int Kp = pass == 0 ? P.sample_rank : P.K; // how many best candidates the pass keeps track of
-            float* cs = P.cand_approx + (size_t)ul * C;
-            int* ci = P.cand_item + (size_t)ul * C;
+            float* cs = P.cand_approx + (size_t)ul * C + slot * RC;      // this warp's region of the row's buffer
+            int* ci = P.cand_item + (size_t)ul * C + slot * RC;
             if (slot == 0) {
-                const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0) && !(P.dbg & 2);
+                const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0) && !(RMB_F_DBG && (P.dbg & 2));
                 // |approx - exact| <= c ||a|| max||b|| (c = P.err_coef, see filter_err_coef); the approximate scores live in the
                 // scaled units of the operand image (row scale x matrix scale, both powers of two), and so does the slack
                 float slack = 0.f;
@@ -414,79 +417,99 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 }
                 rs->slack[row] = pass == 0 ? 0.f : slack;
                 rs->thr[row] = thr0;
-                if (thr0 != CUDART_INF_F) rs->cnt[row] = 0;  // (a closed row keeps what pass 1 found for it)
-                else if (pass < 2) rs->cnt[row] = 0;
-                // the row's sorted train items (hpp:494-495 takes them out of the pool): cursor = first one >= the current tile
-                int cur = 0, end = 0;
-                if (thr0 != CUDART_INF_F) { cur = P.trp[P.user0 + ul]; end = P.trp[P.user0 + ul + 1]; }
-                rs->tr_cur[row] = cur;
-                rs->tr_end[row] = end;
-                rs->nxt_train[row] = cur < end ? P.tri[cur] : INT_MAX;
-                rs->nxt2_train[row] = cur + 1 < end ? P.tri[cur + 1] : INT_MAX;
+                rs->trig[row] = Kp + F_CUT_MARGIN;
+                if (thr0 != CUDART_INF_F || pass < 2) rs->cnt[row] = 0;   // (a row closed in the retry pass keeps what pass 1 found)
             }
             asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+            // private per-thread row state: region fill, cursor into the row's sorted train items (hpp:494-495 takes those out
+            // of the pool): t_nxt = the first train item id >= the current tile, the one after it prefetched in shared memory
+            int mycnt = 0, t_cur = 0, t_end = 0, t_nxt = INT_MAX;
+            if (rs->thr[row] != CUDART_INF_F) {
+                t_cur = P.trp[P.user0 + ul]; t_end = P.trp[P.user0 + ul + 1];
+                if (t_cur < t_end) t_nxt = P.tri[t_cur];
+                rs->nxt2_train[slot][row] = t_cur + 1 < t_end ? P.tri[t_cur + 1] : INT_MAX;
+            }
+            int tot_prev = 0;                               // row total after the previous meeting (the same in all four warps)
+            int meet_in = 0, interval = 1;                  // tiles until the next meeting; tiles since the previous one
+            // loop-carried pipeline state, kept incrementally (no per-tile index arithmetic): accumulator buffer and its phase
+            // parity, first item id of this warp's 32-column chunk, the item step between two tiles of the pass
+            int buf = it0 & (F_ACCBUFS - 1);
+            unsigned par = (unsigned)(it0 >> F_ACCSHIFT) & 1u;
+            int item_base = slot * F_CHUNK;
+            const int item_step = (pass == 0 ? P.sample_stride : 1) * FN;
+            const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(slot * F_CHUNK);
+            int* const flag_p = &rs->flags[row];
+            float thr = rs->thr[row];                       // the row's threshold only moves at the meetings: kept in a register in between
 
-            for (int j = 0; j < ntiles; j++) {
-                const int it = it0 + j, b = it & (F_ACCBUFS - 1);
-                const int t = filter_pass_tile(P, pass, j);
-                const int tile_end = (t + 1) * FN;
-                mbar_wait(bar_accf + 8 * b, (it >> F_ACCSHIFT) & 1);
+#pragma unroll 1
+            for (int left = ntiles; left > 0; left--, item_base += item_step) {
+                const int tile_end = item_base - slot * F_CHUNK + FN;
+                mbar_wait(bar_accf + 8 * buf, par);
                 tc_fence_after();
                 unsigned v[32];
-                if (!(P.dbg & 8)) tmem_ld32(tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(b * FN + slot * F_CHUNK), v);
+#if RMB_F_DBG
+                if (!(P.dbg & 8))
+#endif
+                tmem_ld32(taddr0 + (unsigned)(buf * FN), v);
                 tc_fence_before();                      // this warp's part of the accumulator is in registers
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acce + 8 * b);
-
+                if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+                if (++buf == F_ACCBUFS) { buf = 0; par ^= 1u; }
+#if RMB_F_DBG
                 if (P.dbg & 1) continue;
-                const float thr = rs->thr[row];
-                const int item_base = t * FN + slot * F_CHUNK;
-                const bool has_train = rs->nxt_train[row] < tile_end;
-                // NaN-propagating max of each group of 8 columns; only groups holding a score >= thr are looked at
+#endif
+                const bool has_train = t_nxt < tile_end;
+                // NaN-propagating max of each group of 8 columns; one compare for the whole chunk, groups only when it passes
+                float gm[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     const float m01 = max_nan(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]));
                     const float m23 = max_nan(__uint_as_float(v[8 * g + 2]), __uint_as_float(v[8 * g + 3]));
                     const float m45 = max_nan(__uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]));
                     const float m67 = max_nan(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
-                    const float m = max_nan(max_nan(m01, m23), max_nan(m45, m67));
-                    if (!(m < thr)) {
-                        F_STAT(2, 1);
-                        // slow path: drop padding columns and train items (hpp:494-495), flag NaN scores (hpp:195-197),
-                        // append the rest to the row's candidate buffer
+                    gm[g] = max_nan(max_nan(m01, m23), max_nan(m45, m67));
+                }
+                if (!(max_nan(max_nan(gm[0], gm[1]), max_nan(gm[2], gm[3])) < thr)) {
 #pragma unroll
-                        for (int jj = 0; jj < 8; jj++) {
-                            const float s = __uint_as_float(v[8 * g + jj]);
-                            if (!(s < thr)) {
-                                const int item = item_base + 8 * g + jj;
-                                if (item < P.n && !(has_train && train_hit(P.tri, rs->tr_cur[row], rs->tr_end[row], item))) {
-                                    if (s != s) rs->flags[row] |= 1;
-                                    else { const int at = atomicAdd(&rs->cnt[row], 1); cs[at] = s; ci[at] = item; F_STAT(0, 1); }
-                                }
-                            }
+                    for (int g = 0; g < 4; g++) {
+                        if (!(gm[g] < thr)) {
+                            F_STAT(2, 1);
+                            const int before = mycnt;
+                            mycnt = filter_append_group<RC>(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]),
+                                                            __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]),
+                                                            __uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), thr, item_base + 8 * g, P.n,
+                                                            P.tri, t_cur, has_train ? t_end : t_cur, cs, ci, mycnt, flag_p);
+                            F_STAT(0, mycnt - before);
+                            (void)before;
                         }
                     }
                 }
+                // move the train cursor past this tile: the id after t_nxt was prefetched into shared memory when the cursor last moved
+                if (has_train) {
+                    F_STAT(3, 1);
+                    asm volatile("cp.async.wait_all;" ::: "memory");
+                    int nxt = rs->nxt2_train[slot][row];
+                    t_cur++;
+                    while (nxt < tile_end) { t_cur++; nxt = t_cur < t_end ? P.tri[t_cur] : INT_MAX; }    // several train items in one tile
+                    t_nxt = nxt;
+                    if (t_cur + 1 < t_end)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&rs->nxt2_train[slot][row])), "l"(P.tri + t_cur + 1) : "memory");
+                    else rs->nxt2_train[slot][row] = INT_MAX;
+                }
+                if (--meet_in >= 0 && left > 1) continue;
+#if RMB_F_DBG
                 if (P.dbg & 4) continue;
-                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");     // the quarter's chunks of this tile are done
-                // rows whose buffer may not take another tile, rows whose train cursor has to move: the same masks in all four warps
-                unsigned need = __ballot_sync(FULL, rs->cnt[row] > C - FN);
-                const unsigned move = __ballot_sync(FULL, rs->nxt_train[row] < tile_end);
-                if (need | move) {
-                    if (slot == 0 && rs->nxt_train[row] < tile_end) {
-                        // the id after the current one was prefetched into shared memory when the cursor last moved (cp.async:
-                        // the three sibling warps wait at the barrier below, a global-memory round trip here would stall them all)
-                        asm volatile("cp.async.wait_all;" ::: "memory");
-                        F_STAT(3, 1);
-                        int cur = rs->tr_cur[row] + 1, nxt = rs->nxt2_train[row];
-                        const int end = rs->tr_end[row];
-                        while (nxt < tile_end) { cur++; nxt = cur < end ? P.tri[cur] : INT_MAX; }    // several train items in one tile
-                        rs->tr_cur[row] = cur;
-                        rs->nxt_train[row] = nxt;
-                        if (cur + 1 < end)
-                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&rs->nxt2_train[row])), "l"(P.tri + cur + 1) : "memory");
-                        else rs->nxt2_train[row] = INT_MAX;
-                    }
+#endif
+
+                // ---- meeting point of the quarter's four warps: publish the region fills, cut rows that grew past their trigger
+                rs->cnt4[slot][row] = mycnt;
+                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+                int c0 = rs->cnt4[0][row], c1 = rs->cnt4[1][row], c2 = rs->cnt4[2][row], c3 = rs->cnt4[3][row];
+                int tot = c0 + c1 + c2 + c3;
+                const int grown = tot - tot_prev;                              // appends to the row since the previous meeting
+                unsigned need = __ballot_sync(FULL, tot > rs->trig[row] && !(rs->flags[row] & 2));
+                if (left == 1) need = 0;                                       // the pass ends with the exact cut below
+                if (need) {                                                    // (the same mask in all four warps)
                     while (need) {
                         const int r = __ffs(need) - 1;
                         need &= need - 1;
@@ -494,37 +517,49 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                         const int rr = q * 32 + r;
                         const size_t base = (size_t)(tile_u0 + rr) * C;
                         float tau_r;
-#if RMB_F_HIST_ROUNDS > 0
-                        const int kept = approx_compact_hist<C, RMB_F_HIST_ROUNDS>(P.cand_approx + base, P.cand_item + base, rs->cnt[rr], Kp, rs->slack[rr],
-                                                                                   lane, rs->hist[warp], &tau_r);
-#else
-                        const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, rs->cnt[rr], Kp, rs->slack[rr], lane, &tau_r);
-#endif
+                        const int kept = cut_regions<C, RMB_F_HIST_ROUNDS, false>(P.cand_approx + base, P.cand_item + base, rs->cnt4[0][rr], rs->cnt4[1][rr],
+                                                                                  rs->cnt4[2][rr], rs->cnt4[3][rr], Kp, rs->slack[rr], lane, rs->hist[warp], &tau_r);
                         if (lane == 0) {
                             F_STAT(1, 1);
                             float thr_r = __fsub_rd(tau_r, rs->slack[rr]);
                             if (!(thr_r == thr_r)) thr_r = -CUDART_INF_F;       // non-finite bound: keep everything
                             thr_r = fmaxf(thr_r, rs->thr[rr]);                  // an earlier (valid) bound may be the sharper one
-                            int cnt_r = kept;
-                            if (kept > C - FN) { rs->flags[rr] |= 2; thr_r = CUDART_INF_F; cnt_r = 0; }   // slack band does not fit
+                            if (kept > 4 * (RC - 32)) { rs->flags[rr] |= 2; thr_r = CUDART_INF_F; }     // the slack band does not fit
                             rs->thr[rr] = thr_r;
-                            rs->cnt[rr] = cnt_r;
+                            rs->trig[rr] = kept + F_CUT_MARGIN;
+#pragma unroll
+                            for (int sgm = 0; sgm < 4; sgm++) rs->cnt4[sgm][rr] = (kept + 3 - sgm) >> 2;
                         }
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+                    c0 = rs->cnt4[0][row]; c1 = rs->cnt4[1][row]; c2 = rs->cnt4[2][row]; c3 = rs->cnt4[3][row];
+                    tot = c0 + c1 + c2 + c3;
+                    mycnt = slot == 0 ? c0 : (slot == 1 ? c1 : (slot == 2 ? c2 : c3));
                 }
+                thr = rs->thr[row];
+                if (rs->flags[row] & 2) { mycnt = 0; thr = CUDART_INF_F; if (slot == 0) rs->thr[row] = CUDART_INF_F; }     // the row is closed: whatever it holds is void
+                tot_prev = tot;
+                // next meeting: far enough that barriers are rare, close enough that no region can fill up at twice the
+                // append rate just seen (all of it into one region); a burst beyond that closes the row (flag 2)
+                const int headroom = RC - max(max(c0, c1), max(c2, c3));
+                int nxt_iv = grown > 0 ? (headroom * interval) / (2 * grown) : F_MAX_MEET;
+                nxt_iv = __reduce_min_sync(FULL, nxt_iv);
+                interval = nxt_iv < 1 ? 1 : (nxt_iv > F_MAX_MEET ? F_MAX_MEET : nxt_iv);
+                meet_in = interval - 1;
             }
-            // end of the pass: the exact Kp-th best approximate score of what each row kept
+            // end of the pass (all four warps are past the last meeting): the exact Kp-th best approximate score of what each
+            // row kept, the survivors packed at the head of the row's buffer
             for (int r = slot; r < 32; r += 4) {
                 const int rr = q * 32 + r;
                 if (rs->thr[rr] == CUDART_INF_F && !(rs->flags[rr] & 2)) continue;    // closed row (not ranked / settled in pass 1)
-                const int nv = rs->cnt[rr];
+                const int c0 = rs->cnt4[0][rr], c1 = rs->cnt4[1][rr], c2 = rs->cnt4[2][rr], c3 = rs->cnt4[3][rr];
+                const int nv = c0 + c1 + c2 + c3;
                 float tau_r = -CUDART_INF_F;
-                bool have_k = false;
-                if (nv >= Kp && !(rs->flags[rr] & 2)) {
+                const bool have_k = nv >= Kp && !(rs->flags[rr] & 2);
+                if (nv > 0 && !(rs->flags[rr] & 2)) {
                     const size_t base = (size_t)(tile_u0 + rr) * C;
-                    const int kept = approx_compact<C>(P.cand_approx + base, P.cand_item + base, nv, Kp, rs->slack[rr], lane, &tau_r);
-                    have_k = true;
+                    const int kept = cut_regions<C, 7, true>(P.cand_approx + base, P.cand_item + base, c0, c1, c2, c3, have_k ? Kp : nv, rs->slack[rr], lane,
+                                                             rs->hist[warp], &tau_r);
                     if (lane == 0 && pass > 0) rs->cnt[rr] = kept;      // last cut: the exact stage gets only what can still be in the top K
                 }
                 if (lane == 0) {
