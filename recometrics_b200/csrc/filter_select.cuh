@@ -46,7 +46,11 @@ namespace rmb {
 
 constexpr int FN = 128;                  // items per MMA tile = TMEM columns per accumulator buffer
 constexpr int F_EPI_WARPS = 16;          // warp w reads TMEM lanes (user rows) 32*(w%4)..+31, column chunk w/4 of every tile
-constexpr int F_THREADS = (F_EPI_WARPS + 2) * 32;   // + TMA producer warp + MMA warp
+#ifndef RMB_F_MMA_WARPS
+#define RMB_F_MMA_WARPS 2                // MMA-issuing warps, taking turns tile by tile: one warp's per-tile barrier waits and commits
+#endif                                   // (~300 cycles in which it issues nothing) overlap with the other warp's MMAs
+constexpr int F_MMA_WARPS = RMB_F_MMA_WARPS;
+constexpr int F_THREADS = (F_EPI_WARPS + 1 + F_MMA_WARPS) * 32;   // + TMA producer warp + MMA warps
 #ifndef RMB_F_ACCBUFS
 #define RMB_F_ACCBUFS 4                  // TMEM accumulator buffers (2 or 4): slack between the MMA warp and the slowest epilogue warp
 #endif
@@ -60,7 +64,7 @@ constexpr int F_CHUNK = 32;              // TMEM columns per tcgen05.ld
 #endif
 constexpr int F_CUT_MARGIN = RMB_F_CUT_MARGIN;
 #ifndef RMB_F_MAX_MEET
-#define RMB_F_MAX_MEET 16                 // most item tiles between two meetings of a quarter's warps
+#define RMB_F_MAX_MEET 64                 // most item tiles between two meetings of a quarter's warps
 #endif
 constexpr int F_MAX_MEET = RMB_F_MAX_MEET;
 
@@ -96,7 +100,7 @@ struct FilterParams {
     int K;
     int sample_tiles, sample_stride, sample_rank;   // pass 0 (see filter_pass_tile); sample_tiles == 0: no sampling
     int* retries;                           // rows that needed the retry pass (statistics; may be nullptr)
-    int dbg;                                // developer switch (env RMB200_DBG): 1 = skip the scan (pipeline ceiling), 2 = no row is ranked (fast path only), 4 = no per-tile meeting, 8 = no tcgen05.ld
+    int dbg;                                // developer switch (env RMB200_DBG): 1 = skip the scan (pipeline ceiling), 2 = no row is ranked (fast path only), 4 = no meetings, 8 = no tcgen05.ld, 16 = no TMA after the first ring round, 32 = half of the k steps (bits honoured only in -DRMB_F_DBG=1 builds)
 };
 
 struct FilterRowState {      // per user row of the CTA, shared by the four epilogue warps of its TMEM lane quarter
@@ -267,13 +271,17 @@ __device__ __noinline__ int filter_append_group(const float s0, const float s1, 
                                                 const int* __restrict__ tri, const int t_lo, const int t_hi,
                                                 float* cs, int* ci, int mycnt, int* flagp)
 {
-    const float sv[8] = {s0, s1, s2, s3, s4, s5, s6, s7};
-#pragma unroll
-    for (int jj = 0; jj < 8; jj++) {
-        const float s = sv[jj];
-        if (s < thr) continue;
+    // which of the 8 pass (branch-free), then one trip per passing score (almost always a single one)
+    unsigned m = (s0 < thr ? 0u : 1u) | (s1 < thr ? 0u : 2u) | (s2 < thr ? 0u : 4u) | (s3 < thr ? 0u : 8u) |
+                 (s4 < thr ? 0u : 16u) | (s5 < thr ? 0u : 32u) | (s6 < thr ? 0u : 64u) | (s7 < thr ? 0u : 128u);
+    while (m) {
+        const int jj = __ffs(m) - 1;
+        m &= m - 1;
+        const float lo4 = (jj & 2) ? ((jj & 1) ? s3 : s2) : ((jj & 1) ? s1 : s0);
+        const float hi4 = (jj & 2) ? ((jj & 1) ? s7 : s6) : ((jj & 1) ? s5 : s4);
+        const float s = (jj & 4) ? hi4 : lo4;
         const int item = item0 + jj;
-        if (item >= n) continue;
+        if (item >= n) break;                                   // padding columns (and all after them)
         bool in_train = false;
         for (int lo = t_lo; lo < t_hi; lo++) {
             const int v = tri[lo];
@@ -352,22 +360,32 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             for (int j = 0; j < ntiles; j++) {
                 mbar_wait(bar_empty + 8 * s, ph ^ 1);                         // first round passes immediately
                 if (elect_one()) {
+#if RMB_F_DBG
+                    if ((P.dbg & 16) && it0 + j >= S) { mbar_arrive(bar_full + 8 * s); } else       // 16: no TMA after the first round (stale tiles)
+#endif
+                    {
                     mbar_arrive_expect_tx(bar_full + 8 * s, tile_bytes);
                     tma_bulk_g2s(smem_u32(b_ring) + (unsigned)s * tile_bytes, P.Bb + (size_t)filter_pass_tile(P, pass, j) * KB * 128, tile_bytes,
                                  bar_full + 8 * s);
+                    }
                 }
                 __syncwarp();
                 if (++s == S) { s = 0; ph ^= 1; }
             }
-        } else if (warp == F_EPI_WARPS + 1) {
-            // ===================== MMA issuer (converged warp, one elected lane issues) =====================
+        } else if (warp > F_EPI_WARPS) {
+            // ===================== MMA issuers (converged warps, one elected lane issues; warp w takes iterations it % F_MMA_WARPS == w) =====================
             // D fp32 (bit 4), A and B fp16 (format 0 at bits 7 and 10), both K-major, N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
             const unsigned idesc = (1u << 4) | ((unsigned)(FN >> 3) << 17) | ((128u >> 4) << 24);
             const uint64_t adesc0 = umma_desc(smem_u32(a_tile)), bdesc0 = umma_desc(smem_u32(b_ring));
-            const int ksteps = KB / 16;                                       // K=16 per MMA = two 16-byte k chunks of 2048 B
-            if (it0 == 0) mbar_wait(bar_a, 0);
-            int s = it0 % S, ph = (it0 / S) & 1;
-            for (int j = 0; j < ntiles; j++) {
+            int ksteps = KB / 16;                                             // K=16 per MMA = two 16-byte k chunks of 2048 B
+#if RMB_F_DBG
+            if (P.dbg & 32) ksteps = ksteps / 2 > 0 ? ksteps / 2 : 1;         // 32: half of the k steps
+#endif
+            const int w = warp - (F_EPI_WARPS + 1);
+            mbar_wait(bar_a, 0);
+            int j = (w - it0 % F_MMA_WARPS + F_MMA_WARPS) % F_MMA_WARPS;      // first iteration of this pass that is this warp's
+            int s = (it0 + j) % S, ph = ((it0 + j) / S) & 1;
+            for (; j < ntiles; j += F_MMA_WARPS) {
                 const int it = it0 + j, b = it & (F_ACCBUFS - 1);
                 mbar_wait(bar_acce + 8 * b, ((it >> F_ACCSHIFT) & 1) ^ 1);     // accumulator buffer drained by the epilogue
                 mbar_wait(bar_full + 8 * s, ph);                              // B tile landed
@@ -383,7 +401,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     umma_commit(bar_accf + 8 * b);                            // accumulator complete
                 }
                 __syncwarp();
-                if (++s == S) { s = 0; ph ^= 1; }
+                s += F_MMA_WARPS;
+                while (s >= S) { s -= S; ph ^= 1; }
             }
         } else {
             // ===================== epilogue warps =====================
