@@ -236,7 +236,7 @@ def product_arm(args, cfg, rank, world, local_rank):
     barrier()
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kernel_ms, launches, path, fallbacks = 0.0, 0, 0, 0
+    kernel_ms, launches, path, fallbacks, retry_rows = 0.0, 0, 0, 0, 0
     phases = {}
     e0.record()
     for _ in range(args.steps):
@@ -246,6 +246,7 @@ def product_arm(args, cfg, rank, world, local_rank):
         for f in ("total_ms", "prep_ms", "score_select_ms", "metrics_ms"):
             phases[f] = phases.get(f, 0.0) + getattr(tm, f) / args.steps
         path, fallbacks = int(tm.scoring_path), fallbacks + int(tm.filter_fallback_batches)
+        retry_rows += int(tm.filter_retry_rows)
     e1.record()
     barrier()
     clocks = sampler.stop()
@@ -274,17 +275,21 @@ def product_arm(args, cfg, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (score_select): algorithmic flops / CUDA-event kernel time
     ach = flops * args.steps / (kernel_ms * 1e-3) / 1e12
-    traffic = None
+    traffic, traffic_note = None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
             traffic = json.load(open(tpath)).get(str(cfg.cfg_id))
+            if isinstance(traffic, dict):      # DRAM bytes of one launch of the dominant kernel, from the committed ncu capture
+                traffic_note = "%s; %s" % (traffic.get("per"), traffic.get("source"))
+                traffic = int(traffic["dram_bytes_read"]) + int(traffic["dram_bytes_write"])
         except Exception:
             traffic = None
     batches = -(-m // (8 * 148 * 128))
     if path == 2:
-        # tensor-core filter: every (user, item) score is an MMA on bf16 copies of the factors; the measured
-        # denominator is the driver's cuBLAS bf16 figure (sustained: the kernel IS the long step)
+        # tensor-core filter: every (user, item) score is an MMA on fp16 copies of the factors (tcgen05 kind::f16 runs
+        # fp16 and bf16 operands at the same rate); the measured denominator is the driver's cuBLAS bf16 figure
+        # (sustained: the kernel IS the long step)
         try:
             mp0 = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
             tpeak, tsrc = float(mp0["bf16_tflops_sustained"]), "MEASURED_PEAKS.json bf16_tflops_sustained (of measured); burst %.1f" % mp0["bf16_tflops"]
@@ -292,10 +297,10 @@ def product_arm(args, cfg, rank, world, local_rank):
             tpeak, tsrc = 1400.0, "fallback 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md; of fallback)"
         roofline = {
             "bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": traffic,
-            "kernel": "filter_select_kernel (tcgen05 bf16 candidate filter; survivors re-scored exactly in %s by exact_topk_kernel)" % ("fp32" if T == np.float32 else "fp64"),
+            "kernel": "filter_select_kernel (tcgen05 fp16 candidate filter, fp32 accumulation in TMEM; survivors re-scored exactly in %s by exact_topk_kernel)" % ("fp32" if T == np.float32 else "fp64"),
             "kernel_ms_per_step": kernel_ms / args.steps, "kernel_share_of_step": kernel_ms / dev_ms if world == 1 else None,
             "algorithmic_flops_per_step": flops, "launches_per_step": batches, "peak_source": tsrc,
-            "fma_peak_tflops_live": peak_tflops, "filter_fallback_batches": fallbacks,
+            "fma_peak_tflops_live": peak_tflops, "filter_fallback_batches": fallbacks, "filter_retry_rows": retry_rows,
         }
     else:
         roofline = {
@@ -307,6 +312,8 @@ def product_arm(args, cfg, rank, world, local_rank):
             "peak_source": "FMA microbenchmark run live on this GPU (rmb200_measure_fma_peak): MEASURED_PEAKS.json holds "
                            "HBM and bf16-tensor peaks only; nominal %s" % ("74.4 TFLOP/s FP32" if T == np.float32 else "37.2 TFLOP/s FP64"),
         }
+    if traffic_note:
+        roofline["traffic_note"] = traffic_note
     try:
         mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         roofline["hbm_peak_gbs_measured"] = mp.get("hbm_gbs")
