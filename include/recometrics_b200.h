@@ -93,10 +93,22 @@ typedef struct rmb200_extra {
                                 /* 2 NaN by the cand<=K rule (hpp:485-486), 3 NaN by score validity     */
     rmb200_timing_t *timing;    /* optional out                                                        */
     int32_t scoring_path;       /* 0 = automatic; 1 = FP32/FP64 FMA tiles for every score; 2 = tensor-core     */
-                                /* (bf16 tcgen05) candidate filter + exact FMA re-scoring of the survivors:    */
+                                /* (fp16 tcgen05) candidate filter + exact FMA re-scoring of the survivors:    */
                                 /* same top-K, same scores; not available with ROC/PR-AUC (rank counting).     */
                                 /* Env RMB200_PATH=fma|tensor overrides 0.                                     */
-    int32_t reserved_;
+    int32_t skip_row_copy;      /* 1 (host-pointer calls): the per-user rows of every requested metric are computed  */
+                                /* in device memory but NOT copied back -- the non-NULL output pointers only say    */
+                                /* which metrics are wanted and are left untouched; use with metric_means           */
+    double  *metric_means;      /* optional out [10 * W], W = cumulative ? k_metrics : 1: mean over the users of   */
+                                /* this call ([user_begin, user_end)) of every requested metric, NaN rows left out */
+                                /* (numpy.nanmean of the per-user output -- the step that follows the call in the   */
+                                /* reference's examples, examples/recometrics_example.ipynb cell 15); row q of the  */
+                                /* table = metric q in the order of the signature (p, tp, r, ap, tap, ndcg, hit,    */
+                                /* rr, roc_auc, pr_auc; the last two use column 0).  Computed on the device from    */
+                                /* the metric rows in double, in a fixed order (results are reproducible); NaN for */
+                                /* metrics that were not requested or have no valid user.  Host pointer, or device */
+                                /* pointer when inputs_on_device.                                                   */
+    int64_t *metric_counts;     /* optional out [10 * W]: users that entered each mean                              */
 } rmb200_extra_t;
 
 /* Drop-in for calc_metrics_float (src/recometrics_signatures.hpp:73-98).  Returns rmb200_status. */
@@ -154,6 +166,9 @@ RMB200_API int rmb200_calc_metrics_ex_f64(
 RMB200_API int rmb200_device_count(void);
 /* RMB200_VERSION of the loaded library. */
 RMB200_API int rmb200_version(void);
+/* sizeof(rmb200_extra_t) / sizeof(rmb200_timing_t) as compiled into the library (bindings check their mirrors against it). */
+RMB200_API int rmb200_sizeof_extra(void);
+RMB200_API int rmb200_sizeof_timing(void);
 /* Message of the last failing call on this thread ("" if none).  Never NULL. */
 RMB200_API const char *rmb200_last_error(void);
 /* Ask a running call to stop at the next user-batch boundary (what SIGINT does). */

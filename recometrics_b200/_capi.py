@@ -24,6 +24,7 @@ EXPORTS = (
     "rmb200_calc_metrics_ex_f32", "rmb200_calc_metrics_ex_f64",
     "rmb200_device_count", "rmb200_version", "rmb200_last_error",
     "rmb200_request_interrupt", "rmb200_measure_fma_peak", "rmb200_release_workspace",
+    "rmb200_sizeof_extra", "rmb200_sizeof_timing",
 )
 
 
@@ -48,7 +49,8 @@ class Extra(ctypes.Structure):
         ("topk_items", ctypes.c_void_p), ("topk_scores", ctypes.c_void_p),
         ("pos_rank", ctypes.c_void_p), ("status", ctypes.c_void_p),
         ("timing", ctypes.POINTER(Timing)),
-        ("scoring_path", ctypes.c_int32), ("reserved_", ctypes.c_int32),
+        ("scoring_path", ctypes.c_int32), ("skip_row_copy", ctypes.c_int32),
+        ("metric_means", ctypes.c_void_p), ("metric_counts", ctypes.c_void_p),
     ]
 
 
@@ -74,6 +76,10 @@ def load():
             raise NativeLibraryError("recometrics_b200: %s does not export %s" % (LIB_PATH, name))
     lib.rmb200_device_count.restype = ctypes.c_int
     lib.rmb200_version.restype = ctypes.c_int
+    lib.rmb200_sizeof_extra.restype = ctypes.c_int
+    lib.rmb200_sizeof_timing.restype = ctypes.c_int
+    if lib.rmb200_sizeof_extra() != ctypes.sizeof(Extra) or lib.rmb200_sizeof_timing() != ctypes.sizeof(Timing):
+        raise NativeLibraryError("recometrics_b200: %s was built from a different include/recometrics_b200.h (struct sizes differ); rebuild it" % LIB_PATH)
     lib.rmb200_last_error.restype = ctypes.c_char_p
     lib.rmb200_request_interrupt.restype = None
     lib.rmb200_release_workspace.restype = None
@@ -160,7 +166,8 @@ def calc_metrics(dtype, A, lda, B, ldb, m, n, k, trp, tri, tep, tei, tev, k_metr
 
 
 def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, strict_min_pos_test=False,
-               topk_items=None, topk_scores=None, pos_rank=None, status=None, timing=None, scoring_path=0):
+               topk_items=None, topk_scores=None, pos_rank=None, status=None, timing=None, scoring_path=0,
+               metric_means=None, metric_counts=None, skip_row_copy=False):
     ex = Extra()
     ex.struct_size = ctypes.sizeof(Extra)
     ex.device = int(device)
@@ -173,6 +180,9 @@ def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, stri
     ex.topk_scores = _vp(topk_scores)
     ex.pos_rank = _vp(pos_rank)
     ex.status = _vp(status)
+    ex.metric_means = _vp(metric_means)
+    ex.metric_counts = _vp(metric_counts)
+    ex.skip_row_copy = int(bool(skip_row_copy))
     if timing is not None:
         ex.timing = ctypes.pointer(timing)
     return ex

@@ -289,8 +289,9 @@ int run_call(const CallArgs<T>& a)
     if (ex && ex->struct_size != (int32_t)sizeof(rmb200_extra_t)) { set_err("bad argument", "rmb200_extra_t::struct_size mismatch"); return RMB200_ERR_BAD_ARG; }
     bool any_out = false;
     for (int q = 0; q < 10; q++) any_out |= (a.out[q] != nullptr);
+    const bool want_means = ex && (ex->metric_means || ex->metric_counts);
     const bool want_extras = ex && (ex->topk_items || ex->topk_scores || ex->pos_rank || ex->status);
-    if (!any_out && !want_extras) return RMB200_OK;
+    if (!any_out && !want_extras && !want_means) return RMB200_OK;
 
     int ub = 0, ue = a.m;
     if (ex && (ex->user_begin != 0 || ex->user_end != 0)) { ub = ex->user_begin; ue = ex->user_end; }
@@ -565,6 +566,16 @@ int run_call(const CallArgs<T>& a)
         if (ex && ex->status) CK(d_stat_out.alloc((size_t)UB * sizeof(int)));
     }
 
+    // per-metric means over the users of the call (extension): partial sums per 256 users, added up in order at the end
+    DevBuf d_psum, d_pcnt, d_means, d_mcounts;
+    const int mean_W = a.cumulative ? K : 1;
+    int mean_blocks_total = 0, mean_block0 = 0;
+    if (want_means) {
+        for (int b0 = 0; b0 < mr; b0 += UB) mean_blocks_total += (((mr - b0) < UB ? (mr - b0) : UB) + MEAN_CHUNK - 1) / MEAN_CHUNK;
+        CK(d_psum.alloc((size_t)mean_blocks_total * 10 * mean_W * sizeof(double)));
+        CK(d_pcnt.alloc((size_t)mean_blocks_total * 10 * mean_W * sizeof(int)));
+    }
+
     for (int b0 = 0; b0 < mr; b0 += UB) {
         if (g_interrupt.load()) break;                     // hpp:488-489
         const int nb = (mr - b0) < UB ? (mr - b0) : UB;
@@ -711,6 +722,16 @@ int run_call(const CallArgs<T>& a)
             user_metrics_kernel<T><<<(nb + 127) / 128, 128, 0, st>>>(mp);
             CK(cudaGetLastError());
             tm.kernel_launches++;
+            if (want_means) {
+                MeanParams<T> qp;
+                for (int q = 0; q < 10; q++) qp.out[q] = outs[q];
+                qp.nb = nb; qp.W = mean_W; qp.part_sum = d_psum.as<double>(); qp.part_cnt = d_pcnt.as<int>(); qp.block0 = mean_block0;
+                const int blocks = (nb + MEAN_CHUNK - 1) / MEAN_CHUNK;
+                metric_partial_kernel<T><<<dim3(blocks, 10), MEAN_CHUNK, 0, st>>>(qp);
+                CK(cudaGetLastError());
+                tm.kernel_launches++;
+                mean_block0 += blocks;
+            }
         }
         pt.stop(tm.metrics_ms);
 
@@ -719,7 +740,7 @@ int run_call(const CallArgs<T>& a)
         if (!on_dev) {
             pt.start();
             for (int q = 0; q < 10; q++) {
-                if (!a.out[q]) continue;
+                if (!a.out[q] || (ex && ex->skip_row_copy)) continue;
                 const size_t stride = q < 8 ? rs : 1;
                 const size_t bytes = (size_t)nb * stride * sizeof(T);
                 CK(cudaMemcpyAsync(a.out[q] + (size_t)(ub + b0) * stride, d_out[q].p, bytes, cudaMemcpyDeviceToHost, st));
@@ -736,6 +757,24 @@ int run_call(const CallArgs<T>& a)
         CK(cudaMemcpyAsync(ex->pos_rank + lo_hi[2], pos_rank_d, nnz_te * sizeof(long long), cudaMemcpyDeviceToHost, st));
         tm.d2h_bytes += (int64_t)(nnz_te * sizeof(long long));
         pt.stop(tm.d2h_ms);
+    }
+    if (want_means && !g_interrupt.load()) {
+        double* means_d = nullptr; long long* counts_d = nullptr;
+        const size_t cells = (size_t)10 * mean_W;
+        if (on_dev) { means_d = ex->metric_means; counts_d = reinterpret_cast<long long*>(ex->metric_counts); }
+        else {
+            if (ex->metric_means) { CK(d_means.alloc(cells * sizeof(double))); means_d = d_means.as<double>(); }
+            if (ex->metric_counts) { CK(d_mcounts.alloc(cells * sizeof(long long))); counts_d = d_mcounts.as<long long>(); }
+        }
+        pt.start();
+        metric_final_kernel<<<(int)((cells + 127) / 128), 128, 0, st>>>(d_psum.as<double>(), d_pcnt.as<int>(), mean_block0, mean_W, means_d, counts_d);
+        CK(cudaGetLastError());
+        tm.kernel_launches++;
+        pt.stop(tm.metrics_ms);
+        if (!on_dev) {
+            if (ex->metric_means) { CK(cudaMemcpyAsync(ex->metric_means, means_d, cells * sizeof(double), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)(cells * sizeof(double)); }
+            if (ex->metric_counts) { CK(cudaMemcpyAsync(ex->metric_counts, counts_d, cells * sizeof(long long), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)(cells * sizeof(long long)); }
+        }
     }
     CK(cudaStreamSynchronize(st));
 
@@ -856,6 +895,10 @@ int rmb200_device_count(void)
 }
 
 int rmb200_version(void) { return RMB200_VERSION; }
+
+int rmb200_sizeof_extra(void) { return (int)sizeof(rmb200_extra_t); }
+
+int rmb200_sizeof_timing(void) { return (int)sizeof(rmb200_timing_t); }
 
 const char* rmb200_last_error(void) { return g_err.c_str(); }
 

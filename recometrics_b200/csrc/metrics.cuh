@@ -284,4 +284,73 @@ __global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
     }
 }
 
+// ---------------------------------------------------------------- per-metric means over users (extension)
+// numpy.nanmean of the per-user rows, on the device and in a fixed summation order:
+//   metric_partial_kernel  one block per 256 users of a batch and metric (blockIdx.y): sum and count of the non-NaN
+//                          entries of every column (W = K if cumulative else 1), users in ascending order
+//   metric_final_kernel    one thread per (metric, column): adds the blocks' partials in ascending order, divides
+constexpr int MEAN_CHUNK = 256;
+
+template <typename T>
+struct MeanParams {
+    const T* out[10];        // metric rows of the batch (nullptr: not requested), row stride W (roc/pr: 1)
+    int nb, W;
+    double* part_sum;        // [blocks_total][10][W]
+    int* part_cnt;
+    int block0;              // first partial block of this batch
+};
+
+template <typename T>
+__global__ void metric_partial_kernel(const __grid_constant__ MeanParams<T> P)
+{
+    const int q = blockIdx.y;
+    const T* src = P.out[q];
+    const int W = P.W, Wq = q < 8 ? W : 1;
+    const int u0 = blockIdx.x * MEAN_CHUNK;
+    const int u1 = min(u0 + MEAN_CHUNK, P.nb);
+    double* ps = P.part_sum + ((size_t)(P.block0 + blockIdx.x) * 10 + q) * W;
+    int* pc = P.part_cnt + ((size_t)(P.block0 + blockIdx.x) * 10 + q) * W;
+    if (Wq > 1) {
+        // a thread per column walks the chunk's users in order (consecutive threads read consecutive columns)
+        for (int c = threadIdx.x; c < W; c += blockDim.x) {
+            double s = 0.;
+            int cnt = 0;
+            if (src)
+                for (int u = u0; u < u1; u++) {
+                    const double v = (double)src[(size_t)u * Wq + c];
+                    if (v == v) { s += v; cnt++; }
+                }
+            ps[c] = s;
+            pc[c] = cnt;
+        }
+    } else {
+        // one value per user: fixed-shape tree over the chunk
+        __shared__ double sh_s[MEAN_CHUNK];
+        __shared__ int sh_c[MEAN_CHUNK];
+        const int u = u0 + threadIdx.x;
+        double v = (src && u < u1) ? (double)src[u] : CUDART_NAN;
+        sh_s[threadIdx.x] = (v == v) ? v : 0.;
+        sh_c[threadIdx.x] = (v == v) ? 1 : 0;
+        __syncthreads();
+        for (int o = MEAN_CHUNK / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o) { sh_s[threadIdx.x] += sh_s[threadIdx.x + o]; sh_c[threadIdx.x] += sh_c[threadIdx.x + o]; }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) { ps[0] = sh_s[0]; pc[0] = sh_c[0]; }
+        for (int c = 1 + threadIdx.x; c < W; c += blockDim.x) { ps[c] = 0.; pc[c] = 0; }
+    }
+}
+
+__global__ void metric_final_kernel(const double* __restrict__ part_sum, const int* __restrict__ part_cnt, const int blocks,
+                                    const int W, double* __restrict__ means, long long* __restrict__ counts)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // (metric, column)
+    if (i >= 10 * W) return;
+    double s = 0.;
+    long long c = 0;
+    for (int b = 0; b < blocks; b++) { s += part_sum[(size_t)b * 10 * W + i]; c += part_cnt[(size_t)b * 10 * W + i]; }
+    if (means) means[i] = c > 0 ? s / (double)c : CUDART_NAN;
+    if (counts) counts[i] = c;
+}
+
 }  // namespace rmb

@@ -40,6 +40,8 @@ class EvalResult:
     topk_items: np.ndarray = None
     topk_scores: np.ndarray = None
     pos_rank: np.ndarray = None
+    means: dict = None       # return_means: reference-style keys -> mean over the evaluated users (NaN rows left out)
+    counts: dict = None      # ... -> how many users entered each mean
 
 
 def _rows_c_layout(X):
@@ -174,13 +176,17 @@ def calc_reco_metrics_ex(
         all_metrics=False, break_ties_with_noise=True, min_pos_test=1, min_items_pool=2,
         consider_cold_start=True, cumulative=False, nthreads=-1, seed=1,
         device=-1, user_range=None, strict_min_pos_test=False,
-        return_topk=False, return_ranks=False, return_status=False, scoring_path="auto"):
+        return_topk=False, return_ranks=False, return_status=False, scoring_path="auto",
+        return_means=False, means_only=False):
     """Same evaluation as :func:`calc_reco_metrics`, returning an :class:`EvalResult` with the
     reference-style dict plus timing and the optional extras (top-K ids/scores, held-out ranks,
     per-user status).  ``user_range=(begin, end)`` evaluates only those rows (the sharding unit);
     rows outside it are left as NaN in the returned arrays.  ``scoring_path``: "auto" | "fma" (every score on
     the FP32/FP64 FMA pipe) | "tensor" (bf16 tensor-core candidate filter + exact FMA re-scoring of the
-    survivors: identical top-K and scores, top-K metrics only)."""
+    survivors: identical top-K and scores, top-K metrics only).  ``return_means``: also reduce every requested
+    metric to its mean over the evaluated users on the device (``numpy.nanmean`` of the per-user output; ``(k,)`` vectors
+    when ``cumulative``) -- ``result.means`` / ``result.counts``; with ``means_only`` the per-user rows are not copied
+    back at all (``result.metrics`` then only holds ``"K"``)."""
     flags = dict(p=precision, tp=trunc_precision, r=recall, ap=average_precision, tap=trunc_average_precision,
                  ndcg=ndcg, hit=hit, rr=rr, roc=roc_auc, pr=pr_auc)
     flags = {q: bool(v) or bool(all_metrics) for q, v in flags.items()}
@@ -202,21 +208,35 @@ def calc_reco_metrics_ex(
     topk_scores = np.full(m * K, np.nan, dtype=dtype) if return_topk else None
     pos_rank = np.zeros(max(int(prep["tep"][-1]), 1), dtype=np.int64) if return_ranks else None
     ub, ue = (0, 0) if user_range is None else (int(user_range[0]), int(user_range[1]))
+    return_means = bool(return_means) or bool(means_only)
+    W = K if cumulative else 1
+    means = np.full(10 * W, np.nan, dtype=np.float64) if return_means else None
+    counts = np.zeros(10 * W, dtype=np.int64) if return_means else None
     extra = _capi.make_extra(device=device, user_begin=ub, user_end=ue, strict_min_pos_test=strict_min_pos_test,
                              topk_items=topk_items, topk_scores=topk_scores, pos_rank=pos_rank, status=status,
-                             timing=timing, scoring_path=scoring_path)
+                             timing=timing, scoring_path=scoring_path, metric_means=means, metric_counts=counts,
+                             skip_row_copy=bool(means_only))
     rc = _capi.calc_metrics(dtype, prep["A"], prep["lda"], prep["B"], prep["ldb"], m, prep["n"], prep["p"],
                             prep["trp"], prep["tri"], prep["tep"], prep["tei"], prep["tev"], K, cumulative,
                             bool(break_ties_with_noise), outs, prep["consider_cold_start"], prep["min_items_pool"],
                             prep["min_pos_test"], prep["nthreads"], prep["seed"], prep["item_biases"], extra)
     _capi.raise_for_status(rc)
 
-    metrics = {}
+    metrics, mean_d, count_d = {}, None, None
     for q, key in _KEYS:
-        if q in outs:
+        if q in outs and not means_only:
             metrics[key] = outs[q].reshape(m, K) if (cumulative and q in _capi.TOPK_METRICS) else outs[q]
     metrics["K"] = K
-    return EvalResult(metrics=metrics, timing=timing.as_dict(), status=status,
+    if return_means:
+        mean_d, count_d = {}, {}
+        for i, q in enumerate(_capi.METRIC_ORDER):
+            if q not in outs:
+                continue
+            key = dict(_KEYS)[q]
+            wide = cumulative and q in _capi.TOPK_METRICS
+            mean_d[key] = means[i * W:(i + 1) * W].copy() if wide else float(means[i * W])
+            count_d[key] = counts[i * W:(i + 1) * W].copy() if wide else int(counts[i * W])
+    return EvalResult(metrics=metrics, timing=timing.as_dict(), status=status, means=mean_d, counts=count_d,
                       topk_items=None if topk_items is None else topk_items.reshape(m, K),
                       topk_scores=None if topk_scores is None else topk_scores.reshape(m, K),
                       pos_rank=None if pos_rank is None else pos_rank[: int(prep["tep"][-1])])

@@ -38,10 +38,14 @@ def test_library_exports_every_declared_symbol(rb):
 def test_extra_struct_layout_matches_header(rb):
     """ctypes mirror of rmb200_extra_t / rmb200_timing_t has the C layout (LP64)."""
     from recometrics_b200 import _capi
-    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 6 * 8
-    assert ctypes.sizeof(_capi.Extra) == 6 * 4 + 5 * 8 + 2 * 4
+    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 7 * 8
+    assert ctypes.sizeof(_capi.Extra) == 6 * 4 + 5 * 8 + 2 * 4 + 2 * 8
     assert _capi.Extra.topk_items.offset == 24
     assert _capi.Extra.scoring_path.offset == 64
+    assert _capi.Extra.metric_means.offset == 72
+    lib = _capi.load()          # the sizes the library itself was compiled with
+    assert lib.rmb200_sizeof_extra() == ctypes.sizeof(_capi.Extra)
+    assert lib.rmb200_sizeof_timing() == ctypes.sizeof(_capi.Timing)
 
 
 def test_no_device_means_error_not_fallback(rb):

@@ -356,3 +356,60 @@ def test_tensor_path_refuses_rank_counting(rb):
     with pytest.raises(NotImplementedError):
         rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, roc_auc=True, break_ties_with_noise=False,
                                 scoring_path="tensor")
+
+
+def test_sampled_threshold_guess_and_retry_pass(rb, monkeypatch):
+    """Catalogues of >= 64K items start the filter's thresholds from a sampled guess (filter_select.cuh pass 0) and
+    verify it; a deliberately hopeless guess (the best item of the sample) sends rows through the retry pass.
+    Either way the ranked ids and scores are the FMA path's, bit for bit."""
+    d = synth.make(4, m=300, n=70000)
+    kw = dict(k=100, precision=True, recall=True, average_precision=True, ndcg=True, break_ties_with_noise=False,
+              return_topk=True, return_status=True)
+    monkeypatch.delenv("RMB200_SAMPLE_RANK", raising=False)
+    ref = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], scoring_path="fma", **kw)
+    for rank, d64 in ((None, False), ("1", False), ("1", True)):
+        if rank is None:
+            monkeypatch.delenv("RMB200_SAMPLE_RANK", raising=False)
+        else:
+            monkeypatch.setenv("RMB200_SAMPLE_RANK", rank)
+        A, B = (d["A"].astype(np.float64), d["B"].astype(np.float64)) if d64 else (d["A"], d["B"])
+        want = ref if not d64 else rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, scoring_path="fma", **kw)
+        r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, scoring_path="tensor", **kw)
+        assert r.timing["scoring_path"] == 2 and r.timing["filter_fallback_batches"] == 0
+        if rank == "1":
+            assert r.timing["filter_retry_rows"] > 0
+        assert np.array_equal(want.status, r.status)
+        assert np.array_equal(want.topk_items, r.topk_items)
+        assert np.array_equal(want.topk_scores, r.topk_scores, equal_nan=True)
+        for key in ("P@K", "R@K", "AP@K", "NDCG@K"):
+            assert np.array_equal(want.metrics[key], r.metrics[key], equal_nan=True), key
+
+
+@pytest.mark.parametrize("cumulative", [False, True])
+def test_metric_means_on_device(rb, cumulative):
+    """Extension (SURVEY 8f-2): per-metric means over users, reduced on the device, equal numpy.nanmean of the rows;
+    means_only leaves the per-user rows on the device."""
+    d = synth.make(1, m=1500, n=1200, p=16)
+    kw = dict(k=7, all_metrics=True, break_ties_with_noise=False, cumulative=cumulative)
+    r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], return_means=True, **kw)
+    assert set(r.means) == {k for k in r.metrics if k != "K"}
+    for key, rows in r.metrics.items():
+        if key == "K":
+            continue
+        rows = np.asarray(rows, dtype=np.float64)
+        want_cnt = (~np.isnan(rows)).sum(axis=0)
+        assert np.array_equal(np.asarray(r.counts[key]), want_cnt), key
+        with np.errstate(invalid="ignore"):
+            want = np.nansum(rows, axis=0) / want_cnt
+        assert np.allclose(np.asarray(r.means[key]), want, rtol=1e-12, atol=0, equal_nan=True), key
+    only = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], means_only=True, user_range=(100, 1400), **kw)
+    assert list(only.metrics) == ["K"]
+    sub = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], user_range=(100, 1400), **kw)
+    for key, rows in sub.metrics.items():
+        if key == "K":
+            continue
+        rows = np.asarray(rows, dtype=np.float64)[100:1400]
+        with np.errstate(invalid="ignore"):
+            want = np.nansum(rows, axis=0) / (~np.isnan(rows)).sum(axis=0)
+        assert np.allclose(np.asarray(only.means[key]), want, rtol=1e-12, atol=0, equal_nan=True), key
+    assert only.timing["d2h_bytes"] < sub.timing["d2h_bytes"] / 10
