@@ -106,7 +106,7 @@ def ref_calc(A, B, Xtr, Xte, k, metrics=("p", "ap", "ndcg"), cumulative=False,
 
 def oracle_calc(A, B, Xtr, Xte, k, metrics=("p", "ap", "ndcg"), cumulative=False,
                 consider_cold_start=True, min_items_pool=2, min_pos_test=1, nthreads=1,
-                fix_quirks=True, extras=False, dtype=np.float32):
+                fix_quirks=True, extras=False, break_ties_with_noise=False, seed=1, dtype=np.float32):
     """Run the C restatement.  With extras=True also returns status / top-K ids+scores / ranks."""
     lib = _lib(ORACLE_SO)
     A, B, trp, tri, tep, tei, tev = _prep(A, B, Xtr, Xte, dtype)
@@ -124,7 +124,7 @@ def oracle_calc(A, B, Xtr, Xte, k, metrics=("p", "ap", "ndcg"), cumulative=False
             _i32(k), _int(int(cumulative)),
             *[_ptr(outs[q]) for q in METRICS],
             _int(int(consider_cold_start)), _i32(min_items_pool), _i32(min_pos_test),
-            _i32(nthreads), _int(int(fix_quirks)),
+            _i32(nthreads), _int(int(fix_quirks)), _int(int(break_ties_with_noise)), _u64(seed),
             _ptr(status), _ptr(topk_items), _ptr(topk_scores), _ptr(pos_rank), _ptr(tie_flags))
     if rc != 0:
         raise MemoryError("oracle allocation failed")

@@ -64,6 +64,60 @@ static void FN(fill_nan)(const FN(outs_t) *o, int32_t user, int32_t K, int cumul
     if (o->pr) o->pr[user] = (REAL)NAN;
 }
 
+/* src/recometrics.hpp:531-534  per-user tie-breaking noise:
+ *     std::mt19937 rng_user(seed + (uint64_t)user);
+ *     std::uniform_real_distribution<real_t> runif((real_t)(-1e-12), (real_t)1e-12);
+ *     for (ix < move_to) pred[ind[ix]] += runif(rng_user);
+ * restated from the published algorithms: MT19937 (Matsumoto & Nishimura 1998; the parameters of
+ * std::mt19937, seeded with value mod 2^32) and libstdc++ 13's uniform_real_distribution =
+ * generate_canonical<real_t, digits>(rng) * (b - a) + a, where generate_canonical draws
+ * ceil(digits / 32) words (1 for float, 2 for double), sums them as real_t(word) * 2^(32 i), divides by
+ * 2^(32 m) and replaces a result >= 1 by nextafter(1, 0).  Pinned against the compiled reference by the
+ * noise cases of tests/golden (tie-heavy inputs whose ranking is decided by the noise alone). */
+#ifndef RMO_MT_DEFINED
+#define RMO_MT_DEFINED
+typedef struct { uint32_t x[624]; int pos; } rmo_mt_t;
+static void rmo_mt_seed(rmo_mt_t *g, uint64_t value)
+{
+    g->x[0] = (uint32_t)(value & 0xffffffffu);
+    for (int i = 1; i < 624; i++) g->x[i] = 1812433253u * (g->x[i-1] ^ (g->x[i-1] >> 30)) + (uint32_t)i;
+    g->pos = 624;
+}
+static uint32_t rmo_mt_next(rmo_mt_t *g)
+{
+    if (g->pos >= 624) {
+        for (int k = 0; k < 624; k++) {
+            const uint32_t y = (g->x[k] & 0x80000000u) | (g->x[(k + 1) % 624] & 0x7fffffffu);
+            g->x[k] = g->x[(k + 397) % 624] ^ (y >> 1) ^ ((y & 1u) ? 0x9908b0dfu : 0u);
+        }
+        g->pos = 0;
+    }
+    uint32_t z = g->x[g->pos++];
+    z ^= (z >> 11);
+    z ^= (z << 7) & 0x9d2c5680u;
+    z ^= (z << 15) & 0xefc60000u;
+    z ^= (z >> 18);
+    return z;
+}
+#endif
+
+static inline REAL FN(runif)(rmo_mt_t *g)
+{
+    REAL sum, tmp;
+    if (sizeof(REAL) == 4) {
+        sum = (REAL)rmo_mt_next(g);
+        tmp = (REAL)4294967296.0;
+    } else {
+        sum = (REAL)rmo_mt_next(g);
+        sum += (REAL)rmo_mt_next(g) * (REAL)4294967296.0;
+        tmp = (REAL)4294967296.0 * (REAL)4294967296.0;
+    }
+    REAL ret = sum / tmp;
+    if (ret >= (REAL)1) ret = (sizeof(REAL) == 4) ? (REAL)nextafterf(1.0f, 0.0f) : (REAL)nextafter(1.0, 0.0);
+    const REAL a = (REAL)(-1e-12), b = (REAL)1e-12;
+    return FMA(ret, b - a, a);      /* the reference's C++ build contracts (u * (b - a)) + a into one fma */
+}
+
 /* One user of the loop at src/recometrics.hpp:437-962.
  * scratch: pred[n], ind[n], tmp[n], isnew mask[n] */
 static int32_t FN(one_user)(
@@ -74,7 +128,7 @@ static int32_t FN(one_user)(
     const int32_t *restrict tep, const int32_t *restrict tei, const REAL *restrict tev,
     int32_t K, int cumulative, const FN(outs_t) *o,
     int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test,
-    int fix_quirks,
+    int fix_quirks, int noise, uint64_t seed,
     REAL *pred, int32_t *ind, int32_t *tmp, unsigned char *mask,
     int32_t *topk_items, REAL *topk_scores, int64_t *pos_rank, int32_t *tie_flag)
 {
@@ -122,11 +176,24 @@ static int32_t FN(one_user)(
      * the documented rule. */
     if (has_nan) { FN(fill_nan)(o, user, K, cumulative); return 3; }
 
+    if (noise) {
+        /* :516-534 validity of the noise branch (every candidate: NaN above, all equal, infinite extremes), then the noise */
+        REAL pred_max = pred[ind[0]], pred_min = pred[ind[0]];
+        for (int32_t ix = 1; ix < cand; ix++) {
+            if (pred_max < pred[ind[ix]]) pred_max = pred[ind[ix]];
+            if (pred_min > pred[ind[ix]]) pred_min = pred[ind[ix]];
+        }
+        if (pred_max == pred_min || isinf(pred_max) || isinf(pred_min)) { FN(fill_nan)(o, user, K, cumulative); return 3; }
+        rmo_mt_t g;
+        rmo_mt_seed(&g, seed + (uint64_t)user);
+        for (int32_t ix = 0; ix < cand; ix++) pred[ind[ix]] += FN(runif)(&g);
+    }
+
     /* :537-563 ranking + validity.  The oracle always produces the full order; which pair of
      * scores is checked depends on the branch the reference takes. */
     FN(merge_sort)(ind, tmp, cand, pred);
     const int partial_path = ((!o->roc || only_ndcg) && K < cand);
-    {
+    if (!noise) {          /* :541-548, :555-562: only the noise-off branch looks at the sorted extremes */
         REAL pred_max = pred[ind[0]];
         REAL pred_min = partial_path ? pred[ind[K-1]] : pred[ind[cand-1]];
         if (isnan(pred_max) || isnan(pred_min) || isinf(pred_max) || isinf(pred_min) ||
@@ -356,7 +423,7 @@ int FN(rmo_calc_metrics)(
     REAL *p_at_k, REAL *tp_at_k, REAL *r_at_k, REAL *ap_at_k, REAL *tap_at_k,
     REAL *ndcg_at_k, REAL *hit_at_k, REAL *rr_at_k, REAL *roc_auc, REAL *pr_auc,
     int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test,
-    int32_t nthreads, int fix_quirks,
+    int32_t nthreads, int fix_quirks, int break_ties_with_noise, uint64_t seed,
     int32_t *status, int32_t *topk_items, REAL *topk_scores, int64_t *pos_rank, int32_t *tie_flags)
 {
     if (nthreads < 1) nthreads = 1;
@@ -391,7 +458,7 @@ int FN(rmo_calc_metrics)(
 #endif
         int32_t s = FN(one_user)(user, A, lda, B, ldb, n, k, Xtrain_p, Xtrain_i, Xtest_p, Xtest_i, Xtest_v,
                                  k_metrics, cumulative, &o, consider_cold_start, min_items_pool, min_pos_test,
-                                 fix_quirks,
+                                 fix_quirks, break_ties_with_noise, seed,
                                  pred + t*nn, ind + t*nn, tmp + t*nn, mask + t*nn,
                                  topk_items, topk_scores, pos_rank, tie_flags ? tie_flags + user : NULL);
         if (status) status[user] = s;

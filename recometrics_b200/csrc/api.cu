@@ -170,6 +170,7 @@ struct CallArgs {
     int K, cumulative, noise;
     T* out[10];   // p tp r ap tap ndcg hit rr roc pr
     int consider_cold_start, min_items_pool, min_pos_test;
+    uint64_t seed;
     const T* bias;
     const rmb200_extra_t* ex;
 };
@@ -214,30 +215,35 @@ inline cudaError_t launch_filter_select(const rmb::FilterParams& P, int C, int n
     return launch_filter_inst<1024>(P, n_user_tiles, st);
 }
 
+struct NoiseArgs { int on; unsigned long long seed_user0; const int* trp; const int* tri; int n; };
+
 template <typename T, int C>
 cudaError_t launch_exact_topk_inst(const float* capx, T* cs, int* ci, int* cc, int nb, int user0, const T* At, int p_pad, int p,
-                                   const T* Brow, size_t ldb, const T* bias, int* uflags, int K, cudaStream_t st)
+                                   const T* Brow, size_t ldb, const T* bias, int* uflags, int K, const NoiseArgs& nz, cudaStream_t st)
 {
     const int blocks = (nb + rmb::EXACT_WARPS - 1) / rmb::EXACT_WARPS;
-    const size_t smem = rmb::exact_topk_smem_bytes(p_pad, sizeof(T));
-    if (smem <= 100 * 1024) {       // two blocks per SM
+    const size_t staging = (rmb::exact_topk_smem_bytes(p_pad, sizeof(T)) + 15) & ~size_t(15);
+    const size_t mt_bytes = nz.on ? (size_t)rmb::EXACT_WARPS * rmb::MT_N * sizeof(unsigned) : 0;   // generator states (tie_noise.cuh)
+    if (staging + mt_bytes <= 100 * 1024) {       // two blocks per SM
         auto kern = rmb::exact_topk_kernel<T, C, true>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(staging + mt_bytes));
         if (e != cudaSuccess) return e;
-        kern<<<blocks, rmb::EXACT_WARPS * 32, smem, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
+        kern<<<blocks, rmb::EXACT_WARPS * 32, staging + mt_bytes, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K,
+                                                                        nz.on, nz.seed_user0, staging, nz.trp, nz.tri, nz.n);
     } else {
-        rmb::exact_topk_kernel<T, C, false><<<blocks, rmb::EXACT_WARPS * 32, 0, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K);
+        rmb::exact_topk_kernel<T, C, false><<<blocks, rmb::EXACT_WARPS * 32, mt_bytes, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K,
+                                                                                             nz.on, nz.seed_user0, (size_t)0, nz.trp, nz.tri, nz.n);
     }
     return cudaGetLastError();
 }
 
 template <typename T>
 cudaError_t launch_exact_topk(const float* capx, T* cs, int* ci, int* cc, int C, int nb, int user0, const T* At, int p_pad, int p,
-                              const T* Brow, size_t ldb, const T* bias, int* uflags, int K, cudaStream_t st)
+                              const T* Brow, size_t ldb, const T* bias, int* uflags, int K, const NoiseArgs& nz, cudaStream_t st)
 {
-    if (C == 256) return launch_exact_topk_inst<T, 256>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, st);
-    if (C == 512) return launch_exact_topk_inst<T, 512>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, st);
-    return launch_exact_topk_inst<T, 1024>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, st);
+    if (C == 256) return launch_exact_topk_inst<T, 256>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, st);
+    if (C == 512) return launch_exact_topk_inst<T, 512>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, st);
+    return launch_exact_topk_inst<T, 1024>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, st);
 }
 
 // order the <= K survivors of every user (warp per user, bitonic network sized to K)
@@ -284,7 +290,6 @@ int run_call(const CallArgs<T>& a)
     if (!a.A || !a.B || !a.trp || !a.tep) { set_err("bad argument", "A, B, Xtrain_csr_p and Xtest_csr_p are required"); return RMB200_ERR_BAD_ARG; }
     if (a.lda < (size_t)a.k || a.ldb < (size_t)a.k) { set_err("bad argument", "lda/ldb smaller than k"); return RMB200_ERR_BAD_ARG; }
     if (a.out[5] && !a.tev) { set_err("bad argument", "NDCG requested but Xtest_csr (values) is NULL"); return RMB200_ERR_BAD_ARG; }
-    if (a.noise) { set_err("unsupported", "break_ties_with_noise=true is not implemented in this build; pass false"); return RMB200_ERR_UNSUPPORTED; }
     if (a.K > RMB200_MAX_K) { set_err("unsupported", "k_metrics larger than RMB200_MAX_K (384)"); return RMB200_ERR_UNSUPPORTED; }
     if (ex && ex->struct_size != (int32_t)sizeof(rmb200_extra_t)) { set_err("bad argument", "rmb200_extra_t::struct_size mismatch"); return RMB200_ERR_BAD_ARG; }
     bool any_out = false;
@@ -347,9 +352,14 @@ int run_call(const CallArgs<T>& a)
         f_stages = (int)(budget / tile) - 1;
         if (f_stages > F_MAX_STAGES) f_stages = F_MAX_STAGES;
     }
-    const bool tensor_ok = !count_ranks && f_stages >= 2 && K <= 256;
+    // With rank counting (ROC/PR-AUC) every score has to be exact: the FMA tiles do everything.  Exception: with the
+    // reference's tie-breaking noise the ranked top-K comes from the tensor path as well (its exact stage is where the
+    // noise is applied, tie_noise.cuh), after the FMA pass has counted the ranks.
+    const bool tensor_shape_ok = f_stages >= 2 && K <= 256;
+    const bool tensor_ok = tensor_shape_ok && (!count_ranks || a.noise);
     if (path_req == 2 && !tensor_ok) { set_err("unsupported", "scoring_path=tensor needs no ROC/PR-AUC (rank counting), k <= ~400 and k_metrics <= 256"); return RMB200_ERR_UNSUPPORTED; }
     const bool use_tensor = tensor_ok && path_req != 1;
+    const bool fma_counts_first = use_tensor && count_ranks;
     tm.scoring_path = use_tensor ? 2 : 1;
 #ifndef RMB_F_CMID
 #define RMB_F_CMID 512
@@ -430,11 +440,13 @@ int run_call(const CallArgs<T>& a)
         have_Bt = true;
         return RMB200_OK;
     };
-    if (!use_tensor) {
+    if (!use_tensor || fma_counts_first) {
         int rc = pack_Bt();
         if (rc) return rc;
-        d_Brow.release();      // the FMA path reads only the tiled copy
-        if (!on_dev) Bsrc = nullptr;
+        if (!use_tensor) {
+            d_Brow.release();      // the FMA path reads only the tiled copy
+            if (!on_dev) Bsrc = nullptr;
+        }
     }
     const T* bias_d = nullptr;
     if (a.bias) {
@@ -628,6 +640,12 @@ int run_call(const CallArgs<T>& a)
             return RMB200_OK;
         };
         bool batch_on_tensor = use_tensor;
+        if (fma_counts_first) {            // rank counts (and the smallest candidate score) from the FMA tiles; its top-K is replaced below
+            pt.start();
+            int rc = run_fma_batch();
+            if (rc) return rc;
+            pt.stop(tm.score_select_ms);
+        }
         if (use_tensor) {
             // norms + fp16 operand image of the batch's users, then the tensor-core filter and the exact re-scoring
             pt.start();
@@ -650,6 +668,7 @@ int run_call(const CallArgs<T>& a)
             fp.overflow = d_overflow.as<int>(); fp.uflags = d_flags.as<int>(); fp.K = K;
             fp.sample_tiles = f_sample_tiles; fp.sample_stride = f_sample_stride; fp.sample_rank = f_sample_rank;
             fp.retries = d_overflow.as<int>() + 1;
+            fp.noise_band = a.noise ? 2.02e-12f : 0.f;
             fp.dbg = 0; if (const char* env = std::getenv("RMB200_DBG")) fp.dbg = std::atoi(env);
             cudaEventRecord(pk.a, st);
             CK(launch_filter_select(fp, C, nb_pad / BM, st));
@@ -675,11 +694,20 @@ int run_call(const CallArgs<T>& a)
                 int rc = pack_Bt();
                 if (rc) return rc;
                 pt.start();
+                if (fma_counts_first) {
+                    // the rank counters of this batch's users already hold the first FMA pass: clear them before the re-run
+                    int te0 = 0, te1 = 0;
+                    CK(cudaMemcpy(&te0, tep_d + b0, sizeof(int), cudaMemcpyDeviceToHost));
+                    CK(cudaMemcpy(&te1, tep_d + b0 + nb, sizeof(int), cudaMemcpyDeviceToHost));
+                    if (te1 > te0) CK(cudaMemsetAsync(d_auc.as<unsigned int>() + te0, 0, (size_t)(te1 - te0) * sizeof(unsigned int), st));
+                }
                 rc = run_fma_batch();
                 if (rc) return rc;
             } else {
+                NoiseArgs nz;
+                nz.on = a.noise; nz.seed_user0 = (unsigned long long)a.seed + (unsigned long long)(ub + b0); nz.trp = trp_d; nz.tri = tri_d; nz.n = a.n;
                 CK(launch_exact_topk<T>(d_capx.as<float>(), d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, b0, d_At.as<T>(), p_pad, a.k,
-                                        Bsrc, Bld, bias_d, d_flags.as<int>(), K, st));
+                                        Bsrc, Bld, bias_d, d_flags.as<int>(), K, nz, st));
                 tm.kernel_launches++;
             }
         } else {
@@ -689,16 +717,21 @@ int run_call(const CallArgs<T>& a)
         }
         CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
         tm.kernel_launches++;
+        if (a.noise && !batch_on_tensor && !count_ranks) {
+            all_equal_check_kernel<T><<<nb, 128, 0, st>>>(d_cs.as<T>(), d_cc.as<int>(), C, b0, K, a.n, trp_d, tri_d, d_status.as<int>(),
+                                                           d_At.as<T>(), d_Bt.as<T>(), bias_d, p_pad, d_flags.as<int>());
+            CK(cudaGetLastError());
+            tm.kernel_launches++;
+        }
         pt.stop(tm.score_select_ms);
         if (pk_pending) { float ms = 0; cudaEventElapsedTime(&ms, pk.a, pk.b); tm.dominant_kernel_ms += ms; }
-        (void)batch_on_tensor;
 
         // per-user metrics
         pt.start();
         {
             MetricsParams<T> mp;
             mp.n = a.n; mp.K = K; mp.C = C; mp.user0 = b0; mp.mb = nb; mp.cumulative = a.cumulative;
-            mp.want_roc = want_roc; mp.want_pr = want_pr; mp.count_ranks = count_ranks;
+            mp.want_roc = want_roc; mp.want_pr = want_pr; mp.count_ranks = count_ranks; mp.noise = a.noise;
             mp.trp = trp_d; mp.tep = tep_d; mp.tei = tei_d; mp.tev = tev_d;
             mp.ustatus = d_status.as<int>(); mp.uflags = d_flags.as<int>();
             mp.cand_score = d_cs.as<T>(); mp.cand_item = d_ci.as<int>(); mp.cand_count = d_cc.as<int>();
@@ -795,7 +828,7 @@ int entry(const T* A, size_t lda, const T* B, size_t ldb, int32_t m, int32_t n, 
           const int32_t* trp, const int32_t* tri, const int32_t* tep, const int32_t* tei, const T* tev,
           int32_t K, int cumulative, int noise,
           T* p, T* tp, T* r, T* ap, T* tap, T* ndcg, T* hit, T* rr, T* roc, T* pr,
-          int ccs, int32_t mip, int32_t mpt, const T* bias, const rmb200_extra_t* ex)
+          int ccs, int32_t mip, int32_t mpt, uint64_t seed, const T* bias, const rmb200_extra_t* ex)
 {
     g_err.clear();
     CallArgs<T> a;
@@ -804,7 +837,7 @@ int entry(const T* A, size_t lda, const T* B, size_t ldb, int32_t m, int32_t n, 
     a.K = K; a.cumulative = cumulative ? 1 : 0; a.noise = noise ? 1 : 0;
     T* outs[10] = {p, tp, r, ap, tap, ndcg, hit, rr, roc, pr};
     for (int q = 0; q < 10; q++) a.out[q] = outs[q];
-    a.consider_cold_start = ccs ? 1 : 0; a.min_items_pool = mip; a.min_pos_test = mpt;
+    a.consider_cold_start = ccs ? 1 : 0; a.min_items_pool = mip; a.min_pos_test = mpt; a.seed = seed;
     a.bias = bias; a.ex = ex;
     try {
         return run_call<T>(a);
@@ -830,11 +863,11 @@ int rmb200_calc_metrics_f32(
     float* ndcg_at_k, float* hit_at_k, float* rr_at_k, float* roc_auc, float* pr_auc,
     int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, int32_t nthreads, uint64_t seed)
 {
-    (void)nthreads; (void)seed;
+    (void)nthreads;
     return entry<float>(A, lda, B, ldb, m, n, k, Xtrain_csr_p, Xtrain_csr_i, Xtest_csr_p, Xtest_csr_i, Xtest_csr,
                         k_metrics, cumulative, break_ties_with_noise, p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k,
                         ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc, consider_cold_start, min_items_pool,
-                        min_pos_test, nullptr, nullptr);
+                        min_pos_test, seed, nullptr, nullptr);
 }
 
 int rmb200_calc_metrics_f64(
@@ -846,11 +879,11 @@ int rmb200_calc_metrics_f64(
     double* ndcg_at_k, double* hit_at_k, double* rr_at_k, double* roc_auc, double* pr_auc,
     int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, int32_t nthreads, uint64_t seed)
 {
-    (void)nthreads; (void)seed;
+    (void)nthreads;
     return entry<double>(A, lda, B, ldb, m, n, k, Xtrain_csr_p, Xtrain_csr_i, Xtest_csr_p, Xtest_csr_i, Xtest_csr,
                          k_metrics, cumulative, break_ties_with_noise, p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k,
                          ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc, consider_cold_start, min_items_pool,
-                         min_pos_test, nullptr, nullptr);
+                         min_pos_test, seed, nullptr, nullptr);
 }
 
 int rmb200_calc_metrics_ex_f32(
@@ -863,11 +896,11 @@ int rmb200_calc_metrics_ex_f32(
     int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, int32_t nthreads, uint64_t seed,
     const float* item_biases, const rmb200_extra_t* extra)
 {
-    (void)nthreads; (void)seed;
+    (void)nthreads;
     return entry<float>(A, lda, B, ldb, m, n, k, Xtrain_csr_p, Xtrain_csr_i, Xtest_csr_p, Xtest_csr_i, Xtest_csr,
                         k_metrics, cumulative, break_ties_with_noise, p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k,
                         ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc, consider_cold_start, min_items_pool,
-                        min_pos_test, item_biases, extra);
+                        min_pos_test, seed, item_biases, extra);
 }
 
 int rmb200_calc_metrics_ex_f64(
@@ -880,11 +913,11 @@ int rmb200_calc_metrics_ex_f64(
     int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, int32_t nthreads, uint64_t seed,
     const double* item_biases, const rmb200_extra_t* extra)
 {
-    (void)nthreads; (void)seed;
+    (void)nthreads;
     return entry<double>(A, lda, B, ldb, m, n, k, Xtrain_csr_p, Xtrain_csr_i, Xtest_csr_p, Xtest_csr_i, Xtest_csr,
                          k_metrics, cumulative, break_ties_with_noise, p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k,
                          ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc, consider_cold_start, min_items_pool,
-                         min_pos_test, item_biases, extra);
+                         min_pos_test, seed, item_biases, extra);
 }
 
 int rmb200_device_count(void)

@@ -41,6 +41,7 @@
 #include <cuda_fp16.h>
 #include "prep.cuh"
 #include "score_select.cuh"
+#include "tie_noise.cuh"
 
 namespace rmb {
 
@@ -85,6 +86,7 @@ struct FilterParams {
     const __half* __restrict__ Bb;          // [item tiles][KB/8][128][8]  fp16 item factors (+bias column), all scaled by pow2_scale_for(max_j ||b_j||)
     int KB;                                 // fp16 factors per row, multiple of 16
     float err_coef;                         // c: |approx - exact| <= c ||a|| max||b|| (host: filter_err_coef)
+    float noise_band;                       // break_ties_with_noise: how far the noise can move two scores apart (2e-12), else 0
     int stages;                             // depth of the B ring
     int n, mb, user0;
     const float* __restrict__ anorm;        // [mb] ||a_u|| (with the 1.0 bias component), rounded up
@@ -421,7 +423,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 float slack = 0.f;
                 if (ranked) {
                     const float an = P.anorm[ul], bn = __uint_as_float(*P.maxbn);
-                    slack = 2.f * P.err_coef * (an * pow2_scale_for(an)) * (bn * pow2_scale_for(bn));
+                    const float sa = pow2_scale_for(an), sb = pow2_scale_for(bn);
+                    slack = 2.f * P.err_coef * (an * sa) * (bn * sb) + P.noise_band * sa * sb;
                 }
                 float thr0 = CUDART_INF_F;                  // approx < thr: cannot be in the exact top K; +inf: the row is closed
                 if (pass == 0) {
@@ -643,7 +646,9 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
                   int* __restrict__ cand_count, const int mb, const int user0,
                   const T* __restrict__ At, const int p_pad, const int p,
                   const T* __restrict__ Brow, const size_t ldb, const T* __restrict__ bias,
-                  int* __restrict__ uflags, const int K)
+                  int* __restrict__ uflags, const int K,
+                  const int noise, const unsigned long long seed_user0, const size_t mt_off,
+                  const int* __restrict__ trp, const int* __restrict__ tri, const int n)
 {
     typedef typename NumTraits<T>::key_t key_t;
     constexpr int E = C / 32;
@@ -701,6 +706,67 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
         }
     }
     if (__any_sync(FULL, nanflag)) { if (lane == 0) atomicOr(&uflags[user0 + ul], 1); }
+    if (noise) {
+        // break_ties_with_noise (hpp:531-534, tie_noise.cuh): candidate number ix of the user -- candidates in ascending item
+        // order, i.e. item id minus the train items before it -- gets draw ix of mt19937(seed + user).  Only scores the
+        // noise can change need their draw (every double score; float scores below 2^-14 in magnitude).
+        bool want = false;
+        int pos[E];
+        const int t0 = trp[user0 + ul], t1 = trp[user0 + ul + 1];
+        {
+            // validity rule of the noise branch (hpp:524-527): all candidates equal => NaN row.  The filter keeps whatever can
+            // reach the K-th best score: if it kept fewer than all candidates some score is lower than the rest; if it kept
+            // them all, they are all here.
+            key_t kmax = 0, kmin = ~(key_t)0;
+            int cntv = 0;
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                if (key[e] != 0) { kmax = key[e] > kmax ? key[e] : kmax; kmin = key[e] < kmin ? key[e] : kmin; cntv++; }
+            cntv = __reduce_add_sync(FULL, cntv);
+            // warp-wide extremes (64-bit keys for double: reduce through shuffles)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const key_t omax = __shfl_xor_sync(FULL, kmax, o), omin = __shfl_xor_sync(FULL, kmin, o);
+                kmax = omax > kmax ? omax : kmax;
+                kmin = omin < kmin ? omin : kmin;
+            }
+            if (cntv == n - (t1 - t0) && cntv > 0 && kmax == kmin && lane == 0) atomicOr(&uflags[user0 + ul], 4);
+        }
+#pragma unroll
+        for (int e = 0; e < E; e++) {
+            pos[e] = -1;
+            if (key[e] != 0 && TieNoise<T>::can_change(NumTraits<T>::from_orderable((u64)key[e]))) {
+                int lo = t0, hi = t1;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (tri[mid] < it[e]) lo = mid + 1; else hi = mid; }
+                pos[e] = it[e] - (lo - t0);
+                want = true;
+            }
+        }
+        if (__any_sync(FULL, want)) {
+            int maxpos = -1;
+#pragma unroll
+            for (int e = 0; e < E; e++) maxpos = max(maxpos, pos[e]);
+            maxpos = __reduce_max_sync(FULL, maxpos);
+            unsigned* x = reinterpret_cast<unsigned*>(smem_raw + mt_off) + warp * MT_N;
+            mt_seed_warp(x, seed_user0 + (unsigned long long)ul, lane);
+            const int nblocks = (int)(((long long)(maxpos + 1) * TieNoise<T>::WORDS + MT_N - 1) / MT_N);
+            for (int blk = 0; blk < nblocks; blk++) {
+                mt_twist_warp(x, lane);
+#pragma unroll
+                for (int e = 0; e < E; e++) {
+                    if (pos[e] < 0) continue;
+                    const long long w = (long long)pos[e] * TieNoise<T>::WORDS - (long long)blk * MT_N;     // first word of the draw, inside this block?
+                    if (w >= 0 && w < MT_N) {
+                        const unsigned w0 = mt_temper(x[w]);
+                        const unsigned w1 = TieNoise<T>::WORDS == 2 ? mt_temper(x[w + 1]) : 0u;
+                        const T noisy = NumTraits<T>::from_orderable((u64)key[e]) + TieNoise<T>::draw(w0, w1);
+                        key[e] = NumTraits<T>::key(noisy);
+                    }
+                }
+                __syncwarp();
+            }
+        }
+    }
     int nvalid = 0;
 #pragma unroll
     for (int e = 0; e < E; e++) nvalid += (key[e] != 0) ? 1 : 0;

@@ -18,6 +18,7 @@ template <typename T>
 struct MetricsParams {
     int n, K, C, user0, mb, cumulative;
     int want_roc, want_pr, count_ranks;   // count_ranks: the rank-counting pass ran
+    int noise;                            // break_ties_with_noise: validity rules of the noise branch (hpp:516-528)
     const int* trp; const int* tep; const int* tei; const T* tev;
     const int* ustatus; const int* uflags;
     const T* cand_score; const int* cand_item; const int* cand_count;
@@ -93,8 +94,11 @@ __global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
             if (partial_path) pred_min = cs[K - 1];
             else if (cand <= K) pred_min = cs[cand - 1];
             else pred_min = NumTraits<T>::from_orderable(P.umin[u]);   // full order: smallest candidate score
-            bad = (pred_max != pred_max) || (pred_min != pred_min) || isinf(pred_max) || isinf(pred_min) ||
-                  (pred_max == pred_min);
+            // noise off: the sorted extremes decide (hpp:541-548 / :555-562).  Noise on: the rule is "all candidates equal"
+            // (hpp:527), decided before the noise went in: flag 4 from the scoring stage, or -- full order -- the exact extremes
+            const bool equal = !P.noise ? (pred_max == pred_min)
+                                        : ((P.uflags[u] & 4) != 0 || (!partial_path && cand > K && pred_max == pred_min));
+            bad = (pred_max != pred_max) || (pred_min != pred_min) || isinf(pred_max) || isinf(pred_min) || equal;
         }
         if (bad) {
             all_nan(P, ul);
@@ -282,6 +286,39 @@ __global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
             }
         }
     }
+}
+
+// break_ties_with_noise on the FMA path without rank counting: the reference's noise branch turns a user whose candidates
+// all score the same into a NaN row (hpp:524-527).  Necessary: the K best (clean) scores are equal -- only for those users
+// (rare) one block re-scores every candidate with the tile kernel's fma chain and raises flag 4 when none differs.
+template <typename T>
+__global__ void all_equal_check_kernel(const T* __restrict__ cand_score, const int* __restrict__ cand_count, const int C,
+                                       const int user0, const int K, const int n,
+                                       const int* __restrict__ trp, const int* __restrict__ tri, const int* __restrict__ ustatus,
+                                       const T* __restrict__ At, const T* __restrict__ Bt, const T* __restrict__ bias, const int p_pad,
+                                       int* __restrict__ uflags)
+{
+    const int ul = blockIdx.x, u = user0 + ul;
+    if (ustatus[u] != 0) return;
+    const int t0 = trp[u], t1 = trp[u + 1];
+    const int cand = n - (t1 - t0), walk = K < cand ? K : cand;
+    if (walk <= 0 || cand_count[ul] < walk) return;
+    const T ref = cand_score[(size_t)ul * C];
+    if (!(ref == cand_score[(size_t)ul * C + walk - 1])) return;
+    constexpr int BN = NumTraits<T>::BN;
+    const T* a = At + (size_t)(ul / BM) * p_pad * BM + (ul % BM);
+    int differs = 0;
+    for (int item = threadIdx.x; item < n && !differs; item += blockDim.x) {
+        int lo = t0, hi = t1;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (tri[mid] < item) lo = mid + 1; else hi = mid; }
+        if (lo < t1 && tri[lo] == item) continue;
+        const T* b = Bt + (size_t)(item / BN) * p_pad * BN + (item % BN);
+        T acc = (T)0;
+        for (int k = 0; k < p_pad; k++) acc = NumTraits<T>::fma(a[(size_t)k * BM], b[(size_t)k * BN], acc);
+        if (bias != nullptr) acc += bias[item];
+        if (!(acc == ref)) differs = 1;
+    }
+    if (!__syncthreads_or(differs) && threadIdx.x == 0) atomicOr(&uflags[u], 4);
 }
 
 // ---------------------------------------------------------------- per-metric means over users (extension)

@@ -92,6 +92,38 @@ def kat_case(name, scores, te_items, te_vals, k, dtype=np.float64):
     _save(name, A, B, Xtr, Xte, k, ("ndcg",), False, dtype, ref)
 
 
+def tie_case(name, dtype, scale, metrics, cumulative=False, k=6, all_equal_users=2, **kw):
+    """Tie-heavy users: every item factor row is one of 5 distinct rows, so each user has only 5 distinct scores and the
+    order inside a group of tied items is decided by the tie-breaking noise alone (src/recometrics.hpp:531-534) -- the
+    case that pins the per-user mt19937 stream and the uniform_real_distribution arithmetic.  `scale` shrinks the scores
+    (float32 noise of 1e-12 only survives the addition for |score| < 2^-15).  The last users have all-equal scores
+    (NaN row by the noise branch's validity rule, :527)."""
+    rng = np.random.default_rng(11)
+    m, n, p = 40, 60, 3
+    proto = rng.standard_normal((5, p))
+    B = proto[rng.integers(0, 5, n)] * scale
+    A = rng.standard_normal((m, p))
+    A[m - all_equal_users:] = 0.0
+    rows_tr, rows_te = [], []
+    for u in range(m):
+        items = rng.permutation(n)
+        ntr, nte = int(rng.integers(0, 8)), int(rng.integers(1, 9))
+        rows_tr.append(sorted(items[:ntr].tolist()))
+        rows_te.append(sorted(items[ntr:ntr + nte].tolist()))
+
+    def csr(rows, vals=None):
+        indptr = np.cumsum([0] + [len(r) for r in rows]).astype(np.int32)
+        idx = np.array([j for r in rows for j in r], dtype=np.int32)
+        dat = np.ones(len(idx)) if vals is None else vals
+        return csr_array((dat, idx, indptr), shape=(m, n))
+
+    Xtr = csr(rows_tr)
+    Xte = csr(rows_te, rng.integers(1, 6, sum(len(r) for r in rows_te)).astype(np.float64))
+    ref = oracle.ref_calc(A.astype(dtype), B.astype(dtype), Xtr, Xte, k, metrics=metrics, cumulative=cumulative,
+                          nthreads=1, dtype=dtype, **kw)
+    _save(name, A, B, Xtr, Xte, k, metrics, cumulative, dtype, ref, **kw)
+
+
 if __name__ == "__main__":
     oracle.build()
     assert oracle.have_ref(), "oracle/_ref is missing: run `make -C oracle` where /root/reference exists"
@@ -115,3 +147,10 @@ if __name__ == "__main__":
     kat_case("g_kat_neg_b", [0, 0, 3, 4, 0, 600, 0, 8, 9, 10], [2, 3, 5, 7, 9], [1, 2, -300, 4, 5], 5)
     kat_case("g_kat_neg_c", [0, 0, 3, 4, 0, -6, 0, 8, 9, 10], [2, 3, 5, 7, 9], [1, 2, -300, 4, 5], 5)
     kat_case("g_kat_allzero_scores", [0] * 10, [2, 3, 5, 7, 9], [1, 2, -3, 4, 5], 5)
+    # break_ties_with_noise=True (the reference's default): ordinary inputs, and ties that only the noise orders
+    synth_case("g_noise_f64_all", 1, 96, 300, 12, 7, ALL10, False, np.float64, break_ties_with_noise=True, seed=7)
+    synth_case("g_noise_f32_all_cum", 1, 96, 300, 12, 7, ALL10, True, np.float32, break_ties_with_noise=True, seed=1)
+    tie_case("g_noise_ties_f64", np.float64, 1.0, ALL10, break_ties_with_noise=True, seed=3)
+    tie_case("g_noise_ties_f64_cum", np.float64, 1.0, ("p", "ap", "ndcg", "rr"), cumulative=True, break_ties_with_noise=True, seed=12345678901)
+    tie_case("g_noise_ties_f32_tiny", np.float32, 1e-7, ALL10, break_ties_with_noise=True, seed=3)
+    edge_case("g_noise_edge_f64_all", np.float64, ALL10, False, break_ties_with_noise=True, seed=5)

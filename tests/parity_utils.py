@@ -84,9 +84,10 @@ def run_product(rb, data, metrics, k, cumulative=False, dtype=None, separate_bia
     if bias is not None and not separate_bias:
         A, B = synth.fold_biases(A, B, bias)
         bias = None
+    noise = bool(kw.pop("break_ties_with_noise", False))
     return rb.calc_reco_metrics_ex(
         data["X_train"], data["X_test"], A, B, k=k, item_biases=bias, cumulative=cumulative,
-        break_ties_with_noise=False, return_topk=extras, return_ranks=extras and ("roc" in metrics or "pr" in metrics),
+        break_ties_with_noise=noise, return_topk=extras, return_ranks=extras and ("roc" in metrics or "pr" in metrics),
         return_status=extras, **flags, **kw)
 
 
