@@ -182,7 +182,7 @@ def calc_reco_metrics_ex(
     reference-style dict plus timing and the optional extras (top-K ids/scores, held-out ranks,
     per-user status).  ``user_range=(begin, end)`` evaluates only those rows (the sharding unit);
     rows outside it are left as NaN in the returned arrays.  ``scoring_path``: "auto" | "fma" (every score on
-    the FP32/FP64 FMA pipe) | "tensor" (bf16 tensor-core candidate filter + exact FMA re-scoring of the
+    the FP32/FP64 FMA pipe) | "tensor" (fp16 tensor-core candidate filter + exact FMA re-scoring of the
     survivors: identical top-K and scores, top-K metrics only).  ``return_means``: also reduce every requested
     metric to its mean over the evaluated users on the device (``numpy.nanmean`` of the per-user output; ``(k,)`` vectors
     when ``cumulative``) -- ``result.means`` / ``result.counts``; with ``means_only`` the per-user rows are not copied
