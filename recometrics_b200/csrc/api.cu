@@ -752,7 +752,7 @@ int run_call(const CallArgs<T>& a)
             if (ex && ex->topk_items) mp.topk_items = on_dev ? ex->topk_items + (size_t)(ub + b0) * K : d_tki.as<int>();
             if (ex && ex->topk_scores) mp.topk_scores = on_dev ? reinterpret_cast<T*>(ex->topk_scores) + (size_t)(ub + b0) * K : d_tks.as<T>();
             mp.pos_rank = pos_rank_d;
-            user_metrics_kernel<T><<<(nb + 127) / 128, 128, 0, st>>>(mp);
+            user_metrics_kernel<T><<<(nb + METRICS_WARPS - 1) / METRICS_WARPS, METRICS_WARPS * 32, 0, st>>>(mp);
             CK(cudaGetLastError());
             tm.kernel_launches++;
             if (want_means) {

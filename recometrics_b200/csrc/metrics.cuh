@@ -1,7 +1,7 @@
 // metrics.cuh -- per-user metrics from the ranked top-K, the held-out row and the rank buckets.
 //
-// One thread per user; everything is accumulated sequentially in rank order, in double, with the
-// same operations as the reference so that -- given the same ranking -- the results are
+// One warp per user; every accumulator is added up in rank order, in double, with the same
+// operations as the reference so that -- given the same ranking -- the results are
 // bit-identical:
 //   validity of the ranking        /root/reference/src/recometrics.hpp:537-563
 //   top-K walk                      :605-708   (hits, AP, DCG, RR; cumulative writes :625-635)
@@ -32,46 +32,69 @@ struct MetricsParams {
     long long* pos_rank;                  // optional [nnz_test] (absolute)
 };
 
+constexpr int METRICS_WARPS = 8;           // users (warps) per block of user_metrics_kernel
+constexpr unsigned FULL_WARP = 0xffffffffu;
+
 template <typename T>
-__device__ __forceinline__ void fill_row(T* out, const size_t ul, const int K, const int cumulative, const T v)
+__device__ __forceinline__ void fill_row(T* out, const size_t ul, const int K, const int cumulative, const T v, const int lane)
 {
     if (!out) return;
-    if (!cumulative) out[ul] = v;
-    else for (int c = 0; c < K; c++) out[ul * (size_t)K + c] = v;
+    if (!cumulative) { if (lane == 0) out[ul] = v; }
+    else for (int c = lane; c < K; c += 32) out[ul * (size_t)K + c] = v;
 }
 
 template <typename T>
-__device__ void all_nan(const MetricsParams<T>& P, const size_t ul)
+__device__ void all_nan(const MetricsParams<T>& P, const size_t ul, const int lane)
 {
-    fill_row(P.p, ul, P.K, P.cumulative, P.nan_value);
-    fill_row(P.tp, ul, P.K, P.cumulative, P.nan_value);
-    fill_row(P.r, ul, P.K, P.cumulative, P.nan_value);
-    fill_row(P.ap, ul, P.K, P.cumulative, P.nan_value);
-    fill_row(P.tap, ul, P.K, P.cumulative, P.nan_value);
-    fill_row(P.ndcg, ul, P.K, P.cumulative, P.nan_value);
-    fill_row(P.hit, ul, P.K, P.cumulative, P.nan_value);
-    fill_row(P.rr, ul, P.K, P.cumulative, P.nan_value);
-    if (P.roc) P.roc[ul] = P.nan_value;
-    if (P.pr) P.pr[ul] = P.nan_value;
+    fill_row(P.p, ul, P.K, P.cumulative, P.nan_value, lane);
+    fill_row(P.tp, ul, P.K, P.cumulative, P.nan_value, lane);
+    fill_row(P.r, ul, P.K, P.cumulative, P.nan_value, lane);
+    fill_row(P.ap, ul, P.K, P.cumulative, P.nan_value, lane);
+    fill_row(P.tap, ul, P.K, P.cumulative, P.nan_value, lane);
+    fill_row(P.ndcg, ul, P.K, P.cumulative, P.nan_value, lane);
+    fill_row(P.hit, ul, P.K, P.cumulative, P.nan_value, lane);
+    fill_row(P.rr, ul, P.K, P.cumulative, P.nan_value, lane);
+    if (lane == 0) {
+        if (P.roc) P.roc[ul] = P.nan_value;
+        if (P.pr) P.pr[ul] = P.nan_value;
+    }
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL_WARP, v, o);
+    return v;
 }
 
 template <typename T>
-__global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
+__device__ __forceinline__ T warp_max(T v)      // ordinary '>' (no NaNs reach it)
 {
-    const int uli = blockIdx.x * blockDim.x + threadIdx.x;
-    if (uli >= P.mb) return;
+    for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(FULL_WARP, v, o); if (w > v) v = w; }
+    return v;
+}
+
+// One WARP per user.  Rank ix of the walk and column ix of a cumulative row belong to lane ix % 32: the membership
+// tests, the divisions and the row writes run in parallel, while every accumulator (hits, AP, DCG, IDCG) is still
+// added up in rank order, in double, term by term -- the reference's sequence of operations, hence its bits.
+template <typename T>
+__global__ void __launch_bounds__(METRICS_WARPS * 32) user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
+{
+    const int lane = threadIdx.x & 31;
+    const int uli = blockIdx.x * METRICS_WARPS + (threadIdx.x >> 5);
+    if (uli >= P.mb) return;                                  // the whole warp leaves
     const size_t ul = (size_t)uli;
     const int u = P.user0 + uli;
     const int K = P.K, n = P.n;
     const T NaN = P.nan_value;
+    const unsigned lanes_le = FULL_WARP >> (31 - lane);
 
-    if (P.topk_items) for (int c = 0; c < K; c++) P.topk_items[ul * K + c] = -1;
-    if (P.topk_scores) for (int c = 0; c < K; c++) P.topk_scores[ul * K + c] = NaN;
+    if (P.topk_items) for (int c = lane; c < K; c += 32) P.topk_items[ul * K + c] = -1;
+    if (P.topk_scores) for (int c = lane; c < K; c += 32) P.topk_scores[ul * K + c] = NaN;
 
     int st = P.ustatus[u];
     if (st != 0) {
-        all_nan(P, ul);
-        if (P.status_out) P.status_out[uli] = st;
+        all_nan(P, ul, lane);
+        if (P.status_out && lane == 0) P.status_out[uli] = st;
         return;
     }
     const int ntrain = P.trp[u + 1] - P.trp[u];
@@ -101,14 +124,14 @@ __global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
             bad = (pred_max != pred_max) || (pred_min != pred_min) || isinf(pred_max) || isinf(pred_min) || equal;
         }
         if (bad) {
-            all_nan(P, ul);
-            if (P.status_out) P.status_out[uli] = 3;
+            all_nan(P, ul, lane);
+            if (P.status_out && lane == 0) P.status_out[uli] = 3;
             return;
         }
     }
-    if (P.status_out) P.status_out[uli] = 0;
-    if (P.topk_items) for (int c = 0; c < walk; c++) P.topk_items[ul * K + c] = ci[c];
-    if (P.topk_scores) for (int c = 0; c < walk; c++) P.topk_scores[ul * K + c] = cs[c];
+    if (P.status_out && lane == 0) P.status_out[uli] = 0;
+    if (P.topk_items) for (int c = lane; c < walk; c += 32) P.topk_items[ul * K + c] = ci[c];
+    if (P.topk_scores) for (int c = lane; c < walk; c += 32) P.topk_scores[ul * K + c] = cs[c];
 
     const int* ti = P.tei + tp0;
     const T* tv = P.tev ? (P.tev + tp0) : nullptr;
@@ -123,7 +146,7 @@ __global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
     T* rr_u = P.rr ? P.rr + ul * rs : nullptr;
 
     // ---- top-K walk (hpp:605-708).  Unlike the reference (quirk Q2) Hit@K / RR@K requested on their
-    //      own are computed too. ----
+    //      own are computed too.  (The early exit of hpp:637-638 can only trigger on the last rank.) ----
     int hits = 0;
     double avg_p = 0, dcg = 0;
     int min_rank = INT_MAX;
@@ -131,30 +154,52 @@ __global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
     const bool calc_top = P.p || P.tp || P.r || P.ap || P.tap || P.ndcg || P.hit || P.rr;
     if (calc_top && (!k_leq_n || P.ap || P.tap || P.rr || P.ndcg)) {
         did_walk = true;
-        for (int ix = 0; ix < walk; ix++) {
-            const int item = ci[ix];
-            int lo = 0, hi = npos;
-            while (lo < hi) { const int mid = (lo + hi) >> 1; if (ti[mid] < item) lo = mid + 1; else hi = mid; }
-            if (lo < npos && ti[lo] == item) {
-                hits++;
-                avg_p += hits / (double)(ix + 1);
-                dcg += tv ? ((double)tv[lo] / P.log2tab[ix]) : 0.;
-                if (ix < min_rank) min_rank = ix;
+        for (int base = 0; base < walk; base += 32) {
+            const int ix = base + lane;
+            bool hit = false;
+            T val = (T)0;
+            if (ix < walk) {
+                const int item = ci[ix];
+                int lo = 0, hi = npos;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (ti[mid] < item) lo = mid + 1; else hi = mid; }
+                if (lo < npos && ti[lo] == item) { hit = true; if (tv) val = tv[lo]; }
             }
-            if (P.cumulative) {
+            const unsigned mask = __ballot_sync(FULL_WARP, hit);
+            const int my_hits = hits + __popc(mask & lanes_le);          // hits up to and including rank ix
+            // this rank's terms, computed by its lane ...
+            double t_ap = 0., t_dcg = 0.;
+            if (hit) {
+                t_ap = my_hits / (double)(ix + 1);
+                t_dcg = tv ? ((double)val / P.log2tab[ix]) : 0.;
+            }
+            // ... and added in rank order; a lane keeps the sums as of its own rank
+            double my_ap = avg_p, my_dcg = dcg;
+            for (unsigned m = mask; m; m &= m - 1) {
+                const int b = __ffs(m) - 1;
+                avg_p += __shfl_sync(FULL_WARP, t_ap, b);
+                dcg += __shfl_sync(FULL_WARP, t_dcg, b);
+                if (b <= lane) { my_ap = avg_p; my_dcg = dcg; }
+            }
+            int my_min_rank = min_rank;
+            if (mask) {
+                const int first = base + __ffs(mask) - 1;
+                if (my_min_rank == INT_MAX && (mask & lanes_le)) my_min_rank = first;
+                if (min_rank == INT_MAX) min_rank = first;
+            }
+            hits += __popc(mask);
+            if (P.cumulative && ix < walk) {
                 const int tn = (ix + 1) < npos ? (ix + 1) : npos;
-                if (p_u) p_u[ix] = (T)(hits / (double)(ix + 1));
-                if (tp_u) tp_u[ix] = (T)(hits / (double)tn);
-                if (r_u) r_u[ix] = (T)(hits / (double)npos);
-                if (ap_u) ap_u[ix] = (T)(avg_p / (double)npos);
-                if (tap_u) tap_u[ix] = (T)(avg_p / (double)tn);
-                if (ndcg_u) ndcg_u[ix] = (T)dcg;
-                if (hit_u) hit_u[ix] = (T)(hits > 0);
-                if (rr_u) rr_u[ix] = (T)(hits ? (1. / (double)(min_rank + 1)) : 0.);
+                if (p_u) p_u[ix] = (T)(my_hits / (double)(ix + 1));
+                if (tp_u) tp_u[ix] = (T)(my_hits / (double)tn);
+                if (r_u) r_u[ix] = (T)(my_hits / (double)npos);
+                if (ap_u) ap_u[ix] = (T)(my_ap / (double)npos);
+                if (tap_u) tap_u[ix] = (T)(my_ap / (double)tn);
+                if (ndcg_u) ndcg_u[ix] = (T)my_dcg;
+                if (hit_u) hit_u[ix] = (T)(my_hits > 0);
+                if (rr_u) rr_u[ix] = (T)(my_hits ? (1. / (double)(my_min_rank + 1)) : 0.);
             }
-            if (!P.cumulative && hits >= cand) break;        // hpp:637-638
         }
-        if (!P.cumulative) {
+        if (!P.cumulative && lane == 0) {
             const int tn = K < npos ? K : npos;
             if (p_u) *p_u = (T)((double)hits / (double)K);
             if (tp_u) *tp_u = (T)((double)hits / (double)tn);
@@ -165,124 +210,158 @@ __global__ void user_metrics_kernel(const __grid_constant__ MetricsParams<T> P)
             if (rr_u) *rr_u = (T)(hits ? (1. / (double)(min_rank + 1)) : 0.);
         }
     }
+    __syncwarp();
 
-    // ---- post-hoc NaN rules (hpp:750-788) ----
-    if (k_leq_n) {
-        if (!P.cumulative) {
-            if (p_u) *p_u = NaN;
-            if (tp_u) *tp_u = NaN;
-            if (r_u) *r_u = NaN;
-            if (hit_u) *hit_u = NaN;
-        } else if (!did_walk) {
-            for (int c = 0; c < K; c++) {
+    // ---- post-hoc NaN rules (hpp:750-788).  Column c of a row is always touched by lane c % 32, scalars by lane 0. ----
+    {
+        const int cnt = P.cumulative ? K : 1;
+        if (k_leq_n) {
+            if (!P.cumulative || !did_walk)
+                for (int c = lane; c < cnt; c += 32) {
+                    if (p_u) p_u[c] = NaN;
+                    if (tp_u) tp_u[c] = NaN;
+                    if (r_u) r_u[c] = NaN;
+                    if (hit_u) hit_u[c] = NaN;
+                }
+            if (!did_walk)     // outputs the reference leaves untouched here; keep every element defined
+                for (int c = lane; c < cnt; c += 32) {
+                    if (ap_u) ap_u[c] = NaN;
+                    if (tap_u) tap_u[c] = NaN;
+                    if (rr_u) rr_u[c] = NaN;
+                    if (ndcg_u) ndcg_u[c] = NaN;
+                }
+        } else if (only_ndcg) {
+            for (int c = lane; c < cnt; c += 32) {
                 if (p_u) p_u[c] = NaN;
                 if (tp_u) tp_u[c] = NaN;
                 if (r_u) r_u[c] = NaN;
-                if (hit_u) hit_u[c] = NaN;
-            }
-        }
-        if (!did_walk) {   // outputs the reference leaves untouched here; keep every element defined
-            const int cnt = P.cumulative ? K : 1;
-            for (int c = 0; c < cnt; c++) {
                 if (ap_u) ap_u[c] = NaN;
                 if (tap_u) tap_u[c] = NaN;
+                if (hit_u) hit_u[c] = NaN;
                 if (rr_u) rr_u[c] = NaN;
-                if (ndcg_u) ndcg_u[c] = NaN;
             }
-        }
-    } else if (only_ndcg) {
-        const int cnt = P.cumulative ? K : 1;
-        for (int c = 0; c < cnt; c++) {
-            if (p_u) p_u[c] = NaN;
-            if (tp_u) tp_u[c] = NaN;
-            if (r_u) r_u[c] = NaN;
-            if (ap_u) ap_u[c] = NaN;
-            if (tap_u) tap_u[c] = NaN;
-            if (hit_u) hit_u[c] = NaN;
-            if (rr_u) rr_u[c] = NaN;
         }
     }
 
     // ---- ROC-AUC / PR-AUC (hpp:795-865) from the rank counts ----
     if (P.roc || P.pr || P.pos_rank) {
         if (only_ndcg || !P.count_ranks) {
-            if (P.roc) P.roc[ul] = NaN;
-            if (P.pr) P.pr[ul] = NaN;
+            if (lane == 0) {
+                if (P.roc) P.roc[ul] = NaN;
+                if (P.pr) P.pr[ul] = NaN;
+            }
         } else {
             // above[j] = number of candidates scoring strictly above the j-th smallest held-out score
-            // (counted by score_select_kernel); walk the held-out items from the best down.
+            // (counted by score_select_kernel); walk the held-out items from the best down.  Lane l takes the
+            // held-out items h = l+1, l+33, ...: the rank a tie chain assigns is a running maximum, the sums follow
+            // in order.
             const unsigned int* ab = P.auc_cnt + (size_t)tp0;
             unsigned long long prev_rank = 0, sum_ranks = 0;
             double ap_full = 0;
-            for (int h = 1; h <= npos; h++) {
-                const int i = npos - h + 1;
-                unsigned long long rank = (unsigned long long)ab[i - 1] + 1;
-                if (rank <= prev_rank) rank = prev_rank + 1;   // tied held-out scores take consecutive ranks
-                prev_rank = rank;
-                sum_ranks += rank;
-                ap_full += (double)h / (double)rank;
-                if (P.pos_rank) P.pos_rank[(size_t)tp0 + P.pos_perm[tp0 + i - 1]] = (long long)rank;
+            for (int hb = 1; hb <= npos; hb += 32) {
+                const int h = hb + lane;
+                const bool on = h <= npos;
+                // rank_h = max(above_h + 1, rank_{h-1} + 1)  <=>  rank_h - h = max over h' <= h of (above_h' + 1 - h')
+                long long key = on ? (long long)ab[npos - h] + 1 - (long long)h : LLONG_MIN;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const long long w = __shfl_up_sync(FULL_WARP, key, o);
+                    if (lane >= o && w > key) key = w;
+                }
+                const long long carry = (long long)prev_rank - (long long)(hb - 1);   // rank_{hb-1} - (hb-1)
+                if (hb > 1 && carry > key) key = carry;
+                const unsigned long long rank = (unsigned long long)(key + (long long)h);
+                const double t_ap = on ? (double)h / (double)rank : 0.;
+                if (on && P.pos_rank) P.pos_rank[(size_t)tp0 + P.pos_perm[tp0 + npos - h]] = (long long)rank;
+                const int cnt = npos - hb + 1 < 32 ? npos - hb + 1 : 32;
+                for (int t = 0; t < cnt; t++) {
+                    sum_ranks += __shfl_sync(FULL_WARP, rank, t);
+                    ap_full += __shfl_sync(FULL_WARP, t_ap, t);
+                }
+                prev_rank = __shfl_sync(FULL_WARP, rank, cnt - 1);
             }
-            const unsigned long long np = (unsigned long long)npos;
-            const unsigned long long nneg = (unsigned long long)cand - np;
-            if (P.roc)   // hpp:821-822 (long double there; double here, difference < 1e-15)
-                P.roc[ul] = (T)(1. - (double)(sum_ranks - (np * (np + 1)) / 2) / (double)(np * nneg));
-            if (P.pr) P.pr[ul] = (T)(ap_full / (double)npos);
+            if (lane == 0) {
+                const unsigned long long np = (unsigned long long)npos;
+                const unsigned long long nneg = (unsigned long long)cand - np;
+                if (P.roc)   // hpp:821-822 (long double there; double here, difference < 1e-15)
+                    P.roc[ul] = (T)(1. - (double)(sum_ranks - (np * (np + 1)) / 2) / (double)(np * nneg));
+                if (P.pr) P.pr[ul] = (T)(ap_full / (double)npos);
+            }
         }
     }
 
     // ---- NDCG normalisation (hpp:868-961) ----
     if (ndcg_u && did_walk) {
+        __syncwarp();
         const int L = K < npos ? K : npos;
         // what partial_sort + the vmax/vmin checks (hpp:870-887) decide, from one scan
         bool has_nan = false;
         int n_neg_inf = 0;
         T vmax = -NumTraits<T>::inf();
-        for (int j = 0; j < npos; j++) {
+        for (int j = lane; j < npos; j += 32) {
             const T v = tv[j];
             has_nan |= (v != v);
             n_neg_inf += (v == -NumTraits<T>::inf());
             if (v > vmax) vmax = v;
         }
+        has_nan = __any_sync(FULL_WARP, has_nan);
+        n_neg_inf = warp_sum(n_neg_inf);
+        vmax = warp_max(vmax);
         const bool bad = has_nan || isinf(vmax) || vmax <= 0 || (npos - n_neg_inf) < L;
         if (bad) {
             const int cnt = P.cumulative ? K : 1;
-            for (int c = 0; c < cnt; c++) ndcg_u[c] = NaN;
+            for (int c = lane; c < cnt; c += 32) ndcg_u[c] = NaN;
             return;
         }
-        // ideal DCG: the user's values in descending order (ties by position), selected one by one
+        // ideal DCG: the user's values in descending order.  One round per DISTINCT value: the largest value below
+        // the previous round's and how often it occurs (equal values give equal terms, their order is immaterial);
+        // its terms val / log2(ix + 2) are computed by the lanes owning those ranks and added in rank order.
         double idcg = 0;
-        T prev_v = 0;
-        int prev_j = -1;
+        T prev_v = NumTraits<T>::inf();
+        bool first = true, stopped = false;
         int ix = 0;
-        bool stopped = false;
-        for (; ix < L; ix++) {
-            T best_v = 0;
-            int best_j = -1;
-            for (int j = 0; j < npos; j++) {
+        while (ix < L) {
+            T best = -NumTraits<T>::inf();
+            int cnt = 0;
+            for (int j = lane; j < npos; j += 32) {
                 const T v = tv[j];
-                const bool after_prev = (prev_j < 0) || (v < prev_v) || (v == prev_v && j > prev_j);
-                if (after_prev && (best_j < 0 || v > best_v)) { best_v = v; best_j = j; }
+                if (first || v < prev_v) {
+                    if (v > best) { best = v; cnt = 1; }
+                    else if (v == best) cnt++;
+                }
             }
-            prev_v = best_v;
-            prev_j = best_j;
-            const double val = (double)best_v;
-            if (!P.cumulative) {
-                if (val <= 0) { stopped = true; break; }                 // hpp:907-910 (== :901-902 when all >= 0)
-                idcg += val / P.log2tab[ix];
-            } else {
-                if (val < 0) { stopped = true; break; }                  // hpp:938
-                idcg += val / P.log2tab[ix];
-                ndcg_u[ix] = (T)((double)ndcg_u[ix] / idcg);             // hpp:927, :940
+            const T wmax = warp_max(best);
+            const int total = warp_sum(best == wmax ? cnt : 0);
+            if (total <= 0) break;                                           // cannot happen: npos - ix values remain
+            const int take = total < L - ix ? total : L - ix;
+            const double val = (double)wmax;
+            if (!P.cumulative ? (val <= 0) : (val < 0)) { stopped = true; break; }   // hpp:907-910 (== :901-902 when all >= 0), :938
+            const int end = ix + take;
+            for (int cb = ix & ~31; cb < end; cb += 32) {
+                const int r = cb + lane;
+                const bool on = r >= ix && r < end;
+                const double term = on ? val / P.log2tab[r] : 0.;
+                const int t0 = (ix > cb ? ix : cb) - cb, t1 = (end < cb + 32 ? end : cb + 32) - cb;
+                double my_idcg = 0.;
+                for (int t = t0; t < t1; t++) {
+                    idcg += __shfl_sync(FULL_WARP, term, t);
+                    if (t == lane) my_idcg = idcg;
+                }
+                if (P.cumulative && on) ndcg_u[r] = (T)((double)ndcg_u[r] / my_idcg);   // hpp:927, :940
             }
+            ix = end;
+            prev_v = wmax;
+            first = false;
         }
         if (!P.cumulative) {
-            *ndcg_u = (T)(dcg / idcg);                                   // hpp:903, :912
+            if (lane == 0) *ndcg_u = (T)(dcg / idcg);                        // hpp:903, :912
         } else {
-            if (stopped) for (; ix < L; ix++) ndcg_u[ix] = (T)((double)ndcg_u[ix] / idcg);   // hpp:946-948
-            if (npos < K) {                                              // hpp:951-956 frozen tail (quirk Q4)
+            if (stopped) for (int c = ix + lane; c < L; c += 32) ndcg_u[c] = (T)((double)ndcg_u[c] / idcg);   // hpp:946-948
+            __syncwarp();
+            if (npos < K) {                                                  // hpp:951-956 frozen tail (quirk Q4)
                 const int upto = K < cand ? K : cand;
-                for (int c = npos; c < upto; c++) ndcg_u[c] = ndcg_u[npos - 1];
+                const T last = ndcg_u[npos - 1];
+                __syncwarp();
+                for (int c = npos + lane; c < upto; c += 32) ndcg_u[c] = last;
             }
         }
     }
