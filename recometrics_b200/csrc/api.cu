@@ -348,9 +348,11 @@ int run_call(const CallArgs<T>& a)
     const int KB = round_up(a.k + (a.bias ? 1 : 0), 16);            // fp16 factors per row (bias = one more factor)
     int f_stages = 0;
     {
-        const long long tile = (long long)KB * 256, budget = 225 * 1024;
+        // A tile + ring stages + barriers + row state within the 227 KB a CTA can have
+        const long long tile = (long long)KB * 256, budget = 227 * 1024 - (long long)filter_smem_fixed_bytes();
         f_stages = (int)(budget / tile) - 1;
         if (f_stages > F_MAX_STAGES) f_stages = F_MAX_STAGES;
+        if (const char* env = std::getenv("RMB200_STAGES")) { const int v = std::atoi(env); if (v >= 2 && v < f_stages) f_stages = v; }   // developer: shallower ring
     }
     // With rank counting (ROC/PR-AUC) every score has to be exact: the FMA tiles do everything.  Exception: with the
     // reference's tie-breaking noise the ranked top-K comes from the tensor path as well (its exact stage is where the

@@ -58,7 +58,7 @@ constexpr int F_THREADS = (F_EPI_WARPS + 1 + F_MMA_WARPS) * 32;   // + TMA produ
 constexpr int F_ACCBUFS = RMB_F_ACCBUFS;
 constexpr int F_ACCSHIFT = F_ACCBUFS == 4 ? 2 : 1;
 constexpr int F_TMEM_COLS = F_ACCBUFS * FN;
-constexpr int F_MAX_STAGES = 4;
+constexpr int F_MAX_STAGES = 6;              // ring depth: as many B tiles as fit next to the A tile (5 at 128 factors)
 constexpr int F_CHUNK = 32;              // TMEM columns per tcgen05.ld
 #ifndef RMB_F_CUT_MARGIN
 #define RMB_F_CUT_MARGIN 48               // a row's regions are cut back together once they hold this many more than the last cut kept
@@ -130,9 +130,10 @@ inline float filter_err_coef(int KB)
     return (float)(1.01 * c);
 }
 
+inline size_t filter_smem_fixed_bytes() { return 256 + sizeof(FilterRowState); }      // barriers + row state
 inline size_t filter_smem_bytes(int KB, int stages)
 {
-    return (size_t)(1 + stages) * KB * 128 * 2 + 256 + sizeof(FilterRowState);
+    return (size_t)(1 + stages) * KB * 128 * 2 + filter_smem_fixed_bytes();
 }
 
 // ------------------------------------------------------------------ tcgen05 wrappers

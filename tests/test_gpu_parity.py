@@ -97,6 +97,49 @@ def test_f64_all_metrics_with_auc(rb, oracle_mod):
     assert rep["topk_rows_differing"] == 0
 
 
+# ---------------------------------------------------------------- BASELINE catalogue sizes (full n, a block of the users)
+def test_full_catalogue_cfg4_1m_items(rb, oracle_mod):
+    """configs[3] at its full catalogue (1,000,000 items, p=128, K=100): a block of users against the oracle, and the
+    tensor-core path (sampled guess, 7813 item tiles per CTA) against the FMA path bit for bit on a larger block."""
+    d = synth.make(4, m=96, n=1_000_000)
+    _check(rb, oracle_mod, d, ("p", "r", "ap", "ndcg"), 100, label="cfg4 96x1000000 (full catalogue)")
+    d = synth.make(4, m=2048, n=1_000_000)
+    out = {}
+    for path in ("fma", "tensor"):
+        out[path] = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=100, precision=True, recall=True,
+                                            average_precision=True, ndcg=True, break_ties_with_noise=False, return_topk=True,
+                                            return_status=True, scoring_path=path)
+    a, b = out["fma"], out["tensor"]
+    assert b.timing["scoring_path"] == 2 and b.timing["filter_fallback_batches"] == 0
+    assert np.array_equal(a.status, b.status)
+    assert np.array_equal(a.topk_items, b.topk_items)
+    assert np.array_equal(a.topk_scores, b.topk_scores, equal_nan=True)
+    for key in ("P@K", "R@K", "AP@K", "NDCG@K"):
+        assert np.array_equal(a.metrics[key], b.metrics[key], equal_nan=True), key
+    # size-independent properties of the rows: hits are integers within [0, min(K, npos)], ids unique and scores sorted
+    npos = np.diff(d["X_test"].indptr)
+    ok = b.status == 0
+    hits = b.metrics["P@K"][ok].astype(np.float64) * 100
+    assert np.all(np.abs(hits - np.rint(hits)) < 1e-4) and np.all(np.rint(hits) <= np.minimum(100, npos[ok]))
+    assert np.allclose(np.rint(hits) / npos[ok], b.metrics["R@K"][ok], atol=1e-6)
+    ts = b.topk_scores[ok]
+    assert np.all(ts[:, :-1] >= ts[:, 1:])
+    ti = np.sort(b.topk_items[ok], axis=1)
+    assert np.all(ti[:, :-1] != ti[:, 1:])
+
+
+def test_full_catalogue_cfg3_auc_and_cfg5_f64(rb, oracle_mod):
+    """configs[2] (160,112 items, K=20 + ROC/PR-AUC rank counting) and configs[4] (float64, 300,000 items, cumulative
+    K=1..50, min_pos_test=2, cold users) at their full catalogue sizes, a block of users each, against the oracle."""
+    d = synth.make(3, m=400)
+    assert d["B"].shape[0] == 160112
+    _check(rb, oracle_mod, d, ("p", "r", "ap", "ndcg", "roc", "pr"), 20, label="cfg3 400x160112 (full catalogue)")
+    d = synth.make(5, m=600)
+    assert d["B"].shape[0] == 300000 and d["B"].dtype == np.float64
+    _check(rb, oracle_mod, d, ("ap", "ndcg"), 50, cumulative=True, label="cfg5 600x300000 f64 (full catalogue)",
+           product_kw=dict(min_pos_test=2), oracle_kw=dict(min_pos_test=2))
+
+
 # ---------------------------------------------------------------- golden vectors of the reference
 @pytest.mark.parametrize("name", case_names())
 def test_golden_vectors(rb, name, scoring_path):

@@ -11,11 +11,12 @@ ap.add_argument("--config", type=int, default=4)
 ap.add_argument("--users", type=int, default=18944)
 ap.add_argument("--items", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--factors", type=int, default=0)
 ap.add_argument("--f64", action="store_true")
 ap.add_argument("--noise", action="store_true", help="break_ties_with_noise=True (the reference default)")
 a = ap.parse_args()
 cfg = synth.CONFIGS[a.config]
-d = synth.make(a.config, m=a.users, n=a.items or cfg.n)
+d = synth.make(a.config, m=a.users, n=a.items or cfg.n, p=a.factors or None)
 flags = {q: (q in cfg.metrics) for q in synth.ALL10}
 kw = dict(precision=flags["p"], trunc_precision=flags["tp"], recall=flags["r"], average_precision=flags["ap"],
           trunc_average_precision=flags["tap"], ndcg=flags["ndcg"], hit=flags["hit"], rr=flags["rr"],
