@@ -12,6 +12,7 @@ ap.add_argument("--users", type=int, default=18944)
 ap.add_argument("--items", type=int, default=0)
 ap.add_argument("--reps", type=int, default=2)
 ap.add_argument("--factors", type=int, default=0)
+ap.add_argument("--k", type=int, default=0)
 ap.add_argument("--f64", action="store_true")
 ap.add_argument("--noise", action="store_true", help="break_ties_with_noise=True (the reference default)")
 a = ap.parse_args()
@@ -26,7 +27,7 @@ if a.f64:
     A, B = A.astype(np.float64), B.astype(np.float64)
 F = synth.algorithmic_flops(cfg, d["X_train"], d["X_test"])
 for i in range(a.reps):
-    r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=cfg.k, item_biases=d["item_biases"],
+    r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=a.k or cfg.k, item_biases=d["item_biases"],
                                 cumulative=cfg.cumulative, break_ties_with_noise=a.noise, min_pos_test=cfg.min_pos_test, **kw)
     t = r.timing
     print(json.dumps({"rep": i, "dom_ms": round(t["dominant_kernel_ms"], 3), "users": a.users, "kernel_ms": t["score_select_ms"], "tflops": F / t["score_select_ms"] / 1e9,
