@@ -104,3 +104,15 @@ def test_shard_bounds_partition():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(w - 1))
             sizes = [e - b for b, e in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_device_front_end_needs_a_gpu():
+    """calc_reco_metrics_device has no CPU path either: without a CUDA device it raises before touching anything."""
+    import numpy as np
+    import pytest
+    import torch
+    import recometrics_b200 as rb
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="CUDA device"):
+        rb.calc_reco_metrics_device(None, None, np.zeros((2, 2)), np.zeros((2, 2)))

@@ -374,6 +374,39 @@ def test_device_resident_call_equals_host_call(rb):
         assert pu.nan_equal_close(outs[q].cpu().numpy(), host.metrics[key], 0).all(), q
 
 
+def test_device_front_end_torch_tensors(rb, oracle_mod):
+    """calc_reco_metrics_device: factors as torch CUDA tensors (one of them a row-strided view), CSR matrices either
+    scipy (uploaded) or DeviceCSR (resident); rows come back as CUDA tensors and equal the host front-end's bit for bit."""
+    import torch
+    dev = torch.device("cuda", 0)
+    for cfg_id, m, n, k, cum, dtype in ((2, 700, 5000, 10, False, np.float32), (5, 500, 4000, 20, True, np.float64)):
+        d = synth.make(cfg_id, m=m, n=n)
+        A, B = d["A"].astype(dtype), d["B"].astype(dtype)
+        kw = dict(k=k, precision=True, recall=True, average_precision=True, ndcg=True, hit=True, cumulative=cum,
+                  break_ties_with_noise=False, return_topk=True, return_status=True, return_means=True)
+        host = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, item_biases=d["item_biases"], **kw)
+        tA = torch.from_numpy(A).to(dev)
+        wide = torch.zeros(n, A.shape[1] + 5, dtype=tA.dtype, device=dev)
+        wide[:, :A.shape[1]] = torch.from_numpy(B).to(dev)
+        tB = wide[:, :A.shape[1]]                                       # row stride p + 5
+        tb = None if d["item_biases"] is None else torch.from_numpy(d["item_biases"].astype(dtype)).to(dev)
+        Xtr = rb.DeviceCSR.from_scipy(d["X_train"], 0, dtype, with_data=False)
+        Xte = rb.DeviceCSR.from_scipy(d["X_test"], 0, dtype)
+        for xtr, xte in ((d["X_train"], d["X_test"]), (Xtr, Xte)):
+            r = rb.calc_reco_metrics_device(xtr, xte, tA, tB, item_biases=tb, **kw)
+            assert r.timing["h2d_bytes"] == 0 and r.timing["d2h_bytes"] == 0
+            assert np.array_equal(host.status, r.status.cpu().numpy())
+            assert np.array_equal(host.topk_items, r.topk_items.cpu().numpy())
+            for key, v in host.metrics.items():
+                if key == "K":
+                    continue
+                assert r.metrics[key].is_cuda and tuple(r.metrics[key].shape) == v.shape
+                assert np.array_equal(v, r.metrics[key].cpu().numpy(), equal_nan=True), key
+                assert np.array_equal(np.asarray(host.means[key]), np.asarray(r.means[key]), equal_nan=True), key
+    with pytest.raises(TypeError):
+        rb.calc_reco_metrics_device(d["X_train"], d["X_test"], A, B, k=5)        # numpy factors: use calc_reco_metrics
+
+
 def test_unsupported_requests_fail_loudly(rb):
     d = synth.make(1, m=100, n=900, p=8)
     with pytest.raises(NotImplementedError):
