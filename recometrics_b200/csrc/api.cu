@@ -225,13 +225,17 @@ cudaError_t launch_exact_topk_inst(const float* capx, T* cs, int* ci, int* cc, i
     const size_t staging = (rmb::exact_topk_smem_bytes(p_pad, sizeof(T)) + 15) & ~size_t(15);
     const size_t mt_bytes = nz.on ? (size_t)rmb::EXACT_WARPS * rmb::MT_N * sizeof(unsigned) : 0;   // generator states (tie_noise.cuh)
     if (staging + mt_bytes <= 100 * 1024) {       // two blocks per SM
-        auto kern = rmb::exact_topk_kernel<T, C, true>;
+        // 16-byte copies when every factor row starts on a 16-byte boundary and is a multiple of 16 bytes long
+        constexpr int V = 16 / (int)sizeof(T);
+        bool vec = (p % V == 0) && (ldb % V == 0) && ((reinterpret_cast<uintptr_t>(Brow) & 15) == 0);
+        if (const char* env = std::getenv("RMB200_EXACT_VEC")) vec = vec && std::atoi(env) != 0;      // developer: element-wise staging
+        auto kern = vec ? rmb::exact_topk_kernel<T, C, 2> : rmb::exact_topk_kernel<T, C, 1>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(staging + mt_bytes));
         if (e != cudaSuccess) return e;
         kern<<<blocks, rmb::EXACT_WARPS * 32, staging + mt_bytes, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K,
                                                                         nz.on, nz.seed_user0, staging, nz.trp, nz.tri, nz.n);
     } else {
-        rmb::exact_topk_kernel<T, C, false><<<blocks, rmb::EXACT_WARPS * 32, mt_bytes, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K,
+        rmb::exact_topk_kernel<T, C, 0><<<blocks, rmb::EXACT_WARPS * 32, mt_bytes, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K,
                                                                                              nz.on, nz.seed_user0, (size_t)0, nz.trp, nz.tri, nz.n);
     }
     return cudaGetLastError();

@@ -628,8 +628,11 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 // factors, + bias: the chain of score_select_kernel / score_entries_kernel, so the values are bit-identical
 // to the FMA path), NaN scores raise the user's NaN flag (hpp:195-197), best K (score descending, ties by
 // ascending item id) left unordered at the head of cand_score / cand_item.
-// STAGED: the item-factor rows of 32 candidates at a time are fetched with coalesced loads into shared memory
-// (row stride p_pad + 1: conflict-free), then every lane runs the chain of its own candidate from there.
+// MODE 1 / 2 (staged): the item-factor rows of 32 candidates at a time are fetched with cp.async into shared memory --
+// all 32 rows in flight at once, no registers in between -- then every lane runs the chain of its own candidate from
+// there.  MODE 2 moves 16 bytes per cp.async and reads the rows back with 16-byte loads (row stride p_pad + 16 bytes:
+// conflict-free for 16-byte accesses); it needs factor rows that are 16-byte aligned and a multiple of 16 bytes long.
+// MODE 1 moves single elements (row stride p_pad + 1).  MODE 0 reads the rows straight from global memory.
 constexpr int EXACT_WARPS = 4;
 __device__ __forceinline__ void cp_async_elem(float* dst, const float* src)
 {
@@ -639,9 +642,72 @@ __device__ __forceinline__ void cp_async_elem(double* dst, const double* src)
 {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
-inline size_t exact_topk_smem_bytes(int p_pad, size_t elem) { return (size_t)EXACT_WARPS * (32 * (size_t)(p_pad + 1) + p_pad) * elem; }
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+// per warp: 32 rows of p_pad + 16 bytes (either staged mode fits) + the user's factors
+inline size_t exact_topk_smem_bytes(int p_pad, size_t elem) { return (size_t)EXACT_WARPS * (32 * (size_t)(p_pad + 16 / elem) + p_pad) * elem; }
 
-template <typename T, int C, bool STAGED>
+// Best K of the warp's scored candidates (key: order-preserving integer image of the score, 0 = empty slot; ties at the
+// cut by ascending item id), written unordered to the head of the user's buffer.  Only the first EU of the E register
+// slots per lane can be occupied.  Returns the number kept.
+template <typename T, int E, int EU>
+__device__ __forceinline__ int exact_select(const typename NumTraits<T>::key_t (&key)[E], const int (&it)[E], const int K, const int lane,
+                                            T* cs, int* cio)
+{
+    typedef typename NumTraits<T>::key_t key_t;
+    int nvalid = 0;
+#pragma unroll
+    for (int e = 0; e < EU; e++) nvalid += (key[e] != 0) ? 1 : 0;
+    nvalid = __reduce_add_sync(FULL, nvalid);
+    key_t t = 0;                  // keep key > t, and key == t with item id <= id_cut
+    unsigned id_cut = 0x7fffffffu;
+    if (nvalid > K) {
+        for (int b = NumTraits<T>::KEYBITS - 1; b >= 0; b--) {
+            const key_t cand = t | ((key_t)1 << b);
+            int c = 0;
+#pragma unroll
+            for (int e = 0; e < EU; e++) c += (key[e] >= cand) ? 1 : 0;
+            c = __reduce_add_sync(FULL, c);
+            if (c >= K) t = cand;
+        }
+        int cgt = 0, cge = 0;
+#pragma unroll
+        for (int e = 0; e < EU; e++) { cgt += (key[e] > t) ? 1 : 0; cge += (key[e] >= t) ? 1 : 0; }
+        cgt = __reduce_add_sync(FULL, cgt);
+        cge = __reduce_add_sync(FULL, cge);
+        if (cge > K) {
+            const int need = K - cgt;
+            unsigned x = 0;
+            for (int b = 30; b >= 0; b--) {
+                const unsigned cand = x | (1u << b);
+                int c = 0;
+#pragma unroll
+                for (int e = 0; e < EU; e++) c += (key[e] == t && (unsigned)it[e] < cand) ? 1 : 0;
+                c = __reduce_add_sync(FULL, c);
+                if (c < need) x = cand;
+            }
+            id_cut = x;
+        }
+    }
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int e = 0; e < EU; e++) {
+        const bool keep = (key[e] != 0) && ((key[e] > t) || (key[e] == t && (unsigned)it[e] <= id_cut));
+        const unsigned mask = __ballot_sync(FULL, keep);
+        if (keep) {
+            const int pos = base + __popc(mask & ((1u << lane) - 1u));
+            cs[pos] = NumTraits<T>::from_orderable((u64)key[e]);
+            cio[pos] = it[e];
+        }
+        base += __popc(mask);
+    }
+    return base;
+}
+
+template <typename T, int C, int MODE>
 __global__ void __launch_bounds__(EXACT_WARPS * 32)
 exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_score, int* __restrict__ cand_item,
                   int* __restrict__ cand_count, const int mb, const int user0,
@@ -660,8 +726,11 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
     if (nv <= 0) return;
     const T* __restrict__ a = At + (size_t)(ul / BM) * p_pad * BM + (ul % BM);      // + k * BM
     const int* ci = cand_item + (size_t)ul * C;
-    T* rows = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (32 * (size_t)(p_pad + 1) + p_pad);   // [32][p_pad + 1]
-    T* a_sm = rows + 32 * (size_t)(p_pad + 1);                                                     // [p_pad]
+    constexpr bool STAGED = MODE != 0;
+    constexpr int V = 16 / (int)sizeof(T);                                                         // elements per 16 bytes
+    const int RS = p_pad + (MODE == 2 ? V : 1);                                                    // row stride of the staged rows
+    T* rows = reinterpret_cast<T*>(smem_raw) + (size_t)warp * (32 * (size_t)(p_pad + V) + p_pad);   // [32][RS]
+    T* a_sm = rows + 32 * (size_t)(p_pad + V);                                                     // [p_pad]
     if (STAGED) {
         for (int k = lane; k < p; k += 32) a_sm[k] = a[(size_t)k * BM];
         __syncwarp();
@@ -685,14 +754,26 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
                 for (int j = 0; j < 32; j++) {
                     const int item_j = __shfl_sync(FULL, item, j);
                     const T* __restrict__ b = Brow + (size_t)item_j * ldb;
-                    T* dst = rows + (size_t)j * (p_pad + 1);
-                    for (int k = lane; k < p; k += 32) cp_async_elem(dst + k, b + k);
+                    T* dst = rows + (size_t)j * RS;
+                    if (MODE == 2) { for (int k = lane * V; k < p; k += 32 * V) cp_async_16(dst + k, b + k); }
+                    else { for (int k = lane; k < p; k += 32) cp_async_elem(dst + k, b + k); }
                 }
                 asm volatile("cp.async.wait_all;" ::: "memory");
                 __syncwarp();
-                const T* mine = rows + (size_t)lane * (p_pad + 1);
+                const T* mine = rows + (size_t)lane * RS;
+                if (MODE == 2) {
+#pragma unroll 4
+                    for (int k = 0; k < p; k += V) {
+                        T av[V], bv[V];
+                        lds_vec(a_sm + k, av);
+                        lds_vec(mine + k, bv);
+#pragma unroll
+                        for (int x = 0; x < V; x++) acc = NumTraits<T>::fma(av[x], bv[x], acc);
+                    }
+                } else {
 #pragma unroll 8
-                for (int k = 0; k < p; k++) acc = NumTraits<T>::fma(a_sm[k], mine[k], acc);
+                    for (int k = 0; k < p; k++) acc = NumTraits<T>::fma(a_sm[k], mine[k], acc);
+                }
                 __syncwarp();
             } else if (valid) {
                 const T* __restrict__ b = Brow + (size_t)item * ldb;
@@ -768,55 +849,12 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
             }
         }
     }
-    int nvalid = 0;
-#pragma unroll
-    for (int e = 0; e < E; e++) nvalid += (key[e] != 0) ? 1 : 0;
-    nvalid = __reduce_add_sync(FULL, nvalid);
-    key_t t = 0;                  // keep key > t, and key == t with item id <= id_cut
-    unsigned id_cut = 0x7fffffffu;
-    if (nvalid > K) {
-        for (int b = NumTraits<T>::KEYBITS - 1; b >= 0; b--) {
-            const key_t cand = t | ((key_t)1 << b);
-            int c = 0;
-#pragma unroll
-            for (int e = 0; e < E; e++) c += (key[e] >= cand) ? 1 : 0;
-            c = __reduce_add_sync(FULL, c);
-            if (c >= K) t = cand;
-        }
-        int cgt = 0, cge = 0;
-#pragma unroll
-        for (int e = 0; e < E; e++) { cgt += (key[e] > t) ? 1 : 0; cge += (key[e] >= t) ? 1 : 0; }
-        cgt = __reduce_add_sync(FULL, cgt);
-        cge = __reduce_add_sync(FULL, cge);
-        if (cge > K) {
-            const int need = K - cgt;
-            unsigned x = 0;
-            for (int b = 30; b >= 0; b--) {
-                const unsigned cand = x | (1u << b);
-                int c = 0;
-#pragma unroll
-                for (int e = 0; e < E; e++) c += (key[e] == t && (unsigned)it[e] < cand) ? 1 : 0;
-                c = __reduce_add_sync(FULL, c);
-                if (c < need) x = cand;
-            }
-            id_cut = x;
-        }
-    }
     T* cs = cand_score + (size_t)ul * C;
     int* cio = cand_item + (size_t)ul * C;
-    __syncwarp();
-    int base = 0;
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        const bool keep = (key[e] != 0) && ((key[e] > t) || (key[e] == t && (unsigned)it[e] <= id_cut));
-        const unsigned mask = __ballot_sync(FULL, keep);
-        if (keep) {
-            const int pos = base + __popc(mask & ((1u << lane) - 1u));
-            cs[pos] = NumTraits<T>::from_orderable((u64)key[e]);
-            cio[pos] = it[e];
-        }
-        base += __popc(mask);
-    }
+    int base;
+    if (E > 4 && nv <= 128) base = exact_select<T, E, (E < 4 ? E : 4)>(key, it, K, lane, cs, cio);      // (the filter rarely keeps more: K' ~ 1.2 K)
+    else if (E > 8 && nv <= 256) base = exact_select<T, E, (E < 8 ? E : 8)>(key, it, K, lane, cs, cio);
+    else base = exact_select<T, E, E>(key, it, K, lane, cs, cio);
     if (lane == 0) cand_count[ul] = base;
 }
 
