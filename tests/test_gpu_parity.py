@@ -140,6 +140,29 @@ def test_full_catalogue_cfg3_auc_and_cfg5_f64(rb, oracle_mod):
            product_kw=dict(min_pos_test=2), oracle_kw=dict(min_pos_test=2))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("cumulative", [False, True])
+def test_metric_rows_long_walks_ties_and_negative_gains(rb, oracle_mod, dtype, cumulative):
+    """user_metrics_kernel is a warp per user that splits walks and held-out rows into chunks of 32: K = 100 (walk and
+    IDCG longer than a chunk), rows with up to a few hundred held-out items, gains with many ties, zeros and negative
+    values (hpp:906-913, :938), users whose gains are all <= 0 (NaN, hpp:875-887) -- against the oracle, all eight
+    top-K metrics."""
+    d = synth.make(1, m=1200, n=3000, p=16)
+    rng = np.random.default_rng(7)
+    Xte = d["X_test"].copy()
+    vals = rng.integers(-2, 6, size=Xte.data.shape[0]).astype(dtype)
+    for u in range(0, 1200, 97):                                      # some users: nothing positive
+        vals[Xte.indptr[u]:Xte.indptr[u + 1]] = -np.abs(vals[Xte.indptr[u]:Xte.indptr[u + 1]])
+    Xte.data = vals
+    d["X_test"] = Xte
+    d["A"], d["B"] = d["A"].astype(dtype), d["B"].astype(dtype)
+    assert np.diff(Xte.indptr).max() > 100
+    res, orc, rep = _check(rb, oracle_mod, d, ("p", "tp", "r", "ap", "tap", "ndcg", "hit", "rr"), 100, cumulative=cumulative,
+                           label="long walks / ties / negative gains %s cum=%d" % (np.dtype(dtype).name, cumulative))
+    nd = res.metrics["NDCG@K"]
+    assert np.isnan(nd).any() and np.isfinite(nd).any()
+
+
 # ---------------------------------------------------------------- golden vectors of the reference
 @pytest.mark.parametrize("name", case_names())
 def test_golden_vectors(rb, name, scoring_path):
