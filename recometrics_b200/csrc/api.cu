@@ -396,6 +396,29 @@ cudaError_t upload_rows(void* dst, const void* src, size_t src_pitch, size_t row
     return cudaSuccess;
 }
 
+// The user factors are uploaded one user batch ahead, on a stream of their own, into two alternating staging buffers:
+// the upload of batch b+1 runs while the scoring kernel of batch b does.  ready[s]: the upload into buffer s has landed;
+// freed[s]: the kernels that read buffer s have run.
+struct PrefetchStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+    bool freed_valid[2] = {false, false};
+    cudaError_t init()
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+            e = cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming);
+        }
+        return e;
+    }
+    ~PrefetchStream()
+    {
+        if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }     // nothing may still be writing the staging buffers
+        for (int i = 0; i < 2; i++) { if (ready[i]) cudaEventDestroy(ready[i]); if (freed[i]) cudaEventDestroy(freed[i]); }
+    }
+};
+
 template <typename T>
 int stage_rows(const T* src, size_t ld, int rows, int cols, bool on_dev, DevBuf& staging,
                const T** dev_src, size_t* dev_ld, cudaStream_t st, rmb200_timing_t& tm)
@@ -669,7 +692,8 @@ int run_call(const CallArgs<T>& a)
     if (const char* env = std::getenv("RMB200_BATCH_USERS")) { const int v = std::atoi(env); if (v > 0) UB = round_up(v, BM); }
     if (UB > round_up(mr, BM)) UB = round_up(mr, BM);
 
-    DevBuf d_At, d_Arow, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
+    DevBuf d_At, d_Arow[2], d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
+    PrefetchStream pf;                                     // (declared after the buffers: destroyed, i.e. drained, before them)
     CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
     DevBuf d_capx, d_overflow;
     // sampled threshold guess of the filter (filter_select.cuh, pass 0): every stride-th item tile, about 7/K of the
@@ -702,7 +726,22 @@ int run_call(const CallArgs<T>& a)
         CK(d_capx.alloc((size_t)UB * C * sizeof(float)));
         CK(d_overflow.alloc(8 * sizeof(int)));     // [0] users whose slack band overflowed, [1] users that took the retry pass
     }
-    if (!on_dev) CK(d_Arow.alloc((size_t)UB * a.k * sizeof(T)));
+    // upload of users [b0, b0 + UB) into staging buffer `slot`, on the prefetch stream
+    auto upload_users = [&](int b0, int slot) -> int {
+        const int nb = (mr - b0) < UB ? (mr - b0) : UB;
+        if (pf.freed_valid[slot]) CK(cudaStreamWaitEvent(pf.s, pf.freed[slot], 0));
+        CK(upload_rows(d_Arow[slot].p, a.A + (size_t)(ub + b0) * a.lda, a.lda * sizeof(T), (size_t)a.k * sizeof(T), (size_t)nb, pf.s));
+        tm.h2d_bytes += (int64_t)nb * a.k * (int64_t)sizeof(T);
+        CK(cudaEventRecord(pf.ready[slot], pf.s));
+        return RMB200_OK;
+    };
+    if (!on_dev) {
+        CK(pf.init());
+        CK(d_Arow[0].alloc((size_t)UB * a.k * sizeof(T)));
+        if (UB < mr) CK(d_Arow[1].alloc((size_t)UB * a.k * sizeof(T)));
+        int rc = upload_users(0, 0);
+        if (rc) return rc;
+    }
     CK(d_cs.alloc((size_t)UB * C * sizeof(T)));
     CK(d_ci.alloc((size_t)UB * C * sizeof(int)));
     CK(d_cc.alloc((size_t)UB * sizeof(int)));
@@ -728,13 +767,28 @@ int run_call(const CallArgs<T>& a)
         if (g_interrupt.load()) break;                     // hpp:488-489
         const int nb = (mr - b0) < UB ? (mr - b0) : UB;
         const int nb_pad = round_up(nb, BM);
+        const int a_slot = (b0 / UB) & 1;                  // staging buffer holding this batch's user factors (host inputs)
+        // the kernels reading the staged rows are queued: mark the buffer; once the scoring kernel is queued as well, the
+        // next batch's rows go up into the other buffer (pageable sources keep this thread busy copying meanwhile)
+        auto staged_rows_consumed = [&]() -> int {
+            if (on_dev) return RMB200_OK;
+            CK(cudaEventRecord(pf.freed[a_slot], st));
+            pf.freed_valid[a_slot] = true;
+            return RMB200_OK;
+        };
+        bool prefetched = false;
+        auto prefetch_next_users = [&]() -> int {
+            if (on_dev || prefetched || b0 + UB >= mr) return RMB200_OK;
+            prefetched = true;
+            return upload_users(b0 + UB, a_slot ^ 1);
+        };
 
         // user factors of the batch -> k-major
         const T* Asrc = nullptr; size_t Ald = 0;
         if (!on_dev) {
             pt.start();
-            int rc = stage_rows<T>(a.A + (size_t)(ub + b0) * a.lda, a.lda, nb, a.k, false, d_Arow, &Asrc, &Ald, st, tm);
-            if (rc) return rc;
+            CK(cudaStreamWaitEvent(st, pf.ready[a_slot], 0));     // uploaded one batch ahead: only what is still exposed is timed
+            Asrc = d_Arow[a_slot].as<T>(); Ald = (size_t)a.k;
             pt.stop(tm.h2d_ms);
         } else { Asrc = a.A + (size_t)(ub + b0) * a.lda; Ald = a.lda; }
         pt.start();
@@ -743,6 +797,7 @@ int run_call(const CallArgs<T>& a)
             pack_tiles_kernel<T, BM><<<grid, block, 0, st>>>(Asrc, Ald, nb, a.k, d_At.as<T>(), nb_pad, p_pad);
             CK(cudaGetLastError());
             tm.kernel_launches++;
+            if (!use_tensor) { int rc = staged_rows_consumed(); if (rc) return rc; }
         }
         if (count_ranks) {
             const int blocks = (nb + 7) / 8 < 8 * nsm ? (nb + 7) / 8 : 8 * nsm;
@@ -771,6 +826,7 @@ int run_call(const CallArgs<T>& a)
             cudaEventRecord(pk.a, st);
             CK(launch_score_select<T>(sp, C, count_ranks, nb_pad / BM, st));
             cudaEventRecord(pk.b, st);
+            { int rc = prefetch_next_users(); if (rc) return rc; }
             pk_pending = true;
             tm.kernel_launches++;
             return RMB200_OK;
@@ -791,6 +847,7 @@ int run_call(const CallArgs<T>& a)
             pack_f16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
                                                                                 d_anorm.as<float>(), nullptr, d_Ab.as<__half>(), nb_pad, KB);
             CK(cudaGetLastError());
+            { int rc = staged_rows_consumed(); if (rc) return rc; }
             CK(cudaMemsetAsync(d_overflow.p, 0, 8 * sizeof(int), st));
             tm.kernel_launches += 2;
             pt.stop(tm.prep_ms);
@@ -809,6 +866,7 @@ int run_call(const CallArgs<T>& a)
             cudaEventRecord(pk.a, st);
             CK(launch_filter_select(fp, C, nb_pad / BM, st));
             cudaEventRecord(pk.b, st);
+            { int rc = prefetch_next_users(); if (rc) return rc; }
             pk_pending = true;
             tm.kernel_launches++;
             int over_retry[8] = {0, 0, 0, 0, 0, 0, 0, 0};
