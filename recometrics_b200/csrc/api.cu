@@ -402,7 +402,8 @@ cudaError_t upload_rows(void* dst, const void* src, size_t src_pitch, size_t row
 struct PrefetchStream {
     cudaStream_t s = nullptr;
     cudaEvent_t ready[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
-    bool freed_valid[2] = {false, false};
+    cudaEvent_t test_rows = nullptr;                 // the held-out CSR arrays (read first by the metrics kernel) have landed
+    bool freed_valid[2] = {false, false}, test_rows_pending = false;
     cudaError_t init()
     {
         cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
@@ -410,12 +411,14 @@ struct PrefetchStream {
             e = cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming);
             if (e == cudaSuccess) e = cudaEventCreateWithFlags(&freed[i], cudaEventDisableTiming);
         }
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&test_rows, cudaEventDisableTiming);
         return e;
     }
     ~PrefetchStream()
     {
         if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }     // nothing may still be writing the staging buffers
         for (int i = 0; i < 2; i++) { if (ready[i]) cudaEventDestroy(ready[i]); if (freed[i]) cudaEventDestroy(freed[i]); }
+        if (test_rows) cudaEventDestroy(test_rows);
     }
 };
 
@@ -540,7 +543,9 @@ int run_call(const CallArgs<T>& a)
     const size_t nnz_te = (size_t)(lo_hi[3] - lo_hi[2]);
     if ((nnz_tr && !a.tri) || (nnz_te && !a.tei)) { set_err("bad argument", "CSR indices missing"); return RMB200_ERR_BAD_ARG; }
 
-    DevBuf d_trp, d_tri, d_tep, d_tei, d_tev;
+    DevBuf d_trp, d_tri, d_tep, d_tei, d_tev, d_Arow[2];
+    PrefetchStream pf;                                     // (declared after the buffers it fills: destroyed, i.e. drained, before them)
+    if (!on_dev) CK(pf.init());
     CK(d_trp.alloc((size_t)(mr + 1) * sizeof(int)));
     CK(d_tep.alloc((size_t)(mr + 1) * sizeof(int)));
     const int* tri_d = nullptr; const int* tei_d = nullptr; const T* tev_d = nullptr;
@@ -553,12 +558,16 @@ int run_call(const CallArgs<T>& a)
         CK(d_tri.alloc(nnz_tr * sizeof(int)));
         CK(d_tei.alloc(nnz_te * sizeof(int)));
         if (nnz_tr) CK(upload_rows(d_tri.p, a.tri + lo_hi[0], nnz_tr * sizeof(int), nnz_tr * sizeof(int), 1, st));
-        if (nnz_te) CK(upload_rows(d_tei.p, a.tei + lo_hi[2], nnz_te * sizeof(int), nnz_te * sizeof(int), 1, st));
+        // the held-out rows are not needed before the first batch's metrics (rank counting: its first scoring step): they
+        // go up on the prefetch stream, behind the item factors on the link instead of in front of them
+        if (nnz_te) CK(upload_rows(d_tei.p, a.tei + lo_hi[2], nnz_te * sizeof(int), nnz_te * sizeof(int), 1, pf.s));
         if (a.tev) {
             CK(d_tev.alloc(nnz_te * sizeof(T)));
-            if (nnz_te) CK(upload_rows(d_tev.p, a.tev + lo_hi[2], nnz_te * sizeof(T), nnz_te * sizeof(T), 1, st));
+            if (nnz_te) CK(upload_rows(d_tev.p, a.tev + lo_hi[2], nnz_te * sizeof(T), nnz_te * sizeof(T), 1, pf.s));
             tev_d = d_tev.as<T>();
         }
+        CK(cudaEventRecord(pf.test_rows, pf.s));
+        pf.test_rows_pending = true;
         CK(cudaStreamSynchronize(st));   // tmp1/tmp2 go out of scope
         tri_d = d_tri.as<int>(); tei_d = d_tei.as<int>();
         tm.h2d_bytes += (int64_t)(2 * (size_t)(mr + 1) * sizeof(int) + (nnz_tr + nnz_te) * sizeof(int) + (a.tev ? nnz_te * sizeof(T) : 0));
@@ -692,8 +701,7 @@ int run_call(const CallArgs<T>& a)
     if (const char* env = std::getenv("RMB200_BATCH_USERS")) { const int v = std::atoi(env); if (v > 0) UB = round_up(v, BM); }
     if (UB > round_up(mr, BM)) UB = round_up(mr, BM);
 
-    DevBuf d_At, d_Arow[2], d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
-    PrefetchStream pf;                                     // (declared after the buffers: destroyed, i.e. drained, before them)
+    DevBuf d_At, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
     CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
     DevBuf d_capx, d_overflow;
     // sampled threshold guess of the filter (filter_select.cuh, pass 0): every stride-th item tile, about 7/K of the
@@ -736,7 +744,6 @@ int run_call(const CallArgs<T>& a)
         return RMB200_OK;
     };
     if (!on_dev) {
-        CK(pf.init());
         CK(d_Arow[0].alloc((size_t)UB * a.k * sizeof(T)));
         if (UB < mr) CK(d_Arow[1].alloc((size_t)UB * a.k * sizeof(T)));
         int rc = upload_users(0, 0);
@@ -800,6 +807,7 @@ int run_call(const CallArgs<T>& a)
             if (!use_tensor) { int rc = staged_rows_consumed(); if (rc) return rc; }
         }
         if (count_ranks) {
+            if (pf.test_rows_pending) { CK(cudaStreamWaitEvent(st, pf.test_rows, 0)); pf.test_rows_pending = false; }
             const int blocks = (nb + 7) / 8 < 8 * nsm ? (nb + 7) / 8 : 8 * nsm;
             score_entries_kernel<T><<<blocks, 256, 0, st>>>(d_At.as<T>(), d_Bt.as<T>(), bias_d, p_pad, b0, nb,
                                                              tep_d, tei_d, d_status.as<int>(), d_pos_raw.as<T>());
@@ -946,6 +954,7 @@ int run_call(const CallArgs<T>& a)
             if (ex && ex->topk_items) mp.topk_items = on_dev ? ex->topk_items + (size_t)(ub + b0) * K : d_tki.as<int>();
             if (ex && ex->topk_scores) mp.topk_scores = on_dev ? reinterpret_cast<T*>(ex->topk_scores) + (size_t)(ub + b0) * K : d_tks.as<T>();
             mp.pos_rank = pos_rank_d;
+            if (pf.test_rows_pending) { CK(cudaStreamWaitEvent(st, pf.test_rows, 0)); pf.test_rows_pending = false; }
             user_metrics_kernel<T><<<(nb + METRICS_WARPS - 1) / METRICS_WARPS, METRICS_WARPS * 32, 0, st>>>(mp);
             CK(cudaGetLastError());
             tm.kernel_launches++;
