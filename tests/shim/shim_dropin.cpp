@@ -1,0 +1,57 @@
+// Drop-in check of include/recometrics_b200_shim.hpp (tests/test_capi_host.py builds and runs this):
+//  * with -DHAVE_REFERENCE_HEADER the reference's own declarations (src/recometrics_signatures.hpp:46-98) are included
+//    FIRST: the shim's definitions must then be definitions of exactly those functions -- taking their addresses with
+//    the reference's parameter lists is ambiguous or fails to link otherwise;
+//  * the calls go through the C-ABI of librecometrics_b200.so; without a CUDA device they must throw (no CPU path).
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <cmath>
+#include <stdexcept>
+#ifdef HAVE_REFERENCE_HEADER
+#include "recometrics_signatures.hpp"
+#endif
+#include "recometrics_b200_shim.hpp"
+
+typedef void (*metrics_f32_t)(const float*, const size_t, const float*, const size_t, const int32_t, const int32_t, const int32_t,
+                              const int32_t*, const int32_t*, const int32_t*, int32_t*, const float*, const int32_t, const bool, const bool,
+                              float*, float*, float*, float*, float*, float*, float*, float*, float*, float*,
+                              const bool, int32_t, int32_t, int32_t, uint64_t);
+typedef void (*metrics_f64_t)(const double*, const size_t, const double*, const size_t, const int32_t, const int32_t, const int32_t,
+                              const int32_t*, const int32_t*, const int32_t*, int32_t*, const double*, const int32_t, const bool, const bool,
+                              double*, double*, double*, double*, double*, double*, double*, double*, double*, double*,
+                              const bool, int32_t, int32_t, int32_t, uint64_t);
+
+int main()
+{
+    metrics_f32_t f32 = &calc_metrics_float;
+    metrics_f64_t f64 = &calc_metrics_double;
+    // 3 users x 4 items, 2 factors; every user holds out one item
+    const float A[6] = {1.f, 0.f, 0.f, 1.f, 1.f, 1.f}, B[8] = {1.f, 0.f, 0.f, 1.f, .5f, .5f, -1.f, 2.f};
+    const double Ad[6] = {1., 0., 0., 1., 1., 1.}, Bd[8] = {1., 0., 0., 1., .5, .5, -1., 2.};
+    const int32_t trp[4] = {0, 0, 0, 0}, tep[4] = {0, 1, 2, 3};
+    int32_t tei[3] = {0, 1, 3};
+    const float tev[3] = {1.f, 1.f, 1.f};
+    const double tevd[3] = {1., 1., 1.};
+    float p[3], ndcg[3];
+    double pd[3], ndcgd[3];
+    std::printf("has_gpu=%d\n", (int)get_has_openmp());
+    int threw = 0;
+    try {
+        f32(A, 2, B, 2, 3, 4, 2, trp, nullptr, tep, tei, tev, 2, false, false, p, nullptr, nullptr, nullptr, nullptr, ndcg, nullptr, nullptr,
+            nullptr, nullptr, true, 2, 1, 1, 1);
+        f64(Ad, 2, Bd, 2, 3, 4, 2, trp, nullptr, tep, tei, tevd, 2, false, false, pd, nullptr, nullptr, nullptr, nullptr, ndcgd, nullptr, nullptr,
+            nullptr, nullptr, true, 2, 1, 1, 1);
+        // template form used by the Rcpp wrapper (src/Rwrapper.cpp:250-274)
+        calc_metrics<double>(Ad, 2, Bd, 2, 3, 4, 2, trp, nullptr, tep, tei, tevd, 2, false, false, pd, nullptr, nullptr, nullptr, nullptr, ndcgd,
+                             nullptr, nullptr, nullptr, nullptr, true, 2, 1, 1, 1);
+        // users 0 and 1 rank their held-out item first, user 2 ranks item 3 (score 1) behind items 0..2? scores: 1, 1, 1, 1 -> tie row
+        std::printf("ok p=%g,%g ndcg=%g,%g pd=%g\n", p[0], p[1], ndcg[0], ndcg[1], pd[0]);
+        if (!(std::fabs(p[0] - 0.5f) < 1e-6f && std::fabs(p[1] - 0.5f) < 1e-6f && std::fabs(pd[0] - 0.5) < 1e-12)) return 3;
+    } catch (const std::runtime_error& e) {
+        threw = 1;
+        std::printf("threw runtime_error: %s\n", e.what());
+    }
+    if (!get_has_openmp() && !threw) return 2;     // no device and no exception: a CPU path would be a bug
+    return 0;
+}

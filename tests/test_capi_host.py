@@ -116,3 +116,31 @@ def test_device_front_end_needs_a_gpu():
         pytest.skip("a GPU is present")
     with pytest.raises(RuntimeError, match="CUDA device"):
         rb.calc_reco_metrics_device(None, None, np.zeros((2, 2)), np.zeros((2, 2)))
+
+
+def test_cpp_shim_is_a_drop_in_for_the_reference_declarations(tmp_path):
+    """include/recometrics_b200_shim.hpp defines calc_metrics_float / _double / get_has_openmp with the parameter lists of the
+    reference's src/recometrics_signatures.hpp:46-98 (included first when the reference is mounted: a mismatch makes the
+    address-of expressions in tests/shim/shim_dropin.cpp ambiguous) and the template Rwrapper.cpp instantiates; linked against
+    the C-ABI library the calls throw std::runtime_error when there is no CUDA device instead of computing on the CPU."""
+    import os
+    import shutil
+    import subprocess
+    import recometrics_b200 as rb
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else shutil.which("g++")
+    if cxx is None:
+        import pytest
+        pytest.skip("no g++")
+    libdir = os.path.dirname(rb.native_library_path())
+    exe = str(tmp_path / "shim_dropin")
+    cmd = [cxx, "-std=c++11", "-O1", "-Wall", "-I", os.path.join(root, "include")]
+    ref_src = "/root/reference/src"
+    if os.path.exists(os.path.join(ref_src, "recometrics_signatures.hpp")):
+        cmd += ["-DHAVE_REFERENCE_HEADER", "-I", ref_src]
+    cmd += [os.path.join(root, "tests", "shim", "shim_dropin.cpp"), "-o", exe, "-L", libdir, "-lrecometrics_b200", "-Wl,-rpath," + libdir]
+    subprocess.run(cmd, check=True, capture_output=True, text=True)
+    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert run.returncode == 0, run.stdout + run.stderr
+    if rb.device_count() == 0:
+        assert "threw runtime_error" in run.stdout

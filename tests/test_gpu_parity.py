@@ -430,6 +430,15 @@ def test_device_front_end_torch_tensors(rb, oracle_mod):
         rb.calc_reco_metrics_device(d["X_train"], d["X_test"], A, B, k=5)        # numpy factors: use calc_reco_metrics
 
 
+def test_cpp_shim_computes_on_the_gpu(rb, tmp_path):
+    """The C++ drop-in layer (include/recometrics_b200_shim.hpp: the reference's calc_metrics_float / _double / template
+    names) built with g++ and linked against the library: on a GPU box the calls compute (known answers checked inside
+    tests/shim/shim_dropin.cpp) instead of throwing."""
+    import test_capi_host
+    assert rb.device_count() > 0
+    test_capi_host.test_cpp_shim_is_a_drop_in_for_the_reference_declarations(tmp_path)
+
+
 def test_unsupported_requests_fail_loudly(rb):
     d = synth.make(1, m=100, n=900, p=8)
     with pytest.raises(NotImplementedError):
