@@ -15,8 +15,12 @@ torchrun every rank evaluates its own block of `--users` users against its own r
   e2e       the same call through the reference-facing API with HOST (pinned) buffers: host->device
             copies of that step's inputs and device->host copies of its metric rows inside the timed
             region.
-  roofline  FP32 (FP64) FMA pipe of the scoring kernel: algorithmic flops 2*p'*sum_eligible(n-ntrain)
-             / the kernel's CUDA-event time, against the FMA peak measured live.
+  roofline  of the dominant scoring kernel: algorithmic flops 2*p'*sum_eligible(n-ntrain) / the kernel's
+            CUDA-event time.  Top-K-only workloads run the tensor-core candidate filter (filter_select_kernel, fp16 MMAs):
+            bound "tensor", peak = the driver-measured sustained bf16 figure of MEASURED_PEAKS.json.  Rank counting
+            (ROC/PR-AUC) runs the FMA tiles (score_select_kernel): bound "fp32_fma"/"fp64_fma", peak = the FMA
+            microbenchmark run live before the timed region.  traffic = DRAM bytes of one launch from the committed ncu
+            capture (profiles/roofline_traffic.json).
   cpu_baseline  the reference's own OpenMP/SIMD implementation (oracle/_ref; the C port if absent)
             on this box's host cores, on a bounded prefix of the same users.
 """
