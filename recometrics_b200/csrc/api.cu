@@ -277,25 +277,28 @@ cudaError_t launch_rank_topk(T* cs, int* ci, const int* cc, int C, int nb, int K
 // plain cudaMemcpyAsync path.  RMB200_UPLOAD_THREADS=0 switches the pipeline off.
 constexpr size_t UP_CHUNK = 8u << 20;
 constexpr int UP_MAX_THREADS = 16;
-struct UploadLane { cudaStream_t st = nullptr; void* buf[2] = {nullptr, nullptr}; cudaEvent_t ev[2] = {nullptr, nullptr}; };
+struct UploadLane {
+    cudaStream_t st = nullptr;
+    void* buf[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2] = {nullptr, nullptr};      // recorded behind the DMA that reads buf[i]
+    bool recorded[2] = {false, false};           // ... at least once: the buffer may still be in flight from an earlier upload
+};
 struct UploadPool {
     int dev = -1;
     UploadLane lane[UP_MAX_THREADS];
     cudaEvent_t done[UP_MAX_THREADS] = {};
     cudaEvent_t start = nullptr;
+    int lanes = 0;
     bool ok = false;
 };
 UploadPool g_up;                 // (calls are serialised by the library's mutex)
 
 int upload_threads()
 {
-    static const int n = []() {
-        int v = (int)std::thread::hardware_concurrency() / 2;      // measured on a 16-core box: 60 ms plain, 32 ms with 4 threads, 25 ms with 8
-        if (v < 1) v = 1;
-        if (const char* e = std::getenv("RMB200_UPLOAD_THREADS")) v = std::atoi(e);
-        return v < 0 ? 0 : (v > UP_MAX_THREADS ? UP_MAX_THREADS : v);
-    }();
-    return n;
+    int v = (int)std::thread::hardware_concurrency() / 2;      // measured on a 16-core box: 60 ms plain, 32 ms with 4 threads, 25 ms with 8
+    if (v < 1) v = 1;
+    if (const char* e = std::getenv("RMB200_UPLOAD_THREADS")) v = std::atoi(e);
+    return v < 0 ? 0 : (v > UP_MAX_THREADS ? UP_MAX_THREADS : v);
 }
 
 void upload_pool_release()
@@ -306,7 +309,7 @@ void upload_pool_release()
     cudaSetDevice(g_up.dev);
     for (int t = 0; t < UP_MAX_THREADS; t++) {
         UploadLane& L = g_up.lane[t];
-        for (int b = 0; b < 2; b++) { if (L.buf[b]) cudaFreeHost(L.buf[b]); if (L.ev[b]) cudaEventDestroy(L.ev[b]); L.buf[b] = nullptr; L.ev[b] = nullptr; }
+        for (int b = 0; b < 2; b++) { if (L.buf[b]) cudaFreeHost(L.buf[b]); if (L.ev[b]) cudaEventDestroy(L.ev[b]); L.buf[b] = nullptr; L.ev[b] = nullptr; L.recorded[b] = false; }
         if (L.st) cudaStreamDestroy(L.st);
         L.st = nullptr;
         if (g_up.done[t]) cudaEventDestroy(g_up.done[t]);
@@ -314,15 +317,16 @@ void upload_pool_release()
     }
     if (g_up.start) cudaEventDestroy(g_up.start);
     g_up.start = nullptr;
-    g_up.dev = -1; g_up.ok = false;
+    g_up.dev = -1; g_up.ok = false; g_up.lanes = 0;
     cudaSetDevice(cur);
 }
 
 bool upload_pool_ready(int dev, int nthreads)
 {
-    if (g_up.ok && g_up.dev == dev) return true;
+    if (g_up.ok && g_up.dev == dev && g_up.lanes >= nthreads) return true;
     upload_pool_release();
     g_up.dev = dev;
+    g_up.lanes = nthreads;
     for (int t = 0; t < nthreads; t++) {
         UploadLane& L = g_up.lane[t];
         if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); upload_pool_release(); return false; }
@@ -351,7 +355,12 @@ cudaError_t upload_rows(void* dst, const void* src, size_t src_pitch, size_t row
     const int nt = upload_threads();
     int dev = 0;
     cudaGetDevice(&dev);
-    if (total < (32u << 20) || nt == 0 || row_bytes > UP_CHUNK || !host_pointer_is_pageable(src) || !upload_pool_ready(dev, nt)) {
+    // a contiguous source is a byte stream (chunks of UP_CHUNK bytes); a pitched one is cut at row boundaries
+    const bool contiguous = (src_pitch == row_bytes) || rows == 1;
+    size_t min_bytes = 32u << 20;
+    if (const char* env = std::getenv("RMB200_UPLOAD_MIN_BYTES")) min_bytes = (size_t)std::atoll(env);      // developer / tests
+    if (total < min_bytes || total == 0 || nt == 0 || (!contiguous && row_bytes > UP_CHUNK) || !host_pointer_is_pageable(src) ||
+        !upload_pool_ready(dev, nt)) {
         if (src_pitch == row_bytes) return cudaMemcpyAsync(dst, src, total, cudaMemcpyHostToDevice, st);
         return cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st);
     }
@@ -359,8 +368,10 @@ cudaError_t upload_rows(void* dst, const void* src, size_t src_pitch, size_t row
     cudaEvent_t start = g_up.start;
     cudaError_t e = cudaEventRecord(start, st);
     if (e != cudaSuccess) return e;
-    const size_t rows_per_chunk = UP_CHUNK / row_bytes;
-    const size_t nchunks = (rows + rows_per_chunk - 1) / rows_per_chunk;
+    const size_t unit = contiguous ? 1 : row_bytes;                              // bytes per indivisible piece
+    const size_t units = contiguous ? total : rows;
+    const size_t rows_per_chunk = contiguous ? UP_CHUNK : UP_CHUNK / row_bytes;   // pieces per chunk
+    const size_t nchunks = (units + rows_per_chunk - 1) / rows_per_chunk;
     cudaError_t errs[UP_MAX_THREADS];
     std::vector<std::thread> workers;
     for (int t = 0; t < nt; t++) {
@@ -370,17 +381,15 @@ cudaError_t upload_rows(void* dst, const void* src, size_t src_pitch, size_t row
             UploadLane& L = g_up.lane[t];
             if (er == cudaSuccess) er = cudaStreamWaitEvent(L.st, start, 0);
             int b = 0;
-            bool used[2] = {false, false};
             for (size_t c = (size_t)t; c < nchunks && er == cudaSuccess; c += (size_t)nt, b ^= 1) {
-                const size_t r0 = c * rows_per_chunk, nr = (rows - r0) < rows_per_chunk ? (rows - r0) : rows_per_chunk;
-                if (used[b]) er = cudaEventSynchronize(L.ev[b]);           // the DMA that last read this bounce buffer
+                const size_t r0 = c * rows_per_chunk, nr = (units - r0) < rows_per_chunk ? (units - r0) : rows_per_chunk;
+                if (L.recorded[b]) er = cudaEventSynchronize(L.ev[b]);     // the DMA that last read this bounce buffer (this upload's or an earlier one's)
                 if (er != cudaSuccess) break;
-                const unsigned char* sp = static_cast<const unsigned char*>(src) + r0 * src_pitch;
-                if (src_pitch == row_bytes) std::memcpy(L.buf[b], sp, nr * row_bytes);
+                const unsigned char* sp = static_cast<const unsigned char*>(src) + r0 * (contiguous ? 1 : src_pitch);
+                if (contiguous) std::memcpy(L.buf[b], sp, nr);
                 else for (size_t r = 0; r < nr; r++) std::memcpy(static_cast<unsigned char*>(L.buf[b]) + r * row_bytes, sp + r * src_pitch, row_bytes);
-                er = cudaMemcpyAsync(static_cast<unsigned char*>(dst) + r0 * row_bytes, L.buf[b], nr * row_bytes, cudaMemcpyHostToDevice, L.st);
-                if (er == cudaSuccess) er = cudaEventRecord(L.ev[b], L.st);
-                used[b] = true;
+                er = cudaMemcpyAsync(static_cast<unsigned char*>(dst) + r0 * unit, L.buf[b], nr * unit, cudaMemcpyHostToDevice, L.st);
+                if (er == cudaSuccess) { er = cudaEventRecord(L.ev[b], L.st); L.recorded[b] = true; }
             }
             errs[t] = er;
         });

@@ -439,6 +439,29 @@ def test_cpp_shim_computes_on_the_gpu(rb, tmp_path):
     test_capi_host.test_cpp_shim_is_a_drop_in_for_the_reference_declarations(tmp_path)
 
 
+def test_pageable_upload_pipeline_equals_plain_copies(rb, monkeypatch):
+    """Host inputs in ordinary (pageable) numpy memory go up through copy threads and pinned bounce buffers once they are
+    large (api.cu upload_rows); forced on for every array here -- pitched factor matrices, the contiguous CSR arrays,
+    several user batches (two alternating staging buffers on the prefetch stream) -- the results must be those of the
+    plain cudaMemcpy path, bit for bit."""
+    d = synth.make(3, m=5000, n=6000, p=40)
+    Abig = np.zeros((5000, 47), dtype=np.float32)
+    Abig[:, :40] = d["A"]
+    A = Abig[:, :40]                                                    # row pitch 47 floats
+    kw = dict(k=20, all_metrics=True, break_ties_with_noise=False, return_topk=True, return_ranks=True)
+    monkeypatch.setenv("RMB200_BATCH_USERS", "1024")
+    monkeypatch.setenv("RMB200_UPLOAD_THREADS", "0")
+    plain = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, d["B"], **kw)
+    monkeypatch.setenv("RMB200_UPLOAD_THREADS", "3")
+    monkeypatch.setenv("RMB200_UPLOAD_MIN_BYTES", "1")
+    piped = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, d["B"], **kw)
+    for key, v in plain.metrics.items():
+        if key != "K":
+            assert np.array_equal(v, piped.metrics[key], equal_nan=True), key
+    assert np.array_equal(plain.topk_items, piped.topk_items) and np.array_equal(plain.pos_rank, piped.pos_rank)
+    assert plain.timing["h2d_bytes"] == piped.timing["h2d_bytes"]
+
+
 def test_unsupported_requests_fail_loudly(rb):
     d = synth.make(1, m=100, n=900, p=8)
     with pytest.raises(NotImplementedError):
