@@ -144,3 +144,53 @@ def test_cpp_shim_is_a_drop_in_for_the_reference_declarations(tmp_path):
     assert run.returncode == 0, run.stdout + run.stderr
     if rb.device_count() == 0:
         assert "threw runtime_error" in run.stdout
+
+
+_CY_PROBE = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])
+import cpp_funs                                   # the reference's wrapper.pyx, unmodified, linked against librecometrics_b200.so
+from tools import synth
+d = synth.make(1, m=300, n=500, p=8)
+print("HAS", int(cpp_funs._get_has_openmp()))
+try:
+    out = cpp_funs.calc_reco_metrics(d["A"], 8, d["B"], 8, d["X_train"], d["X_test"], k_metrics=5, precision=True, ndcg=True,
+                                     average_precision=True, break_ties_with_noise=False)
+    np.save(sys.argv[3], np.stack([out[0], out[3], out[5]]))
+    print("COMPUTED")
+except RuntimeError as e:
+    print("RuntimeError:", e)
+"""
+
+
+def run_reference_cython_wrapper(tmp_path):
+    """(shared with the GPU suite) Runs the reference's own Cython entry point, cpp_funs.calc_reco_metrics, from the build
+    of oracle/build_ref_cython.py in a fresh interpreter.  Returns (stdout, path of the saved P@K / AP@K / NDCG@K rows)."""
+    import glob
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cy_dir = os.path.join(root, "oracle", "_ref", "cy_b200")
+    if not glob.glob(os.path.join(cy_dir, "cpp_funs*.so")):
+        if os.path.isdir("/root/reference/recometrics"):
+            subprocess.run([sys.executable, os.path.join(root, "oracle", "build_ref_cython.py")], check=True, capture_output=True)
+        else:
+            import pytest
+            pytest.skip("oracle/_ref/cy_b200 was not built (no /root/reference in the build container)")
+    out = str(tmp_path / "cy_rows.npy")
+    run = subprocess.run([sys.executable, "-c", _CY_PROBE, cy_dir, root, out], capture_output=True, text=True, timeout=300)
+    assert run.returncode == 0, run.stdout + run.stderr
+    return run.stdout, out
+
+
+def test_reference_cython_wrapper_binds_the_library(rb, tmp_path):
+    """The north-star's boundary, literally: the reference's existing Cython wrapper (recometrics/wrapper.pyx, cythonized and
+    compiled unmodified by oracle/build_ref_cython.py) calling the C-ABI through include/recometrics_b200_shim.hpp.  Without
+    a CUDA device its metric entry point raises RuntimeError (Cython's `except +` on the shim's exception) -- it does not
+    compute on the CPU."""
+    stdout, _ = run_reference_cython_wrapper(tmp_path)
+    if rb.device_count() == 0:
+        assert "HAS 0" in stdout and "RuntimeError:" in stdout and "no CUDA device" in stdout, stdout
+    else:
+        assert "COMPUTED" in stdout, stdout

@@ -462,6 +462,21 @@ def test_pageable_upload_pipeline_equals_plain_copies(rb, monkeypatch):
     assert plain.timing["h2d_bytes"] == piped.timing["h2d_bytes"]
 
 
+def test_reference_cython_wrapper_computes_on_the_gpu(rb, tmp_path):
+    """The reference's unmodified Cython wrapper built against the library (oracle/build_ref_cython.py; the compiled module
+    travels in oracle/_ref/cy_b200): its cpp_funs.calc_reco_metrics returns, on the GPU, the rows of this package's own
+    front-end bit for bit."""
+    import test_capi_host
+    stdout, path = test_capi_host.run_reference_cython_wrapper(tmp_path)
+    assert "HAS 1" in stdout and "COMPUTED" in stdout, stdout
+    rows = np.load(path)
+    d = synth.make(1, m=300, n=500, p=8)
+    r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, precision=True, average_precision=True, ndcg=True,
+                                break_ties_with_noise=False)
+    for i, key in enumerate(("P@K", "AP@K", "NDCG@K")):
+        assert np.array_equal(rows[i], r.metrics[key], equal_nan=True), key
+
+
 def test_unsupported_requests_fail_loudly(rb):
     d = synth.make(1, m=100, n=900, p=8)
     with pytest.raises(NotImplementedError):
