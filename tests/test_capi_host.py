@@ -194,3 +194,45 @@ def test_reference_cython_wrapper_binds_the_library(rb, tmp_path):
         assert "HAS 0" in stdout and "RuntimeError:" in stdout and "no CUDA device" in stdout, stdout
     else:
         assert "COMPUTED" in stdout, stdout
+
+
+def test_reference_python_package_runs_on_the_library(rb, tmp_path):
+    """One level further up: the reference's own Python package (recometrics/__init__.py, symlinked -- not copied -- next to the
+    cpp_funs module built by oracle/build_ref_cython.py) imports and validates as usual, and its calc_reco_metrics reaches
+    librecometrics_b200.so: on a box without a GPU the call ends in the library's RuntimeError, after the reference's own
+    argument handling (bias folding, CSR canonicalisation, dtype rule) has run.  Needs /root/reference (build container only)."""
+    import glob
+    import os
+    import subprocess
+    import sys
+    import pytest
+    ref_init = "/root/reference/recometrics/__init__.py"
+    if not os.path.exists(ref_init):
+        pytest.skip("no /root/reference here")
+    run_reference_cython_wrapper(tmp_path)                       # makes sure oracle/_ref/cy_b200 is built
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = glob.glob(os.path.join(root, "oracle", "_ref", "cy_b200", "cpp_funs*.so"))[0]
+    pkg = tmp_path / "site" / "recometrics"
+    pkg.mkdir(parents=True)
+    os.symlink(ref_init, pkg / "__init__.py")
+    os.symlink(so, pkg / os.path.basename(so))
+    probe = (
+        "import sys; sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[2])\n"
+        "import numpy as np, recometrics\n"
+        "from tools import synth\n"
+        "d = synth.make(2, m=200, n=400, p=8)\n"
+        "assert recometrics.cpp_funs.__file__.startswith(sys.argv[1])\n"
+        "try:\n"
+        "    df = recometrics.calc_reco_metrics(d['X_train'], d['X_test'], d['A'], d['B'], k=5, item_biases=d['item_biases'],\n"
+        "                                       break_ties_with_noise=False, nthreads=1)\n"
+        "    print('COMPUTED', list(df.columns))\n"
+        "except RuntimeError as e:\n"
+        "    print('RuntimeError:', e)\n")
+    env = dict(os.environ)                                       # ($ORIGIN in the module's rpath follows the symlink's directory)
+    env["LD_LIBRARY_PATH"] = os.path.dirname(rb.native_library_path()) + os.pathsep + env.get("LD_LIBRARY_PATH", "")
+    run = subprocess.run([sys.executable, "-c", probe, str(tmp_path / "site"), root], capture_output=True, text=True, timeout=300, env=env)
+    assert run.returncode == 0, run.stdout + run.stderr
+    if rb.device_count() == 0:
+        assert "RuntimeError:" in run.stdout and "no CUDA device" in run.stdout, run.stdout + run.stderr
+    else:
+        assert "COMPUTED ['P@5', 'AP@5', 'NDCG@5']" in run.stdout, run.stdout + run.stderr
