@@ -477,6 +477,54 @@ def test_reference_cython_wrapper_computes_on_the_gpu(rb, tmp_path):
         assert np.array_equal(rows[i], r.metrics[key], equal_nan=True), key
 
 
+_SIGINT_PROBE = r"""
+import os, signal, sys, threading, time
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+import recometrics_b200 as rb
+from tools import synth
+d = synth.make(3, m=200000, n=60000)
+rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=20, roc_auc=True, break_ties_with_noise=False,
+                        user_range=(0, 2000))                                   # warm-up (library load, workspace)
+def fire():
+    time.sleep(1.0)
+    os.kill(os.getpid(), signal.SIGINT)
+t0 = time.time()
+threading.Thread(target=fire, daemon=True).start()
+calls = 0
+try:
+    for i in range(200):                                                         # ~0.3 s per call: a minute if nothing stops it
+        rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=20, roc_auc=True, break_ties_with_noise=False)
+        calls += 1
+    print("COMPLETED", calls)
+except (KeyboardInterrupt, RuntimeError) as e:
+    print("INTERRUPTED", type(e).__name__, str(e)[:60].replace("\n", " "), "after %.2f s and %d calls" % (time.time() - t0, calls))
+# the handler was put back: the library is usable afterwards and a later Ctrl-C would reach Python again
+assert signal.getsignal(signal.SIGINT) is signal.default_int_handler
+r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=20, roc_auc=True, break_ties_with_noise=False,
+                            user_range=(0, 2000))
+print("AFTER", int(np.isfinite(r.metrics["ROC_AUC"][:2000]).sum() > 0))
+"""
+
+
+def test_sigint_stops_the_call_between_user_batches(scoring_path):
+    """Ctrl-C (reference: SignalSwitcher, src/recometrics.hpp:114-174 -- drain the loop, restore the handler, re-raise, throw):
+    a SIGINT sent while calls are running ends them within a batch or two with KeyboardInterrupt / "procedure was
+    interrupted", the previous handler is back in place, and the library keeps working."""
+    import subprocess
+    import sys
+    if scoring_path != "auto":
+        pytest.skip("one run is enough (the probe is a process of its own; rank counting runs the FMA tiles either way)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run = subprocess.run([sys.executable, "-c", _SIGINT_PROBE, root], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0, run.stdout + run.stderr
+    line = [ln for ln in run.stdout.splitlines() if ln.startswith("INTERRUPTED")]
+    assert line, run.stdout + run.stderr
+    secs = float(line[0].split("after ")[1].split(" s")[0])
+    assert 0.9 <= secs < 6.0, line[0]
+    assert "AFTER 1" in run.stdout, run.stdout + run.stderr
+
+
 def test_unsupported_requests_fail_loudly(rb):
     d = synth.make(1, m=100, n=900, p=8)
     with pytest.raises(NotImplementedError):
