@@ -199,21 +199,38 @@ cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool 
 }
 
 template <int C>
-cudaError_t launch_filter_inst(const rmb::FilterParams& P, int n_user_tiles, cudaStream_t st)
+cudaError_t launch_filter_inst(const rmb::FilterParams& P, int n_user_tiles, bool pair, cudaStream_t st)
 {
-    auto kern = rmb::filter_select_kernel<C>;
     const size_t smem = rmb::filter_smem_bytes(P.KB, P.stages);
+    if (!pair) {
+        auto kern = rmb::filter_select_kernel<C, false>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<n_user_tiles, rmb::F_THREADS, smem, st>>>(P);
+        return cudaGetLastError();
+    }
+    // CTA pairs (experimental, RMB200_PAIR=1): clusters of two CTAs, an even number of user tiles (a padding tile ranks no user)
+    auto kern = rmb::filter_select_kernel<C, true>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<n_user_tiles, rmb::F_THREADS, smem, st>>>(P);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)((n_user_tiles + 1) & ~1), 1, 1);
+    cfg.blockDim = dim3((unsigned)rmb::F_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, P);
 }
 
-inline cudaError_t launch_filter_select(const rmb::FilterParams& P, int C, int n_user_tiles, cudaStream_t st)
+inline cudaError_t launch_filter_select(const rmb::FilterParams& P, int C, int n_user_tiles, bool pair, cudaStream_t st)
 {
-    if (C == 256) return launch_filter_inst<256>(P, n_user_tiles, st);
-    if (C == 512) return launch_filter_inst<512>(P, n_user_tiles, st);
-    return launch_filter_inst<1024>(P, n_user_tiles, st);
+    if (C == 256) return launch_filter_inst<256>(P, n_user_tiles, pair, st);
+    if (C == 512) return launch_filter_inst<512>(P, n_user_tiles, pair, st);
+    return launch_filter_inst<1024>(P, n_user_tiles, pair, st);
 }
 
 struct NoiseArgs { int on; unsigned long long seed_user0; const int* trp; const int* tri; int n; };
@@ -530,6 +547,8 @@ int run_call(const CallArgs<T>& a)
     const bool tensor_ok = tensor_shape_ok && (!count_ranks || a.noise);
     if (path_req == 2 && !tensor_ok) { set_err("unsupported", "scoring_path=tensor needs no ROC/PR-AUC (rank counting), k <= ~400 and k_metrics <= 256"); return RMB200_ERR_UNSUPPORTED; }
     const bool use_tensor = tensor_ok && path_req != 1;
+    bool f_pair = false;               // experimental CTA-pair filter (filter_select_kernel<C, true>)
+    if (const char* env = std::getenv("RMB200_PAIR")) f_pair = use_tensor && std::atoi(env) != 0;
     const bool fma_counts_first = use_tensor && count_ranks;
     tm.scoring_path = use_tensor ? 2 : 1;
 #ifndef RMB_F_CMID
@@ -655,7 +674,7 @@ int run_call(const CallArgs<T>& a)
         row_norm_kernel<T><<<(a.n + 7) / 8, 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0, nullptr, d_maxbn.as<unsigned>());
         CK(cudaGetLastError());
         pack_f16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0, nullptr, d_maxbn.as<unsigned>(),
-                                                                            d_Bb.as<__half>(), n_pad128, KB);
+                                                                            d_Bb.as<__half>(), n_pad128, KB, f_pair ? 1 : 0);
         CK(cudaGetLastError());
         tm.kernel_launches += 2;
         pt.stop(tm.prep_ms);
@@ -738,7 +757,7 @@ int run_call(const CallArgs<T>& a)
         }
     }
     if (use_tensor) {
-        CK(d_Ab.alloc((size_t)UB * KB * sizeof(__half)));
+        CK(d_Ab.alloc((size_t)(UB + BM) * KB * sizeof(__half)));       // (+ one tile: the pair filter pads to an even number of user tiles)
         CK(d_anorm.alloc((size_t)UB * sizeof(float)));
         CK(d_capx.alloc((size_t)UB * C * sizeof(float)));
         CK(d_overflow.alloc(8 * sizeof(int)));     // [0] users whose slack band overflowed, [1] users that took the retry pass
@@ -881,7 +900,7 @@ int run_call(const CallArgs<T>& a)
             fp.noise_band = a.noise ? 2.02e-12f : 0.f;
             fp.dbg = 0; if (const char* env = std::getenv("RMB200_DBG")) fp.dbg = std::atoi(env);
             cudaEventRecord(pk.a, st);
-            CK(launch_filter_select(fp, C, nb_pad / BM, st));
+            CK(launch_filter_select(fp, C, nb_pad / BM, f_pair, st));
             cudaEventRecord(pk.b, st);
             { int rc = prefetch_next_users(); if (rc) return rc; }
             pk_pending = true;

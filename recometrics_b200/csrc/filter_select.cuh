@@ -179,6 +179,50 @@ __device__ __forceinline__ void tmem_ld32(const unsigned taddr, unsigned (&r)[32
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ------------------------------------------------------------------ CTA pair (tcgen05 cta_group::2), see filter_select_kernel<C, true>
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all()
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared-memory address of the same variable in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned mapa_shared(const unsigned saddr, const unsigned rank)
+{
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(const unsigned cluster_addr)
+{
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ unsigned ld_shared_cluster_u32(const unsigned cluster_addr)
+{
+    unsigned v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
+    return v;
+}
+// descriptor of a 64-row half tile: LBO = 64 rows * 16 B = 1024 (>>4 = 64)
+__device__ __forceinline__ uint64_t umma_desc_half(const unsigned saddr)
+{
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)64 << 16) | ((uint64_t)8 << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_f16_pair(const unsigned tmem_d, const uint64_t adesc, const uint64_t bdesc,
+                                               const unsigned idesc, const unsigned accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of the MMAs issued so far -> the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(const unsigned bar)
+{
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((unsigned short)3) : "memory");
+}
+
 // One warp: cut a row's candidates back to those that can still belong to the exact top K: approximate score >=
 // (K-th best approximate score) - slack.  The row's buffer is four regions of C/4 entries (one per epilogue warp of the
 // quarter), region s holding cnt4[s] entries; all of them are read into registers first, so the survivors can be written
@@ -313,12 +357,22 @@ __device__ __noinline__ int filter_append_group(const float s0, const float s1, 
 __device__ __forceinline__ int filter_pass_tiles(const FilterParams& P, const int pass, const int NT) { return pass == 0 ? P.sample_tiles : NT; }
 __device__ __forceinline__ int filter_pass_tile(const FilterParams& P, const int pass, const int j) { return pass == 0 ? j * P.sample_stride : j; }
 
-template <int C>
+// PAIR (launched as clusters of two CTAs; EXPERIMENTAL, off unless RMB200_PAIR=1 -- written at the end of round 1 on top of
+// tools/ubench/umma_pair_probe.cu and not yet tuned): the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 of 256 users x
+// 128 items per k-step.  Each CTA keeps its own 128 user rows, its own accumulators (its TMEM holds its rows of D, so the
+// epilogue below is unchanged) and only HALF of every item tile (CTA r: items r*64..r*64+63 of the tile, 16 KB bulk copy from a
+// B image packed in halves): the L2 -> shared-memory traffic that bounds the pipeline is halved.  The leader (rank 0) issues
+// the MMAs once both halves have landed (the peer's MMA warps forward their `full` barrier with a remote arrive) and both
+// CTAs' epilogues have drained the accumulator buffer (the peer's epilogue warps arrive remotely on the leader's `acc_empty`);
+// its commits are multicast to `empty` / `acc_full` of both CTAs.  The retry pass is taken by both CTAs if either needs it.
+template <int C, bool PAIR>
 __global__ void __launch_bounds__(F_THREADS, 1)
 filter_select_kernel(const __grid_constant__ FilterParams P)
 {
     const int KB = P.KB, S = P.stages;
     const unsigned tile_bytes = (unsigned)KB * 128u * 2u;          // one operand tile (A or B)
+    const unsigned b_bytes = PAIR ? tile_bytes / 2u : tile_bytes;  // what one ring stage receives (the stage slots keep their size)
+    const unsigned rank = PAIR ? cluster_ctarank() : 0u;
     unsigned char* a_tile = smem_raw;
     unsigned char* b_ring = a_tile + tile_bytes;
     u64* bars = reinterpret_cast<u64*>(b_ring + (size_t)S * tile_bytes);
@@ -326,6 +380,7 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
     const unsigned bar_full = smem_u32(bars), bar_empty = bar_full + 8 * F_MAX_STAGES;
     const unsigned bar_accf = bar_empty + 8 * F_MAX_STAGES, bar_acce = bar_accf + 32, bar_a = bar_acce + 32;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * F_MAX_STAGES + 9);
+    const unsigned bar_pfull = bar_a + 16;                         // PAIR, leader: the peer's half of stage s has landed
     FilterRowState* rs = reinterpret_cast<FilterRowState*>(reinterpret_cast<unsigned char*>(bars) + 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -334,18 +389,25 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 
     if (tid == 0) {
         for (int s = 0; s < F_MAX_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < F_ACCBUFS; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, F_EPI_WARPS); }
+        for (int b = 0; b < F_ACCBUFS; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, PAIR ? 2 * F_EPI_WARPS : F_EPI_WARPS); }
         mbar_init(bar_a, 1);
+        if (PAIR) for (int s = 0; s < F_MAX_STAGES; s++) mbar_init(bar_pfull + 8 * s, 1);
         mbar_fence_init();
         rs->retry = 0;
         for (int i = 0; i < 4; i++) rs->stat[i] = 0;
     }
-    if (warp == F_EPI_WARPS + 1) {      // the MMA warp owns the tensor-memory allocation
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((unsigned)F_TMEM_COLS));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+    if (warp == F_EPI_WARPS + 1) {      // the MMA warp owns the tensor-memory allocation (PAIR: one warp of each CTA)
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((unsigned)F_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((unsigned)F_TMEM_COLS));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();       // both CTAs: barriers initialised, tensor memory allocated
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
 
@@ -367,9 +429,11 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     if ((P.dbg & 16) && it0 + j >= S) { mbar_arrive(bar_full + 8 * s); } else       // 16: no TMA after the first round (stale tiles)
 #endif
                     {
-                    mbar_arrive_expect_tx(bar_full + 8 * s, tile_bytes);
-                    tma_bulk_g2s(smem_u32(b_ring) + (unsigned)s * tile_bytes, P.Bb + (size_t)filter_pass_tile(P, pass, j) * KB * 128, tile_bytes,
-                                 bar_full + 8 * s);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
+                    // (PAIR: the item matrix is packed in 64-item halves, [tile][half][k/8][64][8]; this CTA takes half `rank`)
+                    tma_bulk_g2s(smem_u32(b_ring) + (unsigned)s * tile_bytes,
+                                 P.Bb + (PAIR ? ((size_t)filter_pass_tile(P, pass, j) * 2 + rank) * KB * 64 : (size_t)filter_pass_tile(P, pass, j) * KB * 128),
+                                 b_bytes, bar_full + 8 * s);
                     }
                 }
                 __syncwarp();
@@ -378,8 +442,9 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
         } else if (warp > F_EPI_WARPS) {
             // ===================== MMA issuers (converged warps, one elected lane issues; warp w takes iterations it % F_MMA_WARPS == w) =====================
             // D fp32 (bit 4), A and B fp16 (format 0 at bits 7 and 10), both K-major, N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
-            const unsigned idesc = (1u << 4) | ((unsigned)(FN >> 3) << 17) | ((128u >> 4) << 24);
-            const uint64_t adesc0 = umma_desc(smem_u32(a_tile)), bdesc0 = umma_desc(smem_u32(b_ring));
+            const unsigned idesc = (1u << 4) | ((unsigned)(FN >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
+            const uint64_t adesc0 = umma_desc(smem_u32(a_tile)), bdesc0 = PAIR ? umma_desc_half(smem_u32(b_ring)) : umma_desc(smem_u32(b_ring));
+            const unsigned b_kstep = PAIR ? 2048u : 4096u;                    // bytes between two K=16 steps of the B operand
             int ksteps = KB / 16;                                             // K=16 per MMA = two 16-byte k chunks of 2048 B
 #if RMB_F_DBG
             if (P.dbg & 32) ksteps = ksteps / 2 > 0 ? ksteps / 2 : 1;         // 32: half of the k steps
@@ -390,18 +455,37 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             int s = (it0 + j) % S, ph = ((it0 + j) / S) & 1;
             for (; j < ntiles; j += F_MMA_WARPS) {
                 const int it = it0 + j, b = it & (F_ACCBUFS - 1);
-                mbar_wait(bar_acce + 8 * b, ((it >> F_ACCSHIFT) & 1) ^ 1);     // accumulator buffer drained by the epilogue
+                if (PAIR && rank != 0) {
+                    // peer CTA: its half of the tile has landed -> tell the leader; the leader's MMAs do the rest
+                    mbar_wait(bar_full + 8 * s, ph);
+                    if (elect_one()) mbar_arrive_cluster(mapa_shared(bar_pfull + 8 * s, 0u));
+                    __syncwarp();
+                    s += F_MMA_WARPS;
+                    while (s >= S) { s -= S; ph ^= 1; }
+                    continue;
+                }
+                mbar_wait(bar_acce + 8 * b, ((it >> F_ACCSHIFT) & 1) ^ 1);     // accumulator buffer drained by the epilogue (PAIR: of both CTAs)
                 mbar_wait(bar_full + 8 * s, ph);                              // B tile landed
+                if (PAIR) mbar_wait(bar_pfull + 8 * s, ph);                   // ... and the peer's half
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t bdesc = umma_desc_advance(bdesc0, (unsigned)s * tile_bytes);
                     const unsigned d = tmem_base + (unsigned)(b * FN);
-                    umma_f16(d, adesc0, bdesc, idesc, 0u);
+                    if (PAIR) {
+                        umma_f16_pair(d, adesc0, bdesc, idesc, 0u);
 #pragma unroll 7
-                    for (int ks = 1; ks < ksteps; ks++)
-                        umma_f16(d, umma_desc_advance(adesc0, ks * 4096), umma_desc_advance(bdesc, ks * 4096), idesc, 1u);
-                    umma_commit(bar_empty + 8 * s);                           // stage reusable once these MMAs have read it
-                    umma_commit(bar_accf + 8 * b);                            // accumulator complete
+                        for (int ks = 1; ks < ksteps; ks++)
+                            umma_f16_pair(d, umma_desc_advance(adesc0, ks * 4096), umma_desc_advance(bdesc, ks * b_kstep), idesc, 1u);
+                        umma_commit_pair(bar_empty + 8 * s);
+                        umma_commit_pair(bar_accf + 8 * b);
+                    } else {
+                        umma_f16(d, adesc0, bdesc, idesc, 0u);
+#pragma unroll 7
+                        for (int ks = 1; ks < ksteps; ks++)
+                            umma_f16(d, umma_desc_advance(adesc0, ks * 4096), umma_desc_advance(bdesc, ks * 4096), idesc, 1u);
+                        umma_commit(bar_empty + 8 * s);                       // stage reusable once these MMAs have read it
+                        umma_commit(bar_accf + 8 * b);                        // accumulator complete
+                    }
                 }
                 __syncwarp();
                 s += F_MMA_WARPS;
@@ -476,7 +560,10 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 tmem_ld32(taddr0 + (unsigned)(buf * FN), v);
                 tc_fence_before();                      // this warp's part of the accumulator is in registers
                 __syncwarp();
-                if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+                if (lane == 0) {
+                    if (PAIR && rank != 0) mbar_arrive_cluster(mapa_shared(bar_acce + 8 * buf, 0u));    // the leader counts both CTAs' warps
+                    else mbar_arrive(bar_acce + 8 * buf);
+                }
                 if (++buf == F_ACCBUFS) { buf = 0; par ^= 1u; }
 #if RMB_F_DBG
                 if (P.dbg & 1) continue;
@@ -601,7 +688,12 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
         it0 += ntiles;
         if (pass == 0) continue;         // the sample's result is consumed by the epilogue warps alone
         __syncthreads();
-        if (pass == 2 || !__any_sync(FULL, rs->retry != 0)) break;      // (a vote: the compiler keeps the pass loop warp-uniform)
+        unsigned again = rs->retry != 0 ? 1u : 0u;
+        if (PAIR) {                                                      // both CTAs walk the same passes: retry if either needs it
+            cluster_sync_all();
+            again |= ld_shared_cluster_u32(mapa_shared(smem_u32(&rs->retry), rank ^ 1u)) != 0u ? 1u : 0u;
+        }
+        if (pass == 2 || !__any_sync(FULL, again != 0u)) break;          // (a vote: the compiler keeps the pass loop warp-uniform)
     }
 
     if (warp < F_EPI_WARPS && (warp >> 2) == 0) {
@@ -620,8 +712,11 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 #if RMB_F_STATS
     if (tid < 4 && P.retries) atomicAdd(P.retries + 1 + tid, rs->stat[tid]);
 #endif
-    if (warp == F_EPI_WARPS + 1)
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)F_TMEM_COLS));
+    if (PAIR) cluster_sync_all();       // neither CTA leaves (or frees tensor memory) while the pair's MMAs or remote arrivals are in flight
+    if (warp == F_EPI_WARPS + 1) {
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)F_TMEM_COLS));
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)F_TMEM_COLS));
+    }
 }
 
 // One warp per user: exact scores of the candidates the filter kept (sequential fma chain over the original

@@ -146,7 +146,7 @@ template <typename T>
 __global__ void pack_f16_kernel(const T* __restrict__ src, const size_t ld, const int rows, const int cols,
                                 const T* __restrict__ extra, const int ones_col,
                                 const float* __restrict__ row_norm, const unsigned* __restrict__ global_norm_bits,
-                                __half* __restrict__ dst, const int rows_pad, const int KB)
+                                __half* __restrict__ dst, const int rows_pad, const int KB, const int split_halves = 0)
 {
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int chunks = KB / 8;
@@ -169,7 +169,9 @@ __global__ void pack_f16_kernel(const T* __restrict__ src, const size_t ld, cons
         }
         v[e] = __float2half_rn(x * scale);
     }
-    *reinterpret_cast<uint4*>(dst + (size_t)idx * 8) = *reinterpret_cast<const uint4*>(v);
+    // split_halves (item matrix for the CTA-pair filter): a tile is stored as two 64-row halves, [tile][half][k/8][64][8]
+    const size_t out = split_halves ? ((((size_t)tile * 2 + (size_t)(rl / 64)) * chunks + c) * 64 + (size_t)(rl % 64)) : (size_t)idx;
+    *reinterpret_cast<uint4*>(dst + out * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
 // One warp per row: Euclidean norm of the row (with the extra bias / 1.0 component), rounded up a little;
