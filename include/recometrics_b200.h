@@ -71,6 +71,9 @@ typedef struct rmb200_timing {
     int64_t filter_fallback_batches; /* user batches the tensor-core filter handed back to the FMA path         */
     double dominant_kernel_ms; /* the scoring kernel alone (filter_select_kernel / score_select_kernel), all batches */
     int64_t filter_retry_rows; /* users whose sampled threshold guess failed its check (their CTA walked the catalogue twice) */
+    int64_t filter_fallback_users;   /* users the tensor-core filter handed back to the FMA path (only they are re-run)          */
+    double filter_err_ratio_max;     /* extra.filter_stats: largest |approximate - exact| / error bound over all re-scored       */
+                                     /* candidates of the call (the bound holds iff this is <= 1)                                 */
 } rmb200_timing_t;
 
 /* Optional extension block (pass NULL for reference behaviour).  Zero-initialise, then set
@@ -79,7 +82,8 @@ typedef struct rmb200_extra {
     int32_t struct_size;
     int32_t device;             /* CUDA device ordinal; -1 = env RMB200_DEVICE or 0                    */
     int32_t user_begin;         /* evaluate only users [user_begin, user_end) -- the unit by which a   */
-    int32_t user_end;           /* job is sharded over GPUs/processes; 0,0 = all m users.  Arrays keep */
+    int32_t user_end;           /* job is sharded over GPUs/processes; 0,0 = all m users; user_end < 0  */
+                                /* = an empty block (nothing is evaluated or written).  Arrays keep     */
                                 /* their full-size indexing: row u of every output is written at u.    */
     int32_t inputs_on_device;   /* 1: A, B, item_biases, the CSR arrays AND all outputs are device     */
                                 /* pointers on `device` (HBM-resident call, no host copies)            */
@@ -109,6 +113,14 @@ typedef struct rmb200_extra {
                                 /* metrics that were not requested or have no valid user.  Host pointer, or device */
                                 /* pointer when inputs_on_device.                                                   */
     int64_t *metric_counts;     /* optional out [10 * W]: users that entered each mean                              */
+    int32_t has_nan_bits;       /* 1: every "NaN" the call writes into the metric outputs is the bit pattern nan_bits (low 32 bits   */
+    int32_t filter_stats;       /*    for float calls) instead of a plain quiet NaN -- R's NA_REAL, src/recometrics.hpp:75-80.      */
+    uint64_t nan_bits;          /* filter_stats = 1: fill timing.filter_err_ratio_max (costs a little in the exact stage)           */
+    const int32_t *devices;     /* optional [n_devices] (host-pointer calls): CUDA device ordinals to spread the users of this ONE   */
+    int32_t n_devices;          /* call over -- the reference's call uses every core (src/recometrics.hpp:428-437), this uses every   */
+    int32_t reserved0;          /* listed GPU: contiguous user blocks, one host thread and stream set per GPU, item factors uploaded */
+                                /* once and copied GPU-to-GPU, result rows written at the shard offsets.  n_devices = 0: `device`    */
+                                /* alone, unless env RMB200_DEVICES ("all" or "0,1,2,...") names several.                            */
 } rmb200_extra_t;
 
 /* Drop-in for calc_metrics_float (src/recometrics_signatures.hpp:73-98).  Returns rmb200_status. */

@@ -35,6 +35,7 @@ class Timing(ctypes.Structure):
         ("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
         ("scoring_path", ctypes.c_int64), ("filter_fallback_batches", ctypes.c_int64),
         ("dominant_kernel_ms", ctypes.c_double), ("filter_retry_rows", ctypes.c_int64),
+        ("filter_fallback_users", ctypes.c_int64), ("filter_err_ratio_max", ctypes.c_double),
     ]
 
     def as_dict(self):
@@ -51,6 +52,8 @@ class Extra(ctypes.Structure):
         ("timing", ctypes.POINTER(Timing)),
         ("scoring_path", ctypes.c_int32), ("skip_row_copy", ctypes.c_int32),
         ("metric_means", ctypes.c_void_p), ("metric_counts", ctypes.c_void_p),
+        ("has_nan_bits", ctypes.c_int32), ("filter_stats", ctypes.c_int32), ("nan_bits", ctypes.c_uint64),
+        ("devices", ctypes.POINTER(ctypes.c_int32)), ("n_devices", ctypes.c_int32), ("reserved0", ctypes.c_int32),
     ]
 
 
@@ -167,7 +170,7 @@ def calc_metrics(dtype, A, lda, B, ldb, m, n, k, trp, tri, tep, tei, tev, k_metr
 
 def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, strict_min_pos_test=False,
                topk_items=None, topk_scores=None, pos_rank=None, status=None, timing=None, scoring_path=0,
-               metric_means=None, metric_counts=None, skip_row_copy=False):
+               metric_means=None, metric_counts=None, skip_row_copy=False, nan_bits=None, filter_stats=False, devices=None):
     ex = Extra()
     ex.struct_size = ctypes.sizeof(Extra)
     ex.device = int(device)
@@ -183,6 +186,14 @@ def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, stri
     ex.metric_means = _vp(metric_means)
     ex.metric_counts = _vp(metric_counts)
     ex.skip_row_copy = int(bool(skip_row_copy))
+    ex.has_nan_bits = int(nan_bits is not None)
+    ex.nan_bits = int(nan_bits or 0)
+    ex.filter_stats = int(bool(filter_stats))
+    if devices is not None and len(devices) > 0:
+        arr = (ctypes.c_int32 * len(devices))(*[int(d) for d in devices])
+        ex._devices_keepalive = arr            # (the struct only holds the pointer)
+        ex.devices = ctypes.cast(arr, ctypes.POINTER(ctypes.c_int32))
+        ex.n_devices = len(devices)
     if timing is not None:
         ex.timing = ctypes.pointer(timing)
     return ex

@@ -199,45 +199,29 @@ cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool 
 }
 
 template <int C>
-cudaError_t launch_filter_inst(const rmb::FilterParams& P, int n_user_tiles, bool pair, cudaStream_t st)
+cudaError_t launch_filter_inst(const rmb::FilterParams& P, int n_user_tiles, cudaStream_t st)
 {
     const size_t smem = rmb::filter_smem_bytes(P.KB, P.stages);
-    if (!pair) {
-        auto kern = rmb::filter_select_kernel<C, false>;
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        kern<<<n_user_tiles, rmb::F_THREADS, smem, st>>>(P);
-        return cudaGetLastError();
-    }
-    // CTA pairs (experimental, RMB200_PAIR=1): clusters of two CTAs, an even number of user tiles (a padding tile ranks no user)
-    auto kern = rmb::filter_select_kernel<C, true>;
+    auto kern = rmb::filter_select_kernel<C>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)((n_user_tiles + 1) & ~1), 1, 1);
-    cfg.blockDim = dim3((unsigned)rmb::F_THREADS, 1, 1);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, P);
+    kern<<<n_user_tiles, rmb::F_THREADS, smem, st>>>(P);
+    return cudaGetLastError();
 }
 
-inline cudaError_t launch_filter_select(const rmb::FilterParams& P, int C, int n_user_tiles, bool pair, cudaStream_t st)
+inline cudaError_t launch_filter_select(const rmb::FilterParams& P, int C, int n_user_tiles, cudaStream_t st)
 {
-    if (C == 256) return launch_filter_inst<256>(P, n_user_tiles, pair, st);
-    if (C == 512) return launch_filter_inst<512>(P, n_user_tiles, pair, st);
-    return launch_filter_inst<1024>(P, n_user_tiles, pair, st);
+    if (C == 256) return launch_filter_inst<256>(P, n_user_tiles, st);
+    if (C == 512) return launch_filter_inst<512>(P, n_user_tiles, st);
+    return launch_filter_inst<1024>(P, n_user_tiles, st);
 }
 
 struct NoiseArgs { int on; unsigned long long seed_user0; const int* trp; const int* tri; int n; };
 
 template <typename T, int C>
-cudaError_t launch_exact_topk_inst(const float* capx, T* cs, int* ci, int* cc, int nb, int user0, const T* At, int p_pad, int p,
-                                   const T* Brow, size_t ldb, const T* bias, int* uflags, int K, const NoiseArgs& nz, cudaStream_t st)
+cudaError_t launch_exact_topk_inst(const uint2* capx, T* cs, int* ci, int* cc, int nb, int user0, const T* At, int p_pad, int p,
+                                   const T* Brow, size_t ldb, const T* bias, int* uflags, int K, const NoiseArgs& nz,
+                                   const rmb::FilterErrStat& es, cudaStream_t st)
 {
     const int blocks = (nb + rmb::EXACT_WARPS - 1) / rmb::EXACT_WARPS;
     const size_t staging = (rmb::exact_topk_smem_bytes(p_pad, sizeof(T)) + 15) & ~size_t(15);
@@ -251,21 +235,22 @@ cudaError_t launch_exact_topk_inst(const float* capx, T* cs, int* ci, int* cc, i
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(staging + mt_bytes));
         if (e != cudaSuccess) return e;
         kern<<<blocks, rmb::EXACT_WARPS * 32, staging + mt_bytes, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K,
-                                                                        nz.on, nz.seed_user0, staging, nz.trp, nz.tri, nz.n);
+                                                                        nz.on, nz.seed_user0, staging, nz.trp, nz.tri, nz.n, es);
     } else {
         rmb::exact_topk_kernel<T, C, 0><<<blocks, rmb::EXACT_WARPS * 32, mt_bytes, st>>>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K,
-                                                                                             nz.on, nz.seed_user0, (size_t)0, nz.trp, nz.tri, nz.n);
+                                                                                             nz.on, nz.seed_user0, (size_t)0, nz.trp, nz.tri, nz.n, es);
     }
     return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t launch_exact_topk(const float* capx, T* cs, int* ci, int* cc, int C, int nb, int user0, const T* At, int p_pad, int p,
-                              const T* Brow, size_t ldb, const T* bias, int* uflags, int K, const NoiseArgs& nz, cudaStream_t st)
+cudaError_t launch_exact_topk(const uint2* capx, T* cs, int* ci, int* cc, int C, int nb, int user0, const T* At, int p_pad, int p,
+                              const T* Brow, size_t ldb, const T* bias, int* uflags, int K, const NoiseArgs& nz,
+                              const rmb::FilterErrStat& es, cudaStream_t st)
 {
-    if (C == 256) return launch_exact_topk_inst<T, 256>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, st);
-    if (C == 512) return launch_exact_topk_inst<T, 512>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, st);
-    return launch_exact_topk_inst<T, 1024>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, st);
+    if (C == 256) return launch_exact_topk_inst<T, 256>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, es, st);
+    if (C == 512) return launch_exact_topk_inst<T, 512>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, es, st);
+    return launch_exact_topk_inst<T, 1024>(capx, cs, ci, cc, nb, user0, At, p_pad, p, Brow, ldb, bias, uflags, K, nz, es, st);
 }
 
 // order the <= K survivors of every user (warp per user, bitonic network sized to K)
@@ -482,9 +467,11 @@ int run_call(const CallArgs<T>& a)
     for (int q = 0; q < 10; q++) any_out |= (a.out[q] != nullptr);
     const bool want_means = ex && (ex->metric_means || ex->metric_counts);
     const bool want_extras = ex && (ex->topk_items || ex->topk_scores || ex->pos_rank || ex->status);
+    const bool want_filter_stats = (ex && ex->filter_stats) || std::getenv("RMB200_FILTER_STATS") != nullptr;
     if (!any_out && !want_extras && !want_means) return RMB200_OK;
 
     int ub = 0, ue = a.m;
+    if (ex && ex->user_end < 0) return RMB200_OK;                        // explicit empty block
     if (ex && (ex->user_begin != 0 || ex->user_end != 0)) { ub = ex->user_begin; ue = ex->user_end; }
     if (ub < 0 || ue > a.m || ub > ue) { set_err("bad argument", "user range outside [0, m]"); return RMB200_ERR_BAD_ARG; }
     const int mr = ue - ub;   // users of this call ("shard"); device-side rows are shard-local
@@ -514,6 +501,14 @@ int run_call(const CallArgs<T>& a)
     if (mip < 2) mip = 2;
     int mpt = a.min_pos_test;
     if (!(ex && ex->strict_min_pos_test)) mpt = mpt < 1 ? mpt : 1;   // std::min(min_pos_test, 1): quirk Q1
+
+    // what a "NaN" written into the outputs looks like: a quiet NaN, or the caller's bit pattern (R: NA_REAL, hpp:75-80)
+    T nan_value = std::numeric_limits<T>::quiet_NaN();
+    if (ex && ex->has_nan_bits) {
+        if (sizeof(T) == 8) { const uint64_t b = ex->nan_bits; std::memcpy(&nan_value, &b, 8); }
+        else { const uint32_t b = (uint32_t)ex->nan_bits; std::memcpy(&nan_value, &b, 4); }
+        if (nan_value == nan_value) { set_err("bad argument", "rmb200_extra_t::nan_bits is not a NaN"); return RMB200_ERR_BAD_ARG; }
+    }
 
     const int K = a.K;
     // candidate buffer: K kept + 128 appended per tile + head-room between two cuts (the tensor-core filter keeps
@@ -547,8 +542,6 @@ int run_call(const CallArgs<T>& a)
     const bool tensor_ok = tensor_shape_ok && (!count_ranks || a.noise);
     if (path_req == 2 && !tensor_ok) { set_err("unsupported", "scoring_path=tensor needs no ROC/PR-AUC (rank counting), k <= ~400 and k_metrics <= 256"); return RMB200_ERR_UNSUPPORTED; }
     const bool use_tensor = tensor_ok && path_req != 1;
-    bool f_pair = false;               // experimental CTA-pair filter (filter_select_kernel<C, true>)
-    if (const char* env = std::getenv("RMB200_PAIR")) f_pair = use_tensor && std::atoi(env) != 0;
     const bool fma_counts_first = use_tensor && count_ranks;
     tm.scoring_path = use_tensor ? 2 : 1;
 #ifndef RMB_F_CMID
@@ -614,7 +607,7 @@ int run_call(const CallArgs<T>& a)
     const int* tep_d = d_tep.as<int>();
 
     // ---- item factors: row-major staging copy, then the operand image of the chosen path ----
-    DevBuf d_Bt, d_bias, d_Brow, d_Bb, d_maxbn;
+    DevBuf d_Bt, d_bias, d_Brow, d_Bb, d_maxbn, d_chunkn;
     const T* Bsrc = nullptr; size_t Bld = 0;
     if (!on_dev) {
         CK(d_Brow.alloc((size_t)a.n * a.k * sizeof(T)));
@@ -667,14 +660,17 @@ int run_call(const CallArgs<T>& a)
     const int n_pad128 = round_up(a.n, 128);
     if (use_tensor) {
         CK(d_Bb.alloc((size_t)n_pad128 * KB * sizeof(__half)));
-        CK(d_maxbn.alloc(sizeof(unsigned)));
+        CK(d_maxbn.alloc(4 * sizeof(unsigned)));                    // [0] max_j ||b_j||, [1] largest observed error / bound ratio (statistic)
+        CK(d_chunkn.alloc((size_t)(n_pad128 / 32) * sizeof(float)));
         pt.start();
-        CK(cudaMemsetAsync(d_maxbn.p, 0, sizeof(unsigned), st));
+        CK(cudaMemsetAsync(d_maxbn.p, 0, 4 * sizeof(unsigned), st));
+        CK(cudaMemsetAsync(d_chunkn.p, 0, (size_t)(n_pad128 / 32) * sizeof(float), st));
         const long long total = (long long)n_pad128 * (KB / 8);
-        row_norm_kernel<T><<<(a.n + 7) / 8, 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0, nullptr, d_maxbn.as<unsigned>());
+        row_norm_kernel<T><<<(a.n + NORM_ROWS_PER_BLOCK - 1) / NORM_ROWS_PER_BLOCK, 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0, nullptr,
+                                                                                              d_maxbn.as<unsigned>(), d_chunkn.as<float>());
         CK(cudaGetLastError());
         pack_f16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Bsrc, Bld, a.n, a.k, bias_d, 0, nullptr, d_maxbn.as<unsigned>(),
-                                                                            d_Bb.as<__half>(), n_pad128, KB, f_pair ? 1 : 0);
+                                                                            d_Bb.as<__half>(), n_pad128, KB);
         CK(cudaGetLastError());
         tm.kernel_launches += 2;
         pt.stop(tm.prep_ms);
@@ -731,7 +727,7 @@ int run_call(const CallArgs<T>& a)
 
     DevBuf d_At, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
     CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
-    DevBuf d_capx, d_overflow;
+    DevBuf d_capx, d_overflow, d_fb_list, d_At_fb;
     // sampled threshold guess of the filter (filter_select.cuh, pass 0): every stride-th item tile, about 7/K of the
     // catalogue (1/16 .. 1/8); the guess is the r-th best of the sample with r = the smallest rank for which
     // P(Poisson(K * sample / n) >= r) <= 1e-6, i.e. fewer than K items of the whole catalogue reach it about once
@@ -757,10 +753,11 @@ int run_call(const CallArgs<T>& a)
         }
     }
     if (use_tensor) {
-        CK(d_Ab.alloc((size_t)(UB + BM) * KB * sizeof(__half)));       // (+ one tile: the pair filter pads to an even number of user tiles)
+        CK(d_Ab.alloc((size_t)UB * KB * sizeof(__half)));
         CK(d_anorm.alloc((size_t)UB * sizeof(float)));
-        CK(d_capx.alloc((size_t)UB * C * sizeof(float)));
-        CK(d_overflow.alloc(8 * sizeof(int)));     // [0] users whose slack band overflowed, [1] users that took the retry pass
+        CK(d_capx.alloc((size_t)UB * C * sizeof(uint2)));
+        CK(d_overflow.alloc(8 * sizeof(int)));     // [0] users handed back to the FMA path, [1] users that took the retry pass, [6] length of the hand-back list
+        CK(d_fb_list.alloc((size_t)UB * sizeof(int)));
     }
     // upload of users [b0, b0 + UB) into staging buffer `slot`, on the prefetch stream
     auto upload_users = [&](int b0, int slot) -> int {
@@ -848,26 +845,29 @@ int run_call(const CallArgs<T>& a)
         pt.stop(tm.prep_ms);
 
         bool pk_pending = false;
-        auto run_fma_batch = [&]() -> int {
-            // fused score / exclude / select (/ rank counting) on the FMA pipe
+        // fused score / exclude / select (/ rank counting) on the FMA pipe: the whole batch, or (umap) the listed users only
+        auto run_fma = [&](const T* At_ptr, int n_rows, const int* umap, bool with_counts, bool timed) -> int {
             ScoreSelectParams<T> sp;
-            sp.At = d_At.as<T>(); sp.Bt = d_Bt.as<T>(); sp.bias = bias_d;
-            sp.p_pad = p_pad; sp.n = a.n; sp.mb = nb; sp.user0 = b0;
+            sp.At = At_ptr; sp.Bt = d_Bt.as<T>(); sp.bias = bias_d;
+            sp.p_pad = p_pad; sp.n = a.n; sp.mb = n_rows; sp.user0 = b0;
             sp.trp = trp_d; sp.tri = tri_d; sp.tep = tep_d; sp.ustatus = d_status.as<int>();
             sp.cand_score = d_cs.as<T>(); sp.cand_item = d_ci.as<int>(); sp.cand_count = d_cc.as<int>();
             sp.uflags = d_flags.as<int>(); sp.K = K;
-            sp.pos_sorted = count_ranks ? d_pos_sorted.as<T>() : nullptr;
-            sp.auc_cnt = count_ranks ? d_auc.as<unsigned int>() : nullptr;
-            sp.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
-            cudaEventRecord(pk.a, st);
-            CK(launch_score_select<T>(sp, C, count_ranks, nb_pad / BM, st));
-            cudaEventRecord(pk.b, st);
-            { int rc = prefetch_next_users(); if (rc) return rc; }
-            pk_pending = true;
+            sp.pos_sorted = with_counts ? d_pos_sorted.as<T>() : nullptr;
+            sp.auc_cnt = with_counts ? d_auc.as<unsigned int>() : nullptr;
+            sp.umin = with_counts ? d_umin.as<unsigned long long>() : nullptr;
+            sp.umap = umap;
+            if (timed) cudaEventRecord(pk.a, st);
+            CK(launch_score_select<T>(sp, C, with_counts, round_up(n_rows, BM) / BM, st));
+            if (timed) { cudaEventRecord(pk.b, st); pk_pending = true; }
             tm.kernel_launches++;
             return RMB200_OK;
         };
-        bool batch_on_tensor = use_tensor;
+        auto run_fma_batch = [&]() -> int {
+            int rc = run_fma(d_At.as<T>(), nb, nullptr, count_ranks, true);
+            if (rc) return rc;
+            return prefetch_next_users();
+        };
         if (fma_counts_first) {            // rank counts (and the smallest candidate score) from the FMA tiles; its top-K is replaced below
             pt.start();
             int rc = run_fma_batch();
@@ -878,67 +878,76 @@ int run_call(const CallArgs<T>& a)
             // norms + fp16 operand image of the batch's users, then the tensor-core filter and the exact re-scoring
             pt.start();
             const long long total = (long long)nb_pad * (KB / 8);
-            row_norm_kernel<T><<<(nb + 7) / 8, 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0, d_anorm.as<float>(), nullptr);
+            row_norm_kernel<T><<<(nb + NORM_ROWS_PER_BLOCK - 1) / NORM_ROWS_PER_BLOCK, 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
+                                                                                               d_anorm.as<float>(), nullptr, nullptr);
             CK(cudaGetLastError());
             pack_f16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
                                                                                 d_anorm.as<float>(), nullptr, d_Ab.as<__half>(), nb_pad, KB);
             CK(cudaGetLastError());
-            { int rc = staged_rows_consumed(); if (rc) return rc; }
             CK(cudaMemsetAsync(d_overflow.p, 0, 8 * sizeof(int), st));
             tm.kernel_launches += 2;
             pt.stop(tm.prep_ms);
             pt.start();
+            const FilterErrCoef ec = filter_err_coefs(KB);
             FilterParams fp;
-            fp.Ab = d_Ab.as<__half>(); fp.Bb = d_Bb.as<__half>(); fp.KB = KB; fp.err_coef = filter_err_coef(KB); fp.stages = f_stages;
+            fp.Ab = d_Ab.as<__half>(); fp.Bb = d_Bb.as<__half>(); fp.KB = KB; fp.stages = f_stages;
+            fp.c_rel = ec.c_rel; fp.c_abs = ec.c_abs; fp.c_const = ec.c_const;
             fp.n = a.n; fp.mb = nb; fp.user0 = b0;
-            fp.anorm = d_anorm.as<float>(); fp.maxbn = d_maxbn.as<unsigned>();
+            fp.anorm = d_anorm.as<float>(); fp.maxbn = d_maxbn.as<unsigned>(); fp.chunk_norm = d_chunkn.as<float>();
             fp.trp = trp_d; fp.tri = tri_d; fp.ustatus = d_status.as<int>();
-            fp.cand_approx = d_capx.as<float>(); fp.cand_item = d_ci.as<int>(); fp.cand_count = d_cc.as<int>();
+            fp.cand = d_capx.as<uint2>(); fp.cand_count = d_cc.as<int>();
             fp.overflow = d_overflow.as<int>(); fp.uflags = d_flags.as<int>(); fp.K = K;
             fp.sample_tiles = f_sample_tiles; fp.sample_stride = f_sample_stride; fp.sample_rank = f_sample_rank;
             fp.retries = d_overflow.as<int>() + 1;
             fp.noise_band = a.noise ? 2.02e-12f : 0.f;
             fp.dbg = 0; if (const char* env = std::getenv("RMB200_DBG")) fp.dbg = std::atoi(env);
             cudaEventRecord(pk.a, st);
-            CK(launch_filter_select(fp, C, nb_pad / BM, f_pair, st));
+            CK(launch_filter_select(fp, C, nb_pad / BM, st));
             cudaEventRecord(pk.b, st);
-            { int rc = prefetch_next_users(); if (rc) return rc; }
             pk_pending = true;
+            tm.kernel_launches++;
+            // the exact stage reads the staged user factors (through d_At) and the filter is queued: the next batch's rows can go up
+            { int rc = staged_rows_consumed(); if (rc) return rc; }
+            { int rc = prefetch_next_users(); if (rc) return rc; }
+            NoiseArgs nz;
+            nz.on = a.noise; nz.seed_user0 = (unsigned long long)a.seed + (unsigned long long)(ub + b0); nz.trp = trp_d; nz.tri = tri_d; nz.n = a.n;
+            FilterErrStat es;
+            es.anorm = d_anorm.as<float>(); es.maxbn = d_maxbn.as<unsigned>(); es.chunk_norm = d_chunkn.as<float>();
+            es.c_rel = ec.c_rel; es.c_abs = ec.c_abs; es.c_const = ec.c_const;
+            es.max_ratio_bits = want_filter_stats ? d_maxbn.as<unsigned>() + 1 : nullptr;
+            CK(launch_exact_topk<T>(d_capx.as<uint2>(), d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, b0, d_At.as<T>(), p_pad, a.k,
+                                    Bsrc, Bld, bias_d, d_flags.as<int>(), K, nz, es, st));
             tm.kernel_launches++;
             int over_retry[8] = {0, 0, 0, 0, 0, 0, 0, 0};
             CK(cudaMemcpyAsync(over_retry, d_overflow.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
 #if RMB_F_STATS
-            std::fprintf(stderr, "[rmb200 stats] users %d: appends/user %.1f cuts/user %.2f slow-path entries/user %.1f cursor moves/user %.1f retries %d (sample tiles %d stride %d rank %d)\n",
+            std::fprintf(stderr, "[rmb200 stats] users %d: appends/user %.1f cuts/user %.2f slow-path entries/user %.1f cursor moves/user %.1f retries %d handed back %d (sample tiles %d stride %d rank %d)\n",
                          nb, over_retry[2] / (double)nb, over_retry[3] / (double)nb, over_retry[4] / (double)nb, over_retry[5] / (double)nb,
-                         over_retry[1], f_sample_tiles, f_sample_stride, f_sample_rank);
+                         over_retry[1], over_retry[0], f_sample_tiles, f_sample_stride, f_sample_rank);
 #endif
             const int n_over = over_retry[0];
             tm.filter_retry_rows += over_retry[1];
             if (n_over > 0) {
-                // some user's slack band did not fit its candidate buffer (near-constant scores): the whole batch
-                // goes through the FMA path instead -- slower, same results
-                batch_on_tensor = false;
+                // some users' kept band did not fit their candidate buffer (near-constant scores) or their factors cannot be scaled
+                // into fp16 range: THOSE users are re-run on the FMA tiles (same results), everybody else keeps the filter's result
                 tm.filter_fallback_batches++;
+                tm.filter_fallback_users += n_over;
                 pt.stop(tm.score_select_ms);
                 int rc = pack_Bt();
                 if (rc) return rc;
                 pt.start();
-                if (fma_counts_first) {
-                    // the rank counters of this batch's users already hold the first FMA pass: clear them before the re-run
-                    int te0 = 0, te1 = 0;
-                    CK(cudaMemcpy(&te0, tep_d + b0, sizeof(int), cudaMemcpyDeviceToHost));
-                    CK(cudaMemcpy(&te1, tep_d + b0 + nb, sizeof(int), cudaMemcpyDeviceToHost));
-                    if (te1 > te0) CK(cudaMemsetAsync(d_auc.as<unsigned int>() + te0, 0, (size_t)(te1 - te0) * sizeof(unsigned int), st));
-                }
-                rc = run_fma_batch();
+                const int n_over_pad = round_up(n_over, BM);
+                CK(d_At_fb.alloc((size_t)p_pad * n_over_pad * sizeof(T)));
+                collect_flagged_kernel<<<1, 1024, 0, st>>>(d_cc.as<int>(), nb, d_fb_list.as<int>(), d_overflow.as<int>() + 6);
+                CK(cudaGetLastError());
+                dim3 grid(n_over_pad / 32, (p_pad + 31) / 32), block(32, 8);
+                pack_tiles_gather_kernel<T, BM><<<grid, block, 0, st>>>(Asrc, Ald, d_fb_list.as<int>(), n_over, a.k, d_At_fb.as<T>(), n_over_pad, p_pad);
+                CK(cudaGetLastError());
+                tm.kernel_launches += 2;
+                { int rc2 = staged_rows_consumed(); if (rc2) return rc2; }      // (the gather read the staged rows once more)
+                rc = run_fma(d_At_fb.as<T>(), n_over, d_fb_list.as<int>(), false, false);
                 if (rc) return rc;
-            } else {
-                NoiseArgs nz;
-                nz.on = a.noise; nz.seed_user0 = (unsigned long long)a.seed + (unsigned long long)(ub + b0); nz.trp = trp_d; nz.tri = tri_d; nz.n = a.n;
-                CK(launch_exact_topk<T>(d_capx.as<float>(), d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, b0, d_At.as<T>(), p_pad, a.k,
-                                        Bsrc, Bld, bias_d, d_flags.as<int>(), K, nz, st));
-                tm.kernel_launches++;
             }
         } else {
             pt.start();
@@ -947,7 +956,7 @@ int run_call(const CallArgs<T>& a)
         }
         CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
         tm.kernel_launches++;
-        if (a.noise && !batch_on_tensor && !count_ranks) {
+        if (a.noise && !use_tensor && !count_ranks) {
             all_equal_check_kernel<T><<<nb, 128, 0, st>>>(d_cs.as<T>(), d_cc.as<int>(), C, b0, K, a.n, trp_d, tri_d, d_status.as<int>(),
                                                            d_At.as<T>(), d_Bt.as<T>(), bias_d, p_pad, d_flags.as<int>());
             CK(cudaGetLastError());
@@ -967,7 +976,7 @@ int run_call(const CallArgs<T>& a)
             mp.cand_score = d_cs.as<T>(); mp.cand_item = d_ci.as<int>(); mp.cand_count = d_cc.as<int>();
             mp.auc_cnt = d_auc.as<unsigned int>(); mp.umin = d_umin.as<unsigned long long>();
             mp.pos_perm = d_pos_perm.as<int>(); mp.log2tab = d_log2.as<double>();
-            mp.nan_value = std::numeric_limits<T>::quiet_NaN();
+            mp.nan_value = nan_value;
             T* outs[10];
             for (int q = 0; q < 10; q++) {
                 const size_t stride = q < 8 ? rs : 1;
@@ -1039,6 +1048,12 @@ int run_call(const CallArgs<T>& a)
             if (ex->metric_means) { CK(cudaMemcpyAsync(ex->metric_means, means_d, cells * sizeof(double), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)(cells * sizeof(double)); }
             if (ex->metric_counts) { CK(cudaMemcpyAsync(ex->metric_counts, counts_d, cells * sizeof(long long), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)(cells * sizeof(long long)); }
         }
+    }
+    if (use_tensor && want_filter_stats) {
+        float ratio = 0.f;
+        CK(cudaMemcpyAsync(&ratio, d_maxbn.as<unsigned>() + 1, sizeof(float), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        tm.filter_err_ratio_max = (double)ratio;
     }
     CK(cudaStreamSynchronize(st));
 

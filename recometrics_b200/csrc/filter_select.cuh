@@ -16,22 +16,26 @@
 //      of the row's candidate buffer with the counter in a register, its own cursor into the row's train
 //      items -- so the four warps never wait for each other inside a tile: while one of them appends
 //      candidates, the others run ahead (up to the four accumulator buffers).  They meet at a named
-//      barrier only every 1..16 tiles (the distance adapts to the append rate) to cut the row's four
+//      barrier only every 1..64 tiles (the distance adapts to the append rate) to cut the row's four
 //      regions back together and raise the row's shared threshold.
-//      With m_u = c * ||a_u|| * max_j ||b_j|| >= |approx - exact| (fp16 rounding of both operands,
-//      Cauchy-Schwarz; filter_err_coef) and tau~ = the K-th best APPROXIMATE candidate score seen so far, every
-//      member of the exact top K satisfies approx >= tau~ - 2 m_u (the K best approximate scores have
-//      exact scores >= tau~ - m_u, so the exact K-th best is >= tau~ - m_u, and a member's approximate
-//      score is within m_u of its exact one).  The kernel therefore keeps, per user, all candidates with
-//      approx >= tau~ - 2 m_u: train items and padding columns are dropped when appended, the regions are
-//      cut back with a histogram select on the approximate keys.  >= 99.9 % of the catalogue
-//      is rejected with one compare.
+//
+//      INTERVALS.  Every approximate score carries its own error bound
+//          e_uj = c_rel ||a_u|| ||b_j|| + c_abs ||a_u|| + c_const        (scaled units, filter_err_coefs)
+//      with ||b_j|| replaced by the largest item norm of j's 32-item chunk (prep.cuh row_norm_kernel), so
+//      exact_uj lies in [lb, ub] = [approx - e, approx + e].  With tau' = the K-th best LOWER bound seen so far
+//      the exact K-th best score is >= tau', and an item can only belong to the exact top K if its UPPER
+//      bound reaches tau'.  The kernel keeps, per user, exactly the candidates with ub >= tau': one item with a
+//      huge norm widens only its own interval, never the band of the whole row (a single global max_j ||b_j||
+//      did).  Train items and padding columns are dropped when appended; >= 99.9 % of the catalogue is
+//      rejected with one compare per 32 scores.
 //   2. EXACT (exact_topk_kernel) -- one warp per user re-scores the few hundred survivors exactly
 //      (sequential fma chain over the original fp32 / fp64 factors: the same chain, hence bit-identical
 //      scores, as score_select_kernel / score_entries_kernel) and keeps the best K.  The final top-K,
 //      their order and their scores are exactly those of the FP32 (FP64) FMA path; the tensor cores only
-//      decide what is worth looking at.  A user whose slack band does not fit the buffer is flagged and
-//      the host re-runs that batch on the FMA path.
+//      decide what is worth looking at.  A user whose kept band does not fit the buffer (near-constant scores),
+//      or whose factors cannot be scaled into fp16 range, is flagged and the host re-runs THAT USER on the FMA
+//      path (api.cu).  A user whose factors are all zero (every score equal: NaN row, hpp:541-548) is settled
+//      without scoring.
 //
 // Shared-memory operand layout (no swizzle, K-major "interleaved"): [k/8][row][8 halves] -- a core matrix
 // is 8 rows x 16 bytes contiguous; descriptor LBO = 128 rows * 16 B (next k chunk), SBO = 128 B (next 8
@@ -69,6 +73,12 @@ constexpr int F_CUT_MARGIN = RMB_F_CUT_MARGIN;
 #endif
 constexpr int F_MAX_MEET = RMB_F_MAX_MEET;
 
+#ifndef RMB_F_FAST_APPEND
+#define RMB_F_FAST_APPEND 1              // predicated in-line appends on the common slow path (0: always the out-of-line group function)
+#endif
+#ifndef RMB_F_NO_CN
+#define RMB_F_NO_CN 0
+#endif
 #ifndef RMB_F_DBG
 #define RMB_F_DBG 0                      // developer build: honour FilterParams::dbg (env RMB200_DBG) inside the tile loop
 #endif
@@ -85,18 +95,18 @@ struct FilterParams {
     const __half* __restrict__ Ab;          // [user tiles][KB/8][128][8]  fp16 user factors (+1.0 bias column), each row scaled by pow2_scale_for(||a_u||)
     const __half* __restrict__ Bb;          // [item tiles][KB/8][128][8]  fp16 item factors (+bias column), all scaled by pow2_scale_for(max_j ||b_j||)
     int KB;                                 // fp16 factors per row, multiple of 16
-    float err_coef;                         // c: |approx - exact| <= c ||a|| max||b|| (host: filter_err_coef)
+    float c_rel, c_abs, c_const;            // error bound of an approximate score (host: filter_err_coefs)
     float noise_band;                       // break_ties_with_noise: how far the noise can move two scores apart (2e-12), else 0
     int stages;                             // depth of the B ring
     int n, mb, user0;
-    const float* __restrict__ anorm;        // [mb] ||a_u|| (with the 1.0 bias component), rounded up
+    const float* __restrict__ anorm;        // [mb] ||a_u|| (with the 1.0 bias component), rounded up; 0 = all-zero row
     const unsigned* __restrict__ maxbn;     // float bits of max_j ||b_j|| (with the bias component)
+    const float* __restrict__ chunk_norm;   // [ceil(n/128)*4] max ||b_j|| over the 32 items of a chunk (0 for padding chunks)
     const int* __restrict__ trp;
     const int* __restrict__ tri;
     const int* __restrict__ ustatus;
-    float* cand_approx;                     // [mb_pad][C] approximate scores of the kept candidates
-    int* cand_item;                         // [mb_pad][C]
-    int* cand_count;                        // [mb_pad] kept candidates; -1 = slack band overflowed the buffer
+    uint2* cand;                            // [mb_pad][C] kept candidates: x = LOWER bound of the score (approximate score - error bound, float bits), y = item id
+    int* cand_count;                        // [mb_pad] kept candidates; -1 = the user goes to the FMA path (band overflow / unscalable factors)
     int* overflow;                          // number of users flagged -1
     int* uflags;                            // [m] bit0: a candidate score was NaN
     int K;
@@ -106,31 +116,52 @@ struct FilterParams {
 };
 
 struct FilterRowState {      // per user row of the CTA, shared by the four epilogue warps of its TMEM lane quarter
-    float thr[BM], slack[BM], guess[BM];
+    float tau[BM];                   // K-th best lower bound so far (+inf: the row is closed, -inf: nothing known yet)
+    float ca[BM], efl[BM];           // error bound of a score of this row: e = ca * chunk_norm + efl
+    float guess[BM];
     int cnt[BM];                     // candidates left contiguous at the head of the row's buffer when a pass ends
     int cnt4[4][BM];                 // candidates in each warp's region of the buffer, published at the meeting points
     int trig[BM];                    // total above which the regions are cut back together
-    int flags[BM];                   // 1 = NaN candidate score, 2 = buffer overflow (slack band / burst), 4 = guess failed (retry pass)
+    int flags[BM];                   // 1 = NaN candidate score, 2 = buffer overflow (kept band / burst), 4 = guess failed (retry pass),
+                                     // 8 = factors outside the range the fp16 image can be scaled into (FMA path)
     int nxt2_train[4][BM];           // per warp: the train item id after the cursor's next one (prefetched with cp.async)
+    int tcur[4][BM];                 // per warp: position of the cursor in the train CSR (only touched in tiles holding train items)
+    int tend[BM];                    // end of the row's train items in the CSR
+    int tot_prev[4][BM];             // per warp: row total after the previous meeting (the same value in the quarter's four warps)
+    int interval[F_EPI_WARPS];       // per warp: tiles between its last two meetings
     int retry;                       // some row of the CTA needs the retry pass
     int stat[4];                     // RMB_F_STATS: appends, cuts, slow-path entries (8-column groups), cursor moves
     unsigned hist[F_EPI_WARPS][32];  // bucket counters of cut_regions, one set per epilogue warp
 };
 
 
-// Error bound of the filter's approximate scores, as a multiple of ||a_u|| max_j ||b_j||:
-//   fp16 rounding of both operands (scaled so that |x| <= 1; relative 2^-11 each, absolute 2^-25 below 6e-5):
-//       sum_k |a_k b_k| (2^-10 + 2^-22) + 2^-25 sqrt(k) (||a|| + ||b||)   <=  (2^-10 (1 + 2^-10) + 4 sqrt(k) 2^-24) ||a|| ||b||
-//       (Cauchy-Schwarz; the scaled norms are >= 0.5, hence the factor 4 on the absolute term)
-//   fp32 accumulation inside the tensor core plus the rounding of the exact fp32 fma chain it is compared with: k 2^-22
-// and 1 % on top.
-inline float filter_err_coef(int KB)
+// Error bound of the filter's approximate scores, in the scaled units of the operand images (a' = a * 2^-ea with
+// ||a'|| in [0.5, 1), b' = b * 2^-eb with max_j ||b'_j|| in [0.5, 1), every element at most 1 in magnitude):
+//   fp16 rounding of an element x (|x| <= 1): x (1 + d) + h with |d| <= 2^-11 (normal range) and |h| <= 2^-25 (below 2^-14)
+//       | sum_k a^_k b^_k - sum_k a'_k b'_k |  <=  (2^-10 + 2^-22) sum |a' b'|  +  2^-25 (1 + 2^-11) (sum |a'_k| + sum |b'_k|)  +  k 2^-50
+//                                              <=  (2^-10 + 2^-22) ||a'|| ||b'_j||  +  2^-25 (1 + 2^-11) sqrt(k) (||a'|| + ||b'_j||)  +  k 2^-50
+//   fp32 accumulation inside the tensor core plus the rounding of the exact fma chain it is compared with: k 2^-22 ||a'|| ||b'_j||
+// With ||a'|| >= 0.5 the ||b'_j|| part of the second term is at most 2 x 2^-25 (1 + 2^-11) sqrt(k) ||a'|| ||b'_j||, so
+//       e_uj = c_rel ||a'|| ||b'_j|| + c_abs ||a'|| + c_const        (and 1 % on top of every coefficient).
+// The absolute terms matter for items whose norm is tiny next to the largest one: their fp16 image sits in the denormal
+// range and its error no longer shrinks with ||b'_j||.
+struct FilterErrCoef { float c_rel, c_abs, c_const; };
+inline FilterErrCoef filter_err_coefs(int KB)
 {
-    const double c = std::ldexp(1.0, -10) * (1.0 + std::ldexp(1.0, -10)) + 4.0 * std::sqrt((double)KB) * std::ldexp(1.0, -24) + KB * std::ldexp(1.0, -22);
-    return (float)(1.01 * c);
+    const double c2 = std::ldexp(1.0, -25) * (1.0 + std::ldexp(1.0, -11)) * std::sqrt((double)KB);
+    const double c1 = std::ldexp(1.0, -10) * (1.0 + std::ldexp(1.0, -10)) + KB * std::ldexp(1.0, -22);
+    FilterErrCoef c;
+    c.c_rel = (float)(1.01 * (c1 + 2.0 * c2));
+    c.c_abs = (float)(1.01 * c2);
+    c.c_const = (float)(1.01 * KB * std::ldexp(1.0, -50));
+    return c;
 }
+// a norm the power-of-two scaling of prep.cuh can bring into [0.5, 1) (pow2_scale_for clamps its exponent at +-100)
+__device__ __forceinline__ bool filter_scalable(const float nrm) { return nrm >= 1.6e-30f && nrm <= 6.0e29f; }
 
-inline size_t filter_smem_fixed_bytes() { return 256 + sizeof(FilterRowState); }      // barriers + row state
+// dynamic shared memory: [row state, padded][barriers, 256 B][A tile][B ring]
+constexpr size_t F_RS_BYTES = (sizeof(FilterRowState) + 1023) & ~size_t(1023);
+inline size_t filter_smem_fixed_bytes() { return 256 + F_RS_BYTES; }
 inline size_t filter_smem_bytes(int KB, int stages)
 {
     return (size_t)(1 + stages) * KB * 128 * 2 + filter_smem_fixed_bytes();
@@ -179,83 +210,49 @@ __device__ __forceinline__ void tmem_ld32(const unsigned taddr, unsigned (&r)[32
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ------------------------------------------------------------------ CTA pair (tcgen05 cta_group::2), see filter_select_kernel<C, true>
-__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// shared-memory address of the same variable in CTA `rank` of the cluster
-__device__ __forceinline__ unsigned mapa_shared(const unsigned saddr, const unsigned rank)
-{
-    unsigned r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(const unsigned cluster_addr)
-{
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-__device__ __forceinline__ unsigned ld_shared_cluster_u32(const unsigned cluster_addr)
-{
-    unsigned v;
-    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(cluster_addr) : "memory");
-    return v;
-}
-// descriptor of a 64-row half tile: LBO = 64 rows * 16 B = 1024 (>>4 = 64)
-__device__ __forceinline__ uint64_t umma_desc_half(const unsigned saddr)
-{
-    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)64 << 16) | ((uint64_t)8 << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void umma_f16_pair(const unsigned tmem_d, const uint64_t adesc, const uint64_t bdesc,
-                                               const unsigned idesc, const unsigned accumulate)
-{
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-// completion of the MMAs issued so far -> the barrier at this offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(const unsigned bar)
-{
-    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"((unsigned short)3) : "memory");
-}
+// error bound of an approximate score of a row (ca, efl) against an item of a chunk with largest norm cn, rounded up
+__device__ __forceinline__ float filter_err(const float ca, const float cn, const float efl) { return __fmaf_ru(ca, cn, efl); }
 
-// One warp: cut a row's candidates back to those that can still belong to the exact top K: approximate score >=
-// (K-th best approximate score) - slack.  The row's buffer is four regions of C/4 entries (one per epilogue warp of the
-// quarter), region s holding cnt4[s] entries; all of them are read into registers first, so the survivors can be written
-// back in place: CONTIG ? packed at the head of the buffer : dealt round-robin over the four regions.
-// The K-th best key is found by ROUNDS rounds of a 32-bucket histogram (shared-memory counters, one bucket per lane,
-// suffix sums by shuffles) that narrow a window [lo, lo + span] of the key range around it.  The window's lower edge
-// always satisfies #(key >= lo) >= K, so it is a valid (slightly low: window width = key range / 32^ROUNDS) stand-in
-// for the K-th best approximate score; ROUNDS = 7 exhausts 32-bit keys and makes it exact.
-// K <= total entries is required.  Returns the number kept; *tau_out = the (stand-in for the) K-th best score.
+// One warp: cut a row's candidates back to those that can still belong to the exact top K.  Every candidate's exact
+// score lies in [lb, ub] = [approx - e, approx + e] (e from its item's chunk norm).  tau' = the K-th best lower bound;
+// kept: KEEP_LB ? lb >= tau' (sample pass: the K best lower bounds themselves) : ub >= tau' (whatever can still reach
+// the exact top K).  The row's buffer is four regions of C/4 entries (one per epilogue warp of the quarter), region s
+// holding cnt4[s] entries; all of them are read into registers first, so the survivors can be written back in place:
+// CONTIG ? packed at the head of the buffer : dealt round-robin over the four regions.
+// tau' is found by ROUNDS rounds of a 32-bucket histogram (shared-memory counters, one bucket per lane, suffix sums by
+// shuffles) that narrow a window [lo, lo + span] of the key range around it.  The window's lower edge always satisfies
+// #(lb key >= lo) >= K, so it is a valid (slightly low: window width = key range / 32^ROUNDS) stand-in for tau';
+// ROUNDS = 7 exhausts 32-bit keys and makes it exact.  K <= total entries is required.
+// Returns the number kept; *tau_out = (the stand-in for) tau'.
 #ifndef RMB_F_HIST_ROUNDS
 #define RMB_F_HIST_ROUNDS 2
 #endif
 template <int C, int ROUNDS, bool CONTIG>
-__device__ __noinline__ int cut_regions(float* cs, int* ci, const int c0, const int c1, const int c2, const int c3, const int K,
-                                        const float slack, const int lane, unsigned* hist, float* tau_out)
+__device__ __noinline__ int cut_regions(uint2* cd, const int c0, const int c1, const int c2, const int c3, const int K,
+                                        const float ca, const float efl, const float* __restrict__ chunk_norm, const bool keep_lb,
+                                        const int lane, unsigned* hist, float* tau_out)
 {
     constexpr int E = C / 32, RC = C / 4, EPR = E / 4;      // entries per lane, region capacity, per-lane entries per region
-    unsigned key[E];
-    int it[E];
+    // (register budget: this function is called from the tile loop.  Only the lower-bound keys live through the rounds;
+    //  the entries are read again for the write-back, and only those below the cut need their error bound.)
+    const int ns = (max(max(c0, c1), max(c2, c3)) + 31) >> 5;      // occupied 32-entry slots per region (warp-uniform): the rest is skipped
+    unsigned lbk[E];                                        // lower-bound key, 0 = empty slot (the key of -inf is 0x007fffff)
     unsigned kmax = 0u, kmin = 0xffffffffu;
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        const int region = e / EPR, pos = (e % EPR) * 32 + lane;
-        const int cr = region == 0 ? c0 : (region == 1 ? c1 : (region == 2 ? c2 : c3));
-        const bool v = pos < cr;
-        const int idx = region * RC + pos;
-        key[e] = v ? NumTraits<float>::key(cs[idx]) : 0u;      // 0 sorts below every score
-        it[e] = v ? ci[idx] : INT_MAX;
-        if (v) { kmax = max(kmax, key[e]); kmin = min(kmin, key[e]); }
+        lbk[e] = 0u;
+        if ((e % EPR) < ns) {
+            const int region = e / EPR, pos = (e % EPR) * 32 + lane;
+            const int cr = region == 0 ? c0 : (region == 1 ? c1 : (region == 2 ? c2 : c3));
+            if (pos < cr) {
+                lbk[e] = NumTraits<float>::key(__uint_as_float(cd[region * RC + pos].x));
+                kmax = max(kmax, lbk[e]); kmin = min(kmin, lbk[e]);
+            }
+        }
     }
     kmax = __reduce_max_sync(FULL, kmax);
     kmin = __reduce_min_sync(FULL, kmin);
-    unsigned lo = kmin, span = kmax - kmin;     // window [lo, lo + span]; the need-th largest key inside it is wanted
+    unsigned lo = kmin, span = kmax - kmin;     // window [lo, lo + span]; the need-th largest lb key inside it is wanted
     int need = K;
 #pragma unroll 1
     for (int round = 0; round < ROUNDS; round++) {
@@ -264,8 +261,10 @@ __device__ __noinline__ int cut_regions(float* cs, int* ci, const int c0, const 
         __syncwarp();
 #pragma unroll
         for (int e = 0; e < E; e++) {
-            const unsigned d = key[e] - lo;
-            if (key[e] >= lo && d <= span) atomicAdd(&hist[d >> sh], 1u);
+            if ((e % EPR) < ns) {
+                const unsigned d = lbk[e] - lo;
+                if (lbk[e] != 0u && lbk[e] >= lo && d <= span) atomicAdd(&hist[d >> sh], 1u);
+            }
         }
         __syncwarp();
         unsigned suf = hist[lane];                             // -> number of window keys in buckets >= lane
@@ -284,39 +283,59 @@ __device__ __noinline__ int cut_regions(float* cs, int* ci, const int c0, const 
         if (sh == 0) break;
     }
     const float tau = NumTraits<float>::from_orderable((u64)lo);
-    const float cutf = __fsub_rd(tau, slack);                   // NaN (tau or slack not finite): keep everything
-    const unsigned cut = (cutf == cutf) ? NumTraits<float>::key(cutf) : 1u;
+    const unsigned cut = (tau == tau) ? lo : 1u;               // NaN bound (K NaN scores): keep everything
+    // write-back: an entry whose lower bound reaches the cut stays; one below it stays iff its UPPER bound lb + 2e does
+    // (sample pass: lower bounds only).  Its item id is read again (and the error bound looked up) only then.
+    int it[E];
+    unsigned keepbits = 0u;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        it[e] = 0;
+        if ((e % EPR) < ns && lbk[e] != 0u) {
+            const int region = e / EPR, pos = (e % EPR) * 32 + lane;
+            it[e] = (int)cd[region * RC + pos].y;
+            bool keep = lbk[e] >= cut;
+            if (!keep && !keep_lb) {
+                const float er = filter_err(ca, chunk_norm[(unsigned)it[e] >> 5], efl);
+                const float ub = __fadd_ru(NumTraits<float>::from_orderable((u64)lbk[e]), __fadd_ru(er, er));
+                keep = NumTraits<float>::key(ub) >= cut;
+            }
+            if (keep) keepbits |= 1u << e;
+        }
+    }
     int base = 0;
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        const bool keep = key[e] >= cut && key[e] != 0u;
-        const unsigned mask = __ballot_sync(FULL, keep);
-        if (keep) {
-            const int k = base + __popc(mask & ((1u << lane) - 1u));
-            const int pos = CONTIG ? k : (k & 3) * RC + (k >> 2);
-            cs[pos] = NumTraits<float>::from_orderable((u64)key[e]);
-            ci[pos] = it[e];
+        if ((e % EPR) < ns) {
+            const bool keep = (keepbits >> e) & 1u;
+            const unsigned mask = __ballot_sync(FULL, keep);
+            if (keep) {
+                const int k = base + __popc(mask & ((1u << lane) - 1u));
+                const int pos = CONTIG ? k : (k & 3) * RC + (k >> 2);
+                cd[pos] = make_uint2(__float_as_uint(NumTraits<float>::from_orderable((u64)lbk[e])), (unsigned)it[e]);
+            }
+            base += __popc(mask);
         }
-        base += __popc(mask);
     }
     *tau_out = tau;
     __syncwarp();
     return base;
 }
 
-// Slow path of the filter, out of line and in ONE copy (the tile loop must stay small: sixteen warps share the
-// instruction cache): the 8 scores of a column group of which at least one is not below the row's threshold.
-// Padding columns and train items are dropped (hpp:494-495; [t_lo, t_hi) = the part of the row's sorted train items
-// that can intersect this tile, empty when none does: the few inside the tile are scanned linearly), NaN scores raise
-// flag 1 (hpp:195-197), the rest is appended to this warp's region of the row's candidate buffer (flag 2 when it is full).
-// Returns the new fill of the region.
+// General slow path of the filter, out of line and in ONE copy: the 8 scores of a column group of which at least one is
+// not below the threshold, in a tile where the row has train items, in the catalogue's last (partial) tile, or when the
+// warp's region is nearly full.  Padding columns and train items are dropped (hpp:494-495; [t_lo, t_hi) = the part of
+// the row's sorted train items that can intersect this tile: the few inside the tile are scanned linearly), the rest is
+// appended to this warp's region of the row's candidate buffer (flag 2 when it is full).  NaN scores are appended like
+// any other (a NaN is never below a threshold and sorts above everything at the cuts): the exact stage raises the
+// user's NaN flag (hpp:195-197).  Returns the new fill of the region.
 template <int RC>
 __device__ __noinline__ int filter_append_group(const float s0, const float s1, const float s2, const float s3,
                                                 const float s4, const float s5, const float s6, const float s7,
-                                                const float thr, const int item0, const int n,
+                                                const float thr, const float err, const int item0, const int n,
                                                 const int* __restrict__ tri, const int t_lo, const int t_hi,
-                                                float* cs, int* ci, int mycnt, int* flagp)
+                                                uint2* cd, int mycnt, const int row)
 {
     // which of the 8 pass (branch-free), then one trip per passing score (almost always a single one)
     unsigned m = (s0 < thr ? 0u : 1u) | (s1 < thr ? 0u : 2u) | (s2 < thr ? 0u : 4u) | (s3 < thr ? 0u : 8u) |
@@ -335,53 +354,41 @@ __device__ __noinline__ int filter_append_group(const float s0, const float s1, 
             if (v >= item) { in_train = (v == item); break; }
         }
         if (in_train) continue;
-        if (s != s) atomicOr(flagp, 1);
-        else if (mycnt < RC) { cs[mycnt] = s; ci[mycnt] = item; mycnt++; }
-        else atomicOr(flagp, 2);
+        if (mycnt < RC) { cd[mycnt] = make_uint2(__float_as_uint(__fsub_rd(s, err)), (unsigned)item); mycnt++; }
+        else atomicOr(&reinterpret_cast<FilterRowState*>(smem_raw)->flags[row], 2);
     }
     return mycnt;
 }
 
 // The item tiles a CTA walks, pass by pass (all roles -- TMA producer, MMA issuer, epilogue -- step through the same list):
 //   pass 0  SAMPLE  every sample_stride-th tile (sample_tiles of them, ~1/16 of the catalogue; skipped when sample_tiles == 0).
-//                   The rows run the same streaming selection with K = sample_rank and no slack; the sample_rank-th best
-//                   approximate score of the sample becomes the row's GUESS g: with sample_rank chosen by the host so that
+//                   The rows run the same streaming selection with K = sample_rank on the LOWER bounds; the sample_rank-th best
+//                   lower bound of the sample becomes the row's GUESS g: with sample_rank chosen by the host so that
 //                   P(fewer than K of ALL items reach the sample's sample_rank-th best) <= 1e-6 per row.
-//   pass 1  MAIN    every tile, thresholds start at g - slack instead of -inf.  A streaming top-K appends K' (1 + ln(n / K'))
+//   pass 1  MAIN    every tile, tau' starts at g instead of -inf.  A streaming top-K appends K' (1 + ln(n / K'))
 //                   candidates per row, more than half of them in the first percent of the catalogue while the threshold is
-//                   still loose; starting from the guess leaves about (items >= g - slack) appends, 3x fewer at 1M items.
-//                   The guess is VERIFIED: the pass is valid for a row iff at least K of its kept candidates reach g
-//                   (then the K-th best approximate score tau~ >= g and everything >= tau~ - slack was kept).
+//                   still loose; starting from the guess leaves about (items whose upper bound reaches g) appends, 3x fewer at 1M items.
+//                   The guess is VERIFIED: the pass is valid for a row iff at least K of its kept candidates have a lower
+//                   bound >= g (then the final tau' >= g never fell below the threshold any item was tested against).
 //   pass 2  RETRY   only if some row of the CTA failed the check (or had too few sample candidates): every tile again,
 //                   failed rows from -inf, the others closed.  Costs the CTA a second walk; never changes a result.
 __device__ __forceinline__ int filter_pass_tiles(const FilterParams& P, const int pass, const int NT) { return pass == 0 ? P.sample_tiles : NT; }
 __device__ __forceinline__ int filter_pass_tile(const FilterParams& P, const int pass, const int j) { return pass == 0 ? j * P.sample_stride : j; }
 
-// PAIR (launched as clusters of two CTAs; EXPERIMENTAL, off unless RMB200_PAIR=1 -- written at the end of round 1 on top of
-// tools/ubench/umma_pair_probe.cu and not yet tuned): the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 of 256 users x
-// 128 items per k-step.  Each CTA keeps its own 128 user rows, its own accumulators (its TMEM holds its rows of D, so the
-// epilogue below is unchanged) and only HALF of every item tile (CTA r: items r*64..r*64+63 of the tile, 16 KB bulk copy from a
-// B image packed in halves): the L2 -> shared-memory traffic that bounds the pipeline is halved.  The leader (rank 0) issues
-// the MMAs once both halves have landed (the peer's MMA warps forward their `full` barrier with a remote arrive) and both
-// CTAs' epilogues have drained the accumulator buffer (the peer's epilogue warps arrive remotely on the leader's `acc_empty`);
-// its commits are multicast to `empty` / `acc_full` of both CTAs.  The retry pass is taken by both CTAs if either needs it.
-template <int C, bool PAIR>
+template <int C>
 __global__ void __launch_bounds__(F_THREADS, 1)
 filter_select_kernel(const __grid_constant__ FilterParams P)
 {
     const int KB = P.KB, S = P.stages;
     const unsigned tile_bytes = (unsigned)KB * 128u * 2u;          // one operand tile (A or B)
-    const unsigned b_bytes = PAIR ? tile_bytes / 2u : tile_bytes;  // what one ring stage receives (the stage slots keep their size)
-    const unsigned rank = PAIR ? cluster_ctarank() : 0u;
-    unsigned char* a_tile = smem_raw;
+    FilterRowState* rs = reinterpret_cast<FilterRowState*>(smem_raw);
+    u64* bars = reinterpret_cast<u64*>(smem_raw + F_RS_BYTES);
+    unsigned char* a_tile = smem_raw + F_RS_BYTES + 256;
     unsigned char* b_ring = a_tile + tile_bytes;
-    u64* bars = reinterpret_cast<u64*>(b_ring + (size_t)S * tile_bytes);
-    // barriers: full[4], empty[4], acc_full[4], acc_empty[4], a_full
+    // barriers: full[F_MAX_STAGES], empty[F_MAX_STAGES], acc_full[4], acc_empty[4], a_full
     const unsigned bar_full = smem_u32(bars), bar_empty = bar_full + 8 * F_MAX_STAGES;
     const unsigned bar_accf = bar_empty + 8 * F_MAX_STAGES, bar_acce = bar_accf + 32, bar_a = bar_acce + 32;
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + 2 * F_MAX_STAGES + 9);
-    const unsigned bar_pfull = bar_a + 16;                         // PAIR, leader: the peer's half of stage s has landed
-    FilterRowState* rs = reinterpret_cast<FilterRowState*>(reinterpret_cast<unsigned char*>(bars) + 256);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int tile_u0 = blockIdx.x * BM;
@@ -389,25 +396,18 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 
     if (tid == 0) {
         for (int s = 0; s < F_MAX_STAGES; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, 1); }
-        for (int b = 0; b < F_ACCBUFS; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, PAIR ? 2 * F_EPI_WARPS : F_EPI_WARPS); }
+        for (int b = 0; b < F_ACCBUFS; b++) { mbar_init(bar_accf + 8 * b, 1); mbar_init(bar_acce + 8 * b, F_EPI_WARPS); }
         mbar_init(bar_a, 1);
-        if (PAIR) for (int s = 0; s < F_MAX_STAGES; s++) mbar_init(bar_pfull + 8 * s, 1);
         mbar_fence_init();
         rs->retry = 0;
         for (int i = 0; i < 4; i++) rs->stat[i] = 0;
     }
-    if (warp == F_EPI_WARPS + 1) {      // the MMA warp owns the tensor-memory allocation (PAIR: one warp of each CTA)
-        if (PAIR) {
-            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((unsigned)F_TMEM_COLS));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::);
-        } else {
-            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((unsigned)F_TMEM_COLS));
-            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
-        }
+    if (warp == F_EPI_WARPS + 1) {      // the MMA warp owns the tensor-memory allocation
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((unsigned)F_TMEM_COLS));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
     }
     tc_fence_before();
     __syncthreads();
-    if (PAIR) cluster_sync_all();       // both CTAs: barriers initialised, tensor memory allocated
     tc_fence_after();
     const unsigned tmem_base = *tmem_slot;
 
@@ -429,11 +429,9 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     if ((P.dbg & 16) && it0 + j >= S) { mbar_arrive(bar_full + 8 * s); } else       // 16: no TMA after the first round (stale tiles)
 #endif
                     {
-                    mbar_arrive_expect_tx(bar_full + 8 * s, b_bytes);
-                    // (PAIR: the item matrix is packed in 64-item halves, [tile][half][k/8][64][8]; this CTA takes half `rank`)
-                    tma_bulk_g2s(smem_u32(b_ring) + (unsigned)s * tile_bytes,
-                                 P.Bb + (PAIR ? ((size_t)filter_pass_tile(P, pass, j) * 2 + rank) * KB * 64 : (size_t)filter_pass_tile(P, pass, j) * KB * 128),
-                                 b_bytes, bar_full + 8 * s);
+                    mbar_arrive_expect_tx(bar_full + 8 * s, tile_bytes);
+                    tma_bulk_g2s(smem_u32(b_ring) + (unsigned)s * tile_bytes, P.Bb + (size_t)filter_pass_tile(P, pass, j) * KB * 128,
+                                 tile_bytes, bar_full + 8 * s);
                     }
                 }
                 __syncwarp();
@@ -442,9 +440,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
         } else if (warp > F_EPI_WARPS) {
             // ===================== MMA issuers (converged warps, one elected lane issues; warp w takes iterations it % F_MMA_WARPS == w) =====================
             // D fp32 (bit 4), A and B fp16 (format 0 at bits 7 and 10), both K-major, N=128 (>>3 at bit 17), M=128 (>>4 at bit 24)
-            const unsigned idesc = (1u << 4) | ((unsigned)(FN >> 3) << 17) | (((PAIR ? 256u : 128u) >> 4) << 24);
-            const uint64_t adesc0 = umma_desc(smem_u32(a_tile)), bdesc0 = PAIR ? umma_desc_half(smem_u32(b_ring)) : umma_desc(smem_u32(b_ring));
-            const unsigned b_kstep = PAIR ? 2048u : 4096u;                    // bytes between two K=16 steps of the B operand
+            const unsigned idesc = (1u << 4) | ((unsigned)(FN >> 3) << 17) | ((128u >> 4) << 24);
+            const uint64_t adesc0 = umma_desc(smem_u32(a_tile)), bdesc0 = umma_desc(smem_u32(b_ring));
             int ksteps = KB / 16;                                             // K=16 per MMA = two 16-byte k chunks of 2048 B
 #if RMB_F_DBG
             if (P.dbg & 32) ksteps = ksteps / 2 > 0 ? ksteps / 2 : 1;         // 32: half of the k steps
@@ -455,37 +452,18 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             int s = (it0 + j) % S, ph = ((it0 + j) / S) & 1;
             for (; j < ntiles; j += F_MMA_WARPS) {
                 const int it = it0 + j, b = it & (F_ACCBUFS - 1);
-                if (PAIR && rank != 0) {
-                    // peer CTA: its half of the tile has landed -> tell the leader; the leader's MMAs do the rest
-                    mbar_wait(bar_full + 8 * s, ph);
-                    if (elect_one()) mbar_arrive_cluster(mapa_shared(bar_pfull + 8 * s, 0u));
-                    __syncwarp();
-                    s += F_MMA_WARPS;
-                    while (s >= S) { s -= S; ph ^= 1; }
-                    continue;
-                }
-                mbar_wait(bar_acce + 8 * b, ((it >> F_ACCSHIFT) & 1) ^ 1);     // accumulator buffer drained by the epilogue (PAIR: of both CTAs)
+                mbar_wait(bar_acce + 8 * b, ((it >> F_ACCSHIFT) & 1) ^ 1);     // accumulator buffer drained by the epilogue
                 mbar_wait(bar_full + 8 * s, ph);                              // B tile landed
-                if (PAIR) mbar_wait(bar_pfull + 8 * s, ph);                   // ... and the peer's half
                 tc_fence_after();
                 if (elect_one()) {
                     const uint64_t bdesc = umma_desc_advance(bdesc0, (unsigned)s * tile_bytes);
                     const unsigned d = tmem_base + (unsigned)(b * FN);
-                    if (PAIR) {
-                        umma_f16_pair(d, adesc0, bdesc, idesc, 0u);
+                    umma_f16(d, adesc0, bdesc, idesc, 0u);
 #pragma unroll 7
-                        for (int ks = 1; ks < ksteps; ks++)
-                            umma_f16_pair(d, umma_desc_advance(adesc0, ks * 4096), umma_desc_advance(bdesc, ks * b_kstep), idesc, 1u);
-                        umma_commit_pair(bar_empty + 8 * s);
-                        umma_commit_pair(bar_accf + 8 * b);
-                    } else {
-                        umma_f16(d, adesc0, bdesc, idesc, 0u);
-#pragma unroll 7
-                        for (int ks = 1; ks < ksteps; ks++)
-                            umma_f16(d, umma_desc_advance(adesc0, ks * 4096), umma_desc_advance(bdesc, ks * 4096), idesc, 1u);
-                        umma_commit(bar_empty + 8 * s);                       // stage reusable once these MMAs have read it
-                        umma_commit(bar_accf + 8 * b);                        // accumulator complete
-                    }
+                    for (int ks = 1; ks < ksteps; ks++)
+                        umma_f16(d, umma_desc_advance(adesc0, ks * 4096), umma_desc_advance(bdesc, ks * 4096), idesc, 1u);
+                    umma_commit(bar_empty + 8 * s);                       // stage reusable once these MMAs have read it
+                    umma_commit(bar_accf + 8 * b);                        // accumulator complete
                 }
                 __syncwarp();
                 s += F_MMA_WARPS;
@@ -499,45 +477,61 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             const int ul = tile_u0 + row;
             const unsigned qbar = 1 + q;                    // named barrier of the quarter's four warps
             const int Kp = pass == 0 ? P.sample_rank : P.K; // how many best candidates the pass keeps track of
-            float* cs = P.cand_approx + (size_t)ul * C + slot * RC;      // this warp's region of the row's buffer
-            int* ci = P.cand_item + (size_t)ul * C + slot * RC;
+            const bool keep_lb = pass == 0;
             if (slot == 0) {
-                const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0) && !(RMB_F_DBG && (P.dbg & 2));
-                // |approx - exact| <= c ||a|| max||b|| (c = P.err_coef, see filter_err_coef); the approximate scores live in the
-                // scaled units of the operand image (row scale x matrix scale, both powers of two), and so does the slack
-                float slack = 0.f;
-                if (ranked) {
-                    const float an = P.anorm[ul], bn = __uint_as_float(*P.maxbn);
-                    const float sa = pow2_scale_for(an), sb = pow2_scale_for(bn);
-                    slack = 2.f * P.err_coef * (an * sa) * (bn * sb) + P.noise_band * sa * sb;
-                }
-                float thr0 = CUDART_INF_F;                  // approx < thr: cannot be in the exact top K; +inf: the row is closed
-                if (pass == 0) {
-                    rs->flags[row] = 0;
+                bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0) && !(RMB_F_DBG && (P.dbg & 2));
+                if (pass < 2 && (pass == 0 || P.sample_tiles == 0)) {            // first pass of the CTA: the row's error-bound terms
+                    int fl = 0;
+                    float ca = 0.f, efl = 0.f;
+                    if (ranked) {
+                        const float an = P.anorm[ul], bn = __uint_as_float(*P.maxbn);
+                        if (an == 0.f) ranked = false;                           // all-zero user factors: every score equal, NaN row (hpp:541-548, :524-527)
+                        else if (!(filter_scalable(an) && filter_scalable(bn))) { fl = 8; ranked = false; }
+                        else {
+                            const float sa = pow2_scale_for(an), sb = pow2_scale_for(bn);
+                            const float ap = an * sa;                                            // ||a'|| in [0.5, 1.002)
+                            ca = __fmul_ru(__fmul_ru(P.c_rel, ap), sb);                          // x ||b_j|| (unscaled chunk norm)
+                            efl = __fadd_ru(__fmaf_ru(P.c_abs, ap, P.c_const), 0.5f * P.noise_band * sa * sb);
+                        }
+                    }
+                    rs->flags[row] = fl;
                     rs->guess[row] = -CUDART_INF_F;
-                    if (ranked) thr0 = -CUDART_INF_F;
-                } else if (pass == 1) {
-                    if (P.sample_tiles == 0) { rs->flags[row] = 0; rs->guess[row] = -CUDART_INF_F; }
-                    if (ranked) { thr0 = __fsub_rd(rs->guess[row], slack); if (!(thr0 == thr0)) thr0 = -CUDART_INF_F; }
-                } else {
-                    if (rs->flags[row] & 4) thr0 = -CUDART_INF_F;
+                    rs->ca[row] = ca;
+                    rs->efl[row] = efl;
+                    rs->cnt[row] = 0;
+                    rs->trig[row] = ranked ? 0 : -1;                             // (-1 marks rows that are never ranked, see below)
                 }
-                rs->slack[row] = pass == 0 ? 0.f : slack;
-                rs->thr[row] = thr0;
-                rs->trig[row] = Kp + F_CUT_MARGIN;
-                if (thr0 != CUDART_INF_F || pass < 2) rs->cnt[row] = 0;   // (a row closed in the retry pass keeps what pass 1 found)
+                ranked = ranked && rs->trig[row] != -1 && !(rs->flags[row] & 8);
+                float tau0 = CUDART_INF_F;                  // +inf: the row is closed
+                if (pass == 0) { if (ranked) tau0 = -CUDART_INF_F; }
+                else if (pass == 1) { if (ranked) { tau0 = rs->guess[row]; if (!(tau0 == tau0)) tau0 = -CUDART_INF_F; } }
+                else if (ranked && (rs->flags[row] & 4)) tau0 = -CUDART_INF_F;
+                rs->tau[row] = tau0;
+                if (rs->trig[row] != -1) rs->trig[row] = Kp + F_CUT_MARGIN;
+                if (tau0 != CUDART_INF_F || pass < 2) rs->cnt[row] = 0;   // (a row closed in the retry pass keeps what pass 1 found)
             }
             asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
             // private per-thread row state: region fill, cursor into the row's sorted train items (hpp:494-495 takes those out
             // of the pool): t_nxt = the first train item id >= the current tile, the one after it prefetched in shared memory
-            int mycnt = 0, t_cur = 0, t_end = 0, t_nxt = INT_MAX;
-            if (rs->thr[row] != CUDART_INF_F) {
-                t_cur = P.trp[P.user0 + ul]; t_end = P.trp[P.user0 + ul + 1];
-                if (t_cur < t_end) t_nxt = P.tri[t_cur];
-                rs->nxt2_train[slot][row] = t_cur + 1 < t_end ? P.tri[t_cur + 1] : INT_MAX;
+            int mycnt = 0, t_nxt = INT_MAX;
+            float tau = rs->tau[row];                       // the row's bound only moves at the meetings: kept in a register in between
+            {
+                int t_cur = 0, t_end = 0;
+                if (tau != CUDART_INF_F) {
+                    t_cur = P.trp[P.user0 + ul]; t_end = P.trp[P.user0 + ul + 1];
+                    if (t_cur < t_end) t_nxt = P.tri[t_cur];
+                    rs->nxt2_train[slot][row] = t_cur + 1 < t_end ? P.tri[t_cur + 1] : INT_MAX;
+                }
+                rs->tcur[slot][row] = t_cur;
+                rs->tend[row] = t_end;                      // (the same value from the row's four warps)
+                rs->tot_prev[slot][row] = 0;
+                if (lane == 0) rs->interval[warp] = 1;
             }
-            int tot_prev = 0;                               // row total after the previous meeting (the same in all four warps)
-            int meet_in = 0, interval = 1;                  // tiles until the next meeting; tiles since the previous one
+            // error bound in the tile loop: the sample pass compares the approximate scores themselves (the cut then keeps
+            // the best LOWER bounds); the other passes test upper bounds, approx + e >= tau'
+            const float ca_l = pass == 0 ? 0.f : rs->ca[row];
+            float tau_m = pass == 0 ? tau : __fsub_rd(tau, rs->efl[row]);          // tau' minus the row's constant error term
+            int meet_in = 0;                                // tiles until the next meeting
             // loop-carried pipeline state, kept incrementally (no per-tile index arithmetic): accumulator buffer and its phase
             // parity, first item id of this warp's 32-column chunk, the item step between two tiles of the pass
             int buf = it0 & (F_ACCBUFS - 1);
@@ -545,12 +539,15 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
             int item_base = slot * F_CHUNK;
             const int item_step = (pass == 0 ? P.sample_stride : 1) * FN;
             const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(slot * F_CHUNK);
-            int* const flag_p = &rs->flags[row];
-            float thr = rs->thr[row];                       // the row's threshold only moves at the meetings: kept in a register in between
 
 #pragma unroll 1
             for (int left = ntiles; left > 0; left--, item_base += item_step) {
                 const int tile_end = item_base - slot * F_CHUNK + FN;
+#if RMB_F_NO_CN
+                const float cn = __uint_as_float(*P.maxbn);                    // developer: one bound for the whole catalogue (timing experiments)
+#else
+                const float cn = __ldg(P.chunk_norm + (item_base >> 5));       // largest item norm of this chunk (in flight while the warp waits)
+#endif
                 mbar_wait(bar_accf + 8 * buf, par);
                 tc_fence_after();
                 unsigned v[32];
@@ -560,10 +557,7 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 tmem_ld32(taddr0 + (unsigned)(buf * FN), v);
                 tc_fence_before();                      // this warp's part of the accumulator is in registers
                 __syncwarp();
-                if (lane == 0) {
-                    if (PAIR && rank != 0) mbar_arrive_cluster(mapa_shared(bar_acce + 8 * buf, 0u));    // the leader counts both CTAs' warps
-                    else mbar_arrive(bar_acce + 8 * buf);
-                }
+                if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
                 if (++buf == F_ACCBUFS) { buf = 0; par ^= 1u; }
 #if RMB_F_DBG
                 if (P.dbg & 1) continue;
@@ -579,19 +573,47 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     const float m67 = max_nan(__uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]));
                     gm[g] = max_nan(max_nan(m01, m23), max_nan(m45, m67));
                 }
+                const float thr = __fmaf_rd(-ca_l, cn, tau_m);                     // approx < thr: the upper bound stays below tau'
                 if (!(max_nan(max_nan(gm[0], gm[1]), max_nan(gm[2], gm[3])) < thr)) {
+                    uint2* const cd = P.cand + ((size_t)ul * C + slot * RC);      // this warp's region of the row's buffer
+                    const float err = filter_err(rs->ca[row], cn, rs->efl[row]);  // candidates are stored with their lower bound
+#if RMB_F_FAST_APPEND
+                    if (!has_train && tile_end <= P.n && mycnt <= RC - F_CHUNK) {
+                        // common case (no train item of the row in this tile, no padding column, room for the whole chunk):
+                        // predicated appends, no calls, no loops
+#pragma unroll
+                        for (int g = 0; g < 4; g++) {
+                            if (!(gm[g] < thr)) {
+                                F_STAT(2, 1);
+                                const int before = mycnt;
+#pragma unroll
+                                for (int e8 = 0; e8 < 8; e8++) {
+                                    if (!(__uint_as_float(v[8 * g + e8]) < thr)) {
+                                        cd[mycnt] = make_uint2(__float_as_uint(__fsub_rd(__uint_as_float(v[8 * g + e8]), err)), (unsigned)(item_base + 8 * g + e8));
+                                        mycnt++;
+                                    }
+                                }
+                                F_STAT(0, mycnt - before);
+                                (void)before;
+                            }
+                        }
+                    } else
+#endif
+                    {
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
                         if (!(gm[g] < thr)) {
                             F_STAT(2, 1);
                             const int before = mycnt;
+                            const int t_cur = rs->tcur[slot][row];
                             mycnt = filter_append_group<RC>(__uint_as_float(v[8 * g + 0]), __uint_as_float(v[8 * g + 1]), __uint_as_float(v[8 * g + 2]),
                                                             __uint_as_float(v[8 * g + 3]), __uint_as_float(v[8 * g + 4]), __uint_as_float(v[8 * g + 5]),
-                                                            __uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), thr, item_base + 8 * g, P.n,
-                                                            P.tri, t_cur, has_train ? t_end : t_cur, cs, ci, mycnt, flag_p);
+                                                            __uint_as_float(v[8 * g + 6]), __uint_as_float(v[8 * g + 7]), thr, err, item_base + 8 * g, P.n,
+                                                            P.tri, t_cur, has_train ? rs->tend[row] : t_cur, cd, mycnt, row);
                             F_STAT(0, mycnt - before);
                             (void)before;
                         }
+                    }
                     }
                 }
                 // move the train cursor past this tile: the id after t_nxt was prefetched into shared memory when the cursor last moved
@@ -599,9 +621,11 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     F_STAT(3, 1);
                     asm volatile("cp.async.wait_all;" ::: "memory");
                     int nxt = rs->nxt2_train[slot][row];
-                    t_cur++;
+                    int t_cur = rs->tcur[slot][row] + 1;
+                    const int t_end = rs->tend[row];
                     while (nxt < tile_end) { t_cur++; nxt = t_cur < t_end ? P.tri[t_cur] : INT_MAX; }    // several train items in one tile
                     t_nxt = nxt;
+                    rs->tcur[slot][row] = t_cur;
                     if (t_cur + 1 < t_end)
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&rs->nxt2_train[slot][row])), "l"(P.tri + t_cur + 1) : "memory");
                     else rs->nxt2_train[slot][row] = INT_MAX;
@@ -616,8 +640,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
                 int c0 = rs->cnt4[0][row], c1 = rs->cnt4[1][row], c2 = rs->cnt4[2][row], c3 = rs->cnt4[3][row];
                 int tot = c0 + c1 + c2 + c3;
-                const int grown = tot - tot_prev;                              // appends to the row since the previous meeting
-                unsigned need = __ballot_sync(FULL, tot > rs->trig[row] && !(rs->flags[row] & 2));
+                const int grown = tot - rs->tot_prev[slot][row];                   // appends to the row since the previous meeting
+                unsigned need = __ballot_sync(FULL, tot > rs->trig[row] && rs->trig[row] >= 0 && !(rs->flags[row] & 2));
                 if (left == 1) need = 0;                                       // the pass ends with the exact cut below
                 if (need) {                                                    // (the same mask in all four warps)
                     while (need) {
@@ -625,17 +649,15 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                         need &= need - 1;
                         if ((r & 3) != slot) continue;                         // the quarter's warps share the work
                         const int rr = q * 32 + r;
-                        const size_t base = (size_t)(tile_u0 + rr) * C;
                         float tau_r;
-                        const int kept = cut_regions<C, RMB_F_HIST_ROUNDS, false>(P.cand_approx + base, P.cand_item + base, rs->cnt4[0][rr], rs->cnt4[1][rr],
-                                                                                  rs->cnt4[2][rr], rs->cnt4[3][rr], Kp, rs->slack[rr], lane, rs->hist[warp], &tau_r);
+                        const int kept = cut_regions<C, RMB_F_HIST_ROUNDS, false>(P.cand + (size_t)(tile_u0 + rr) * C, rs->cnt4[0][rr], rs->cnt4[1][rr],
+                                                                                  rs->cnt4[2][rr], rs->cnt4[3][rr], Kp, rs->ca[rr], rs->efl[rr], P.chunk_norm,
+                                                                                  keep_lb, lane, rs->hist[warp], &tau_r);
                         if (lane == 0) {
                             F_STAT(1, 1);
-                            float thr_r = __fsub_rd(tau_r, rs->slack[rr]);
-                            if (!(thr_r == thr_r)) thr_r = -CUDART_INF_F;       // non-finite bound: keep everything
-                            thr_r = fmaxf(thr_r, rs->thr[rr]);                  // an earlier (valid) bound may be the sharper one
-                            if (kept > 4 * (RC - 32)) { rs->flags[rr] |= 2; thr_r = CUDART_INF_F; }     // the slack band does not fit
-                            rs->thr[rr] = thr_r;
+                            float t_new = fmaxf(tau_r, rs->tau[rr]);            // an earlier (valid) bound may be the sharper one; a NaN bound is ignored
+                            if (kept > 4 * (RC - 32)) { rs->flags[rr] |= 2; t_new = CUDART_INF_F; }     // the kept band does not fit
+                            rs->tau[rr] = t_new;
                             rs->trig[rr] = kept + F_CUT_MARGIN;
 #pragma unroll
                             for (int sgm = 0; sgm < 4; sgm++) rs->cnt4[sgm][rr] = (kept + 3 - sgm) >> 2;
@@ -646,39 +668,41 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     tot = c0 + c1 + c2 + c3;
                     mycnt = slot == 0 ? c0 : (slot == 1 ? c1 : (slot == 2 ? c2 : c3));
                 }
-                thr = rs->thr[row];
-                if (rs->flags[row] & 2) { mycnt = 0; thr = CUDART_INF_F; if (slot == 0) rs->thr[row] = CUDART_INF_F; }     // the row is closed: whatever it holds is void
-                tot_prev = tot;
+                tau = rs->tau[row];
+                if (rs->flags[row] & 2) { mycnt = 0; tau = CUDART_INF_F; if (slot == 0) rs->tau[row] = CUDART_INF_F; }     // the row is closed: whatever it holds is void
+                tau_m = pass == 0 ? tau : __fsub_rd(tau, rs->efl[row]);
+                const int interval = rs->interval[warp];
                 // next meeting: far enough that barriers are rare, close enough that no region can fill up at twice the
                 // append rate just seen (all of it into one region); a burst beyond that closes the row (flag 2)
                 const int headroom = RC - max(max(c0, c1), max(c2, c3));
                 int nxt_iv = grown > 0 ? (headroom * interval) / (2 * grown) : F_MAX_MEET;
                 nxt_iv = __reduce_min_sync(FULL, nxt_iv);
-                interval = nxt_iv < 1 ? 1 : (nxt_iv > F_MAX_MEET ? F_MAX_MEET : nxt_iv);
-                meet_in = interval - 1;
+                nxt_iv = nxt_iv < 1 ? 1 : (nxt_iv > F_MAX_MEET ? F_MAX_MEET : nxt_iv);
+                meet_in = nxt_iv - 1;
+                rs->tot_prev[slot][row] = tot;
+                if (lane == 0) rs->interval[warp] = nxt_iv;
             }
-            // end of the pass (all four warps are past the last meeting): the exact Kp-th best approximate score of what each
+            // end of the pass (all four warps are past the last meeting): the exact Kp-th best lower bound of what each
             // row kept, the survivors packed at the head of the row's buffer
             for (int r = slot; r < 32; r += 4) {
                 const int rr = q * 32 + r;
-                if (rs->thr[rr] == CUDART_INF_F && !(rs->flags[rr] & 2)) continue;    // closed row (not ranked / settled in pass 1)
+                if (rs->tau[rr] == CUDART_INF_F && !(rs->flags[rr] & 2)) continue;    // closed row (not ranked / settled in pass 1)
                 const int c0 = rs->cnt4[0][rr], c1 = rs->cnt4[1][rr], c2 = rs->cnt4[2][rr], c3 = rs->cnt4[3][rr];
                 const int nv = c0 + c1 + c2 + c3;
                 float tau_r = -CUDART_INF_F;
                 const bool have_k = nv >= Kp && !(rs->flags[rr] & 2);
                 if (nv > 0 && !(rs->flags[rr] & 2)) {
-                    const size_t base = (size_t)(tile_u0 + rr) * C;
-                    const int kept = cut_regions<C, 7, true>(P.cand_approx + base, P.cand_item + base, c0, c1, c2, c3, have_k ? Kp : nv, rs->slack[rr], lane,
-                                                             rs->hist[warp], &tau_r);
+                    const int kept = cut_regions<C, 7, true>(P.cand + (size_t)(tile_u0 + rr) * C, c0, c1, c2, c3, have_k ? Kp : nv, rs->ca[rr], rs->efl[rr],
+                                                             P.chunk_norm, keep_lb, lane, rs->hist[warp], &tau_r);
                     if (lane == 0 && pass > 0) rs->cnt[rr] = kept;      // last cut: the exact stage gets only what can still be in the top K
                 }
                 if (lane == 0) {
                     if (pass == 0) {
-                        rs->guess[rr] = have_k ? tau_r : -CUDART_INF_F;                 // too small a sample / overflow: no guess
+                        rs->guess[rr] = (have_k && tau_r == tau_r) ? tau_r : -CUDART_INF_F;   // too small a sample / overflow: no guess
                         rs->flags[rr] &= ~2;
                     } else if (pass == 1 && !(rs->flags[rr] & 2)) {
                         const float g = rs->guess[rr];
-                        const bool ok = (g == -CUDART_INF_F) || (have_k && tau_r >= g);  // >= K kept candidates reach the guess
+                        const bool ok = (g == -CUDART_INF_F) || (have_k && !(tau_r < g));     // >= K kept lower bounds reach the guess (a NaN bound: everything was kept)
                         if (!ok) { rs->flags[rr] |= 4; rs->retry = 1; }
                     }
                 }
@@ -688,11 +712,7 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
         it0 += ntiles;
         if (pass == 0) continue;         // the sample's result is consumed by the epilogue warps alone
         __syncthreads();
-        unsigned again = rs->retry != 0 ? 1u : 0u;
-        if (PAIR) {                                                      // both CTAs walk the same passes: retry if either needs it
-            cluster_sync_all();
-            again |= ld_shared_cluster_u32(mapa_shared(smem_u32(&rs->retry), rank ^ 1u)) != 0u ? 1u : 0u;
-        }
+        const unsigned again = rs->retry != 0 ? 1u : 0u;
         if (pass == 2 || !__any_sync(FULL, again != 0u)) break;          // (a vote: the compiler keeps the pass loop warp-uniform)
     }
 
@@ -700,9 +720,9 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
         const int row = (warp & 3) * 32 + lane, ul = tile_u0 + row;
         if (ul < P.mb) {
             const int fl = rs->flags[row];
-            P.cand_count[ul] = (fl & 2) ? -1 : rs->cnt[row];
-            if (fl & 2) atomicAdd(P.overflow, 1);
-            if (fl & 1) atomicOr(&P.uflags[P.user0 + ul], 1);
+            const bool to_fma = (fl & (2 | 8)) != 0;
+            P.cand_count[ul] = to_fma ? -1 : rs->cnt[row];
+            if (to_fma) atomicAdd(P.overflow, 1);
             if ((fl & 4) && P.retries) atomicAdd(P.retries, 1);
         }
     }
@@ -712,11 +732,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 #if RMB_F_STATS
     if (tid < 4 && P.retries) atomicAdd(P.retries + 1 + tid, rs->stat[tid]);
 #endif
-    if (PAIR) cluster_sync_all();       // neither CTA leaves (or frees tensor memory) while the pair's MMAs or remote arrivals are in flight
-    if (warp == F_EPI_WARPS + 1) {
-        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)F_TMEM_COLS));
-        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)F_TMEM_COLS));
-    }
+    if (warp == F_EPI_WARPS + 1)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((unsigned)F_TMEM_COLS));
 }
 
 // One warp per user: exact scores of the candidates the filter kept (sequential fma chain over the original
@@ -802,15 +819,24 @@ __device__ __forceinline__ int exact_select(const typename NumTraits<T>::key_t (
     return base;
 }
 
+// optional statistic (developer / tests): how close the observed error of the filter's approximate scores comes to its bound
+struct FilterErrStat {
+    const float* anorm;            // [mb]
+    const unsigned* maxbn;
+    const float* chunk_norm;
+    float c_rel, c_abs, c_const;
+    unsigned* max_ratio_bits;      // float bits of max over re-scored candidates of |approx - exact| / bound (nullptr: off)
+};
+
 template <typename T, int C, int MODE>
 __global__ void __launch_bounds__(EXACT_WARPS * 32)
-exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_score, int* __restrict__ cand_item,
+exact_topk_kernel(const uint2* __restrict__ cand, T* __restrict__ cand_score, int* __restrict__ cand_item,
                   int* __restrict__ cand_count, const int mb, const int user0,
                   const T* __restrict__ At, const int p_pad, const int p,
                   const T* __restrict__ Brow, const size_t ldb, const T* __restrict__ bias,
                   int* __restrict__ uflags, const int K,
                   const int noise, const unsigned long long seed_user0, const size_t mt_off,
-                  const int* __restrict__ trp, const int* __restrict__ tri, const int n)
+                  const int* __restrict__ trp, const int* __restrict__ tri, const int n, const FilterErrStat es)
 {
     typedef typename NumTraits<T>::key_t key_t;
     constexpr int E = C / 32;
@@ -820,7 +846,7 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
     const int nv = cand_count[ul];
     if (nv <= 0) return;
     const T* __restrict__ a = At + (size_t)(ul / BM) * p_pad * BM + (ul % BM);      // + k * BM
-    const int* ci = cand_item + (size_t)ul * C;
+    const uint2* cd = cand + (size_t)ul * C;
     constexpr bool STAGED = MODE != 0;
     constexpr int V = 16 / (int)sizeof(T);                                                         // elements per 16 bytes
     const int RS = p_pad + (MODE == 2 ? V : 1);                                                    // row stride of the staged rows
@@ -840,7 +866,8 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
         it[e] = INT_MAX;
         if (e * 32 < nv) {                       // warp-uniform
             const bool valid = idx < nv;
-            const int item = valid ? ci[idx] : 0;
+            const uint2 cde = valid ? cd[idx] : make_uint2(0u, 0u);
+            const int item = (int)cde.y;
             if (valid) it[e] = item;
             T acc = (T)0;
             if (STAGED) {
@@ -879,6 +906,16 @@ exact_topk_kernel(const float* __restrict__ cand_approx, T* __restrict__ cand_sc
                 if (bias != nullptr) acc += bias[item];
                 if (acc != acc) nanflag = 1;
                 else key[e] = NumTraits<T>::key(acc);
+                if (es.max_ratio_bits != nullptr) {
+                    // observed error of the approximate score against the bound the filter used for it (scaled units)
+                    const float an = es.anorm[ul], bn = __uint_as_float(*es.maxbn);
+                    const float sa = pow2_scale_for(an), sb = pow2_scale_for(bn), ap = an * sa;
+                    const float bound = filter_err(__fmul_ru(__fmul_ru(es.c_rel, ap), sb), es.chunk_norm[item >> 5], __fmaf_ru(es.c_abs, ap, es.c_const));
+                    // (the candidate carries its lower bound: approximate score = lower bound + bound, up to one rounding)
+                    const double diff = fabs((double)__uint_as_float(cde.x) + (double)bound - (double)acc * (double)sa * (double)sb);
+                    const float ratio = (float)(diff / (double)bound);
+                    if (ratio == ratio && ratio < CUDART_INF_F) atomicMax(es.max_ratio_bits, __float_as_uint(ratio));
+                }
             }
         }
     }

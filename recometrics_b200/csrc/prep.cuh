@@ -32,6 +32,52 @@ __global__ void pack_tiles_kernel(const T* __restrict__ src, const size_t ld_src
     }
 }
 
+// The same for a LIST of rows: slab row r of dst = src row base + rowmap[r] (r < rows; the rest is zero).  Used to re-run
+// the users the tensor-core filter handed back on the FMA tiles (api.cu).
+template <typename T, int W>
+__global__ void pack_tiles_gather_kernel(const T* __restrict__ src, const size_t ld_src, const int* __restrict__ rowmap, const int rows,
+                                         const int cols, T* __restrict__ dst, const int rows_pad, const int cols_pad)
+{
+    __shared__ T tile[32][33];
+    const int r0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x, ty = threadIdx.y;      // 32 x 8
+    for (int i = ty; i < 32; i += 8) {
+        const int r = r0 + i, c = c0 + tx;
+        tile[i][tx] = (r < rows && c < cols) ? src[(size_t)rowmap[r] * ld_src + c] : (T)0;
+    }
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8) {
+        const int c = c0 + i, r = r0 + tx;
+        if (c < cols_pad && r < rows_pad)
+            dst[((size_t)(r / W) * cols_pad + c) * W + (r % W)] = tile[tx][i];
+    }
+}
+
+// Users of a batch the filter flagged (cand_count == -1), in ascending order: list[0 .. *count).  One block; the batch
+// has at most a few hundred thousand users and flagged ones are rare.
+__global__ void collect_flagged_kernel(const int* __restrict__ cand_count, const int nb, int* __restrict__ list, int* __restrict__ count)
+{
+    __shared__ int warp_tot[32];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (threadIdx.x == 0) base_s = 0;
+    __syncthreads();
+    for (int u0 = 0; u0 < nb; u0 += blockDim.x) {
+        const int u = u0 + threadIdx.x;
+        const bool f = u < nb && cand_count[u] < 0;
+        const unsigned mask = __ballot_sync(FULL, f);
+        if (lane == 0) warp_tot[warp] = __popc(mask);
+        __syncthreads();
+        int off = base_s;
+        for (int w = 0; w < warp; w++) off += warp_tot[w];
+        if (f) list[off + __popc(mask & ((1u << lane) - 1u))] = u;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int w = 0; w < nw; w++) t += warp_tot[w]; base_s += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *count = base_s;
+}
+
 template <typename T>
 __global__ void pad_copy_kernel(const T* __restrict__ src, const int n, T* __restrict__ dst, const int n_pad)
 {
@@ -174,25 +220,62 @@ __global__ void pack_f16_kernel(const T* __restrict__ src, const size_t ld, cons
     *reinterpret_cast<uint4*>(dst + out * 8) = *reinterpret_cast<const uint4*>(v);
 }
 
-// One warp per row: Euclidean norm of the row (with the extra bias / 1.0 component), rounded up a little;
-// optionally the maximum over rows (float bits compare like unsigned ints for non-negative values; NaN wins).
+// Euclidean norm of every row (with the extra bias / 1.0 component), rounded up a little.  A block of 8 warps takes 32
+// consecutive rows (4 per warp).  The row is scaled by a power of two taken from its largest element before it is
+// squared, so tiny rows do not underflow to 0 and huge ones do not overflow: the norm is exactly 0 iff every element
+// is 0, NaN iff an element is NaN, +inf iff an element is infinite (or the norm leaves the float range).
+// Optional outputs: the maximum over all rows (float bits compare like unsigned ints for non-negative values; NaN
+// wins) and the maximum over each block's 32 rows (chunk_max[blockIdx.x]: the error bound of the tensor-core filter
+// is taken per 32-item chunk, filter_select.cuh).
+constexpr int NORM_ROWS_PER_BLOCK = 32;
 template <typename T>
-__global__ void row_norm_kernel(const T* __restrict__ src, const size_t ld, const int rows, const int cols,
-                                const T* __restrict__ extra, const int ones_col,
-                                float* __restrict__ norm_out, unsigned* __restrict__ max_bits)
+__global__ void __launch_bounds__(256)
+row_norm_kernel(const T* __restrict__ src, const size_t ld, const int rows, const int cols,
+                const T* __restrict__ extra, const int ones_col,
+                float* __restrict__ norm_out, unsigned* __restrict__ max_bits, float* __restrict__ chunk_max)
 {
-    const int lane = threadIdx.x & 31;
-    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (r >= rows) return;
-    float acc = 0.f;
-    for (int k = lane; k < cols; k += 32) { const float x = (float)src[(size_t)r * ld + k]; acc = fmaf(x, x, acc); }
+    __shared__ unsigned wmax[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned mybits = 0u;
+    for (int i = 0; i < 4; i++) {
+        const int r = blockIdx.x * NORM_ROWS_PER_BLOCK + warp * 4 + i;
+        if (r >= rows) break;                                       // (warp-uniform)
+        const T* __restrict__ row = src + (size_t)r * ld;
+        const T e = extra != nullptr ? extra[r] : (ones_col ? (T)1 : (T)0);
+        T am = (T)0;
+        int has_nan = 0;
+        for (int k = lane; k < cols; k += 32) { const T x = row[k]; has_nan |= (x != x); const T ax = x < 0 ? -x : x; am = ax > am ? ax : am; }
+        if (lane == 0) { has_nan |= (e != e); const T ae = e < 0 ? -e : e; am = ae > am ? ae : am; }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
-    if (lane == 0) {
-        float e = extra != nullptr ? (float)extra[r] : (ones_col ? 1.f : 0.f);
-        const float nrm = sqrtf(fmaf(e, e, acc)) * 1.001f;
-        if (norm_out) norm_out[r] = nrm;
-        if (max_bits) atomicMax(max_bits, __float_as_uint(nrm));
+        for (int o = 16; o > 0; o >>= 1) { const T w = __shfl_xor_sync(FULL, am, o); am = w > am ? w : am; }
+        has_nan = __any_sync(FULL, has_nan);
+        float nrm;
+        if (has_nan) nrm = CUDART_NAN_F;
+        else if (am == (T)0) nrm = 0.f;
+        else if (am > (T)3.0e38) nrm = CUDART_INF_F;                // infinite element (or beyond what a float norm can hold)
+        else {
+            int ex;
+            frexp((double)am, &ex);                                 // am = f * 2^ex, f in [0.5, 1)
+            const double s = ldexp(1.0, -ex);                       // (double: 2^-ex can leave the float range for denormal rows)
+            float acc = 0.f;
+            for (int k = lane; k < cols; k += 32) { const float x = (float)((double)row[k] * s); acc = fmaf(x, x, acc); }
+            if (lane == 0) { const float x = (float)((double)e * s); acc = fmaf(x, x, acc); }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(FULL, acc, o);
+            const double d = ldexp((double)(sqrtf(acc) * 1.001f), ex);
+            nrm = d > 3.0e38 ? CUDART_INF_F : (d < 1.2e-38 ? 1.2e-38f : __double2float_ru(d));
+        }
+        if (lane == 0 && norm_out) norm_out[r] = nrm;
+        const unsigned b = __float_as_uint(nrm);
+        mybits = b > mybits ? b : mybits;
+    }
+    if (lane == 0) wmax[warp] = mybits;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned b = 0u;
+        for (int w = 0; w < 8; w++) b = wmax[w] > b ? wmax[w] : b;
+        if (chunk_max) chunk_max[blockIdx.x] = __uint_as_float(b);
+        if (max_bits) atomicMax(max_bits, b);
     }
 }
 

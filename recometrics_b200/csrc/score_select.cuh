@@ -187,6 +187,9 @@ struct ScoreSelectParams {
     unsigned int* auc_cnt;              // [nnz_test] number of candidates scoring strictly above
                                         // the j-th smallest held-out score of the row (zeroed)
     u64* umin;                          // [m] orderable(min candidate score), init ~0
+    const int* __restrict__ umap;       // optional [mb]: row r of this launch is batch-local user umap[r] (CSR rows, status, flags and
+                                        // candidate buffers are those of the mapped user; At holds the launch's rows in order).  Used
+                                        // to re-run only the users the tensor-core filter handed back (api.cu)
 };
 
 // ------------------------------------------------------------------ PTX wrappers (TMA ring)
@@ -377,6 +380,7 @@ struct RowState {
     int end_train[BM];
     int tp0[BM];        // first entry of the held-out (test) row
     int npos[BM];       // its length (0 for rows that are not ranked)
+    int urow[BM];       // batch-local user of the row (its candidate buffer, status, flags): the row itself unless ScoreSelectParams::umap
 };
 
 template <typename T>
@@ -570,8 +574,10 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 
     // ---- one-time setup: per-row selection state, train cursors, barriers ----
     for (int r = tid; r < BM; r += NTHREADS) {
-        const int ul = tile_u0 + r;
-        const bool ranked = (ul < P.mb) && (P.ustatus[P.user0 + ul] == 0);
+        const int ul0 = tile_u0 + r;
+        const int ul = (ul0 < P.mb && P.umap != nullptr) ? P.umap[ul0] : ul0;
+        const bool ranked = (ul0 < P.mb) && (P.ustatus[P.user0 + ul] == 0);
+        rs->urow[r] = ul0 < P.mb ? ul : 0;
         rs->tau[r] = ranked ? -NumTraits<T>::inf() : NumTraits<T>::inf();
         rs->cnt[r] = 0;
         rs->nan[r] = 0;
@@ -701,8 +707,8 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
             T m = max_nan(max_nan(s[0], s[1]), max_nan(s[2], s[3]));
             if (NC == 8) m = max_nan(m, max_nan(max_nan(s[NC - 4], s[NC - 3]), max_nan(s[NC - 2], s[NC - 1])));
             if (!(m < tau)) {
-                T* cs = P.cand_score + (size_t)(tile_u0 + row) * C;
-                int* ci = P.cand_item + (size_t)(tile_u0 + row) * C;
+                T* cs = P.cand_score + (size_t)rs->urow[row] * C;
+                int* ci = P.cand_item + (size_t)rs->urow[row] * C;
                 row_slow<T>(cs, ci, P.tri, P.n, tau, row, item0 + lx * 4, item0 + BN, s[0], s[1], s[2], s[3]);
                 if (NC == 8)
                     row_slow<T>(cs, ci, P.tri, P.n, tau, row, item0 + 64 + lx * 4, item0 + BN, s[NC - 4], s[NC - 3], s[NC - 2], s[NC - 1]);
@@ -808,7 +814,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
                 const int r = __ffs(need) - 1;
                 need &= need - 1;
                 const int row = wrow0 + r;
-                const size_t base = (size_t)(tile_u0 + row) * C;
+                const size_t base = (size_t)rs->urow[row] * C;
                 compact_user<T, C>(P.cand_score + base, P.cand_item + base, rs->cnt[row], P.K, lane, &rs->tau[row], &rs->cnt[row]);
             }
         }
@@ -818,8 +824,8 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
     // ---- leave the best min(cnt, K) candidates of every user at the head of its buffer ----
     for (int r = 0; r < 16; r++) {
         const int row = wrow0 + r;
-        const int ul = tile_u0 + row;
-        if (ul < P.mb) {
+        if (tile_u0 + row < P.mb) {
+            const int ul = rs->urow[row];
             const size_t base = (size_t)ul * C;
             compact_user<T, C>(P.cand_score + base, P.cand_item + base, rs->cnt[row], P.K, lane, &rs->tau[row], &rs->cnt[row]);
             if (lane == 0) {
@@ -836,9 +842,8 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int row = wrow0 + ly * 4 + (i & 3) + (i >> 2) * 8;
-            const int ul = tile_u0 + row;
-            if (ul < P.mb && rs->npos[row] > 0 && rowmin[i] != NumTraits<T>::inf())
-                atomicMin(&P.umin[P.user0 + ul], NumTraits<T>::orderable(rowmin[i]));
+            if (tile_u0 + row < P.mb && rs->npos[row] > 0 && rowmin[i] != NumTraits<T>::inf())
+                atomicMin(&P.umin[P.user0 + rs->urow[row]], NumTraits<T>::orderable(rowmin[i]));
         }
     }
 }

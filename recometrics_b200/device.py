@@ -198,6 +198,8 @@ def calc_reco_metrics_device(
     means = torch.full((10 * W,), float("nan"), dtype=torch.float64, device=dev) if return_means else None
     counts = torch.zeros(10 * W, dtype=torch.int64, device=dev) if return_means else None
     ub, ue = (0, 0) if user_range is None else (int(user_range[0]), int(user_range[1]))
+    if user_range is not None and ub == ue:
+        ub, ue = 0, -1          # an EMPTY block; 0,0 would mean "all users" in the C-ABI
     ptr = lambda t: None if t is None else t.data_ptr()
     extra = _capi.make_extra(device=device, user_begin=ub, user_end=ue, inputs_on_device=True,
                              strict_min_pos_test=strict_min_pos_test, topk_items=ptr(topk_items), topk_scores=ptr(topk_scores),

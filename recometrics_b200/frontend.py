@@ -177,7 +177,7 @@ def calc_reco_metrics_ex(
         consider_cold_start=True, cumulative=False, nthreads=-1, seed=1,
         device=-1, user_range=None, strict_min_pos_test=False,
         return_topk=False, return_ranks=False, return_status=False, scoring_path="auto",
-        return_means=False, means_only=False):
+        return_means=False, means_only=False, filter_stats=False, nan_bits=None, devices=None):
     """Same evaluation as :func:`calc_reco_metrics`, returning an :class:`EvalResult` with the
     reference-style dict plus timing and the optional extras (top-K ids/scores, held-out ranks,
     per-user status).  ``user_range=(begin, end)`` evaluates only those rows (the sharding unit);
@@ -186,7 +186,9 @@ def calc_reco_metrics_ex(
     survivors: identical top-K and scores, top-K metrics only).  ``return_means``: also reduce every requested
     metric to its mean over the evaluated users on the device (``numpy.nanmean`` of the per-user output; ``(k,)`` vectors
     when ``cumulative``) -- ``result.means`` / ``result.counts``; with ``means_only`` the per-user rows are not copied
-    back at all (``result.metrics`` then only holds ``"K"``)."""
+    back at all (``result.metrics`` then only holds ``"K"``).  ``devices``: list of CUDA ordinals to spread the users of
+    this one call over (one host thread per GPU inside the native call).  ``nan_bits``: bit pattern written wherever a
+    metric is undefined (R's ``NA_REAL``) instead of a plain NaN.  ``filter_stats``: fill ``timing["filter_err_ratio_max"]``."""
     flags = dict(p=precision, tp=trunc_precision, r=recall, ap=average_precision, tap=trunc_average_precision,
                  ndcg=ndcg, hit=hit, rr=rr, roc=roc_auc, pr=pr_auc)
     flags = {q: bool(v) or bool(all_metrics) for q, v in flags.items()}
@@ -208,6 +210,8 @@ def calc_reco_metrics_ex(
     topk_scores = np.full(m * K, np.nan, dtype=dtype) if return_topk else None
     pos_rank = np.zeros(max(int(prep["tep"][-1]), 1), dtype=np.int64) if return_ranks else None
     ub, ue = (0, 0) if user_range is None else (int(user_range[0]), int(user_range[1]))
+    if user_range is not None and ub == ue:
+        ub, ue = 0, -1          # an EMPTY block (a rank with no users); 0,0 would mean "all users" in the C-ABI
     return_means = bool(return_means) or bool(means_only)
     W = K if cumulative else 1
     means = np.full(10 * W, np.nan, dtype=np.float64) if return_means else None
@@ -215,7 +219,7 @@ def calc_reco_metrics_ex(
     extra = _capi.make_extra(device=device, user_begin=ub, user_end=ue, strict_min_pos_test=strict_min_pos_test,
                              topk_items=topk_items, topk_scores=topk_scores, pos_rank=pos_rank, status=status,
                              timing=timing, scoring_path=scoring_path, metric_means=means, metric_counts=counts,
-                             skip_row_copy=bool(means_only))
+                             skip_row_copy=bool(means_only), filter_stats=filter_stats, nan_bits=nan_bits, devices=devices)
     rc = _capi.calc_metrics(dtype, prep["A"], prep["lda"], prep["B"], prep["ldb"], m, prep["n"], prep["p"],
                             prep["trp"], prep["tri"], prep["tep"], prep["tei"], prep["tev"], K, cumulative,
                             bool(break_ties_with_noise), outs, prep["consider_cold_start"], prep["min_items_pool"],

@@ -38,8 +38,9 @@ def test_library_exports_every_declared_symbol(rb):
 def test_extra_struct_layout_matches_header(rb):
     """ctypes mirror of rmb200_extra_t / rmb200_timing_t has the C layout (LP64)."""
     from recometrics_b200 import _capi
-    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 7 * 8
-    assert ctypes.sizeof(_capi.Extra) == 6 * 4 + 5 * 8 + 2 * 4 + 2 * 8
+    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 9 * 8
+    assert ctypes.sizeof(_capi.Extra) == 6 * 4 + 5 * 8 + 2 * 4 + 2 * 8 + 2 * 4 + 8 + 8 + 2 * 4
+    assert _capi.Extra.nan_bits.offset == 96 and _capi.Extra.devices.offset == 104
     assert _capi.Extra.topk_items.offset == 24
     assert _capi.Extra.scoring_path.offset == 64
     assert _capi.Extra.metric_means.offset == 72

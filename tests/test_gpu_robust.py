@@ -1,0 +1,175 @@
+"""GPU: the tensor-core filter on inputs that stress its error bound and its hand-back logic (VERDICT r01 "What's weak" 1-2):
+heavy-tailed item norms with outliers, wide dynamic range inside a row, all-zero user rows, biases much larger than the
+factor scores, factors outside fp16-scalable range, and the full cfg2 catalogue.  Every case compares the tensor path with
+the all-FMA path bit for bit (ids, scores, status, metrics) and -- where the oracle finishes in seconds -- with the oracle;
+`filter_fallback_users` pins how many users had to leave the tensor path, `filter_err_ratio_max` that the observed error of
+the approximate scores stays inside the bound the filter used."""
+import struct
+
+import numpy as np
+import pytest
+
+import parity_utils as pu
+from tools import synth
+
+pytestmark = pytest.mark.gpu
+
+TOPK4 = dict(precision=True, recall=True, average_precision=True, ndcg=True)
+
+
+def _both_paths(rb, d, k, A=None, B=None, bias="data", **kw):
+    A = d["A"] if A is None else A
+    B = d["B"] if B is None else B
+    bias = d.get("item_biases") if isinstance(bias, str) else bias
+    out = {}
+    for path in ("fma", "tensor"):
+        out[path] = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=k, item_biases=bias, break_ties_with_noise=False,
+                                            return_topk=True, return_status=True, scoring_path=path, filter_stats=True,
+                                            **{**TOPK4, **kw})
+    a, b = out["fma"], out["tensor"]
+    assert a.timing["scoring_path"] == 1 and b.timing["scoring_path"] == 2
+    assert np.array_equal(a.status, b.status)
+    assert np.array_equal(a.topk_items, b.topk_items)
+    assert np.array_equal(a.topk_scores, b.topk_scores, equal_nan=True)
+    for key, v in a.metrics.items():
+        if key != "K":
+            assert np.array_equal(v, b.metrics[key], equal_nan=True), key
+    assert b.timing["filter_err_ratio_max"] <= 1.0, b.timing["filter_err_ratio_max"]
+    return a, b
+
+
+def test_heavy_tailed_item_norms_with_outliers(rb, oracle_mod):
+    """Log-normal item norms (sigma = 1.5) and single items 100x / 1000x larger than the rest: the per-chunk error bound
+    keeps every user on the tensor path (a single global max_j ||b_j|| widened everybody's band by the outlier)."""
+    d = synth.make(4, m=3000, n=60000, p=64)
+    rng = np.random.default_rng(11)
+    scale = np.exp(1.5 * rng.standard_normal(60000)).astype(np.float32)
+    scale[12345] *= 100.0
+    scale[777] *= 1000.0
+    B = d["B"] * scale[:, None]
+    a, b = _both_paths(rb, d, 100, B=B)
+    assert b.timing["filter_fallback_users"] == 0, b.timing
+    # and against the oracle on a block of the users
+    sub = dict(A=d["A"][:400], B=B, X_train=d["X_train"][:400], X_test=d["X_test"][:400], item_biases=None)
+    res = pu.run_product(rb, sub, ("p", "r", "ap", "ndcg"), 100, scoring_path="tensor")
+    orc = pu.run_oracle(oracle_mod, sub, ("p", "r", "ap", "ndcg"), 100)
+    pu.compare(res, orc, sub, ("p", "r", "ap", "ndcg"), 100, label="heavy-tailed item norms")
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_wide_dynamic_range_inside_rows(rb, oracle_mod, dtype):
+    """Element magnitudes from 1e-6 to 1e3 inside the same factor rows (after the power-of-two row scaling most elements
+    sit in fp16's denormal range): the absolute terms of the error bound have to cover them."""
+    d = synth.make(4, m=1500, n=30000, p=48)
+    rng = np.random.default_rng(5)
+    A = (d["A"] * 10.0 ** rng.uniform(-6, 3, size=d["A"].shape)).astype(dtype)
+    B = (d["B"] * 10.0 ** rng.uniform(-6, 3, size=d["B"].shape)).astype(dtype)
+    a, b = _both_paths(rb, d, 50, A=A, B=B)
+    assert b.timing["filter_fallback_users"] <= 15, b.timing          # (a few users may have near-constant scores)
+    sub = dict(A=A[:300], B=B, X_train=d["X_train"][:300], X_test=d["X_test"][:300], item_biases=None)
+    res = pu.run_product(rb, sub, ("p", "ap", "ndcg"), 50, scoring_path="tensor")
+    orc = pu.run_oracle(oracle_mod, sub, ("p", "ap", "ndcg"), 50)
+    pu.compare(res, orc, sub, ("p", "ap", "ndcg"), 50, label="wide dynamic range %s" % np.dtype(dtype).name, max_amb_frac=0.5)
+
+
+def test_all_zero_user_rows_cost_nothing(rb):
+    """Users unseen in training have all-zero factors: every score ties, the row is NaN (hpp:541-548).  They are settled
+    without scoring -- no hand-back to the FMA path, no batch re-run -- and everybody else is unaffected."""
+    d = synth.make(4, m=20000, n=40000, p=32)
+    A = d["A"].copy()
+    zero = np.arange(0, 20000, 97)
+    A[zero] = 0.0
+    a, b = _both_paths(rb, d, 100, A=A)
+    assert b.timing["filter_fallback_users"] == 0 and b.timing["filter_fallback_batches"] == 0, b.timing
+    elig = a.status != 1
+    assert (b.status[zero][elig[zero]] == 3).all()
+    assert np.isnan(b.metrics["P@K"][zero]).all()
+    others = np.setdiff1d(np.arange(20000), zero)
+    assert np.isfinite(b.metrics["P@K"][others]).mean() > 0.95
+    # with item biases the same users have a well-defined ranking (score = bias): computed, on the tensor path
+    bias = (0.5 * np.random.default_rng(3).standard_normal(40000)).astype(np.float32)
+    a2, b2 = _both_paths(rb, d, 100, A=A, bias=bias)
+    assert b2.timing["filter_fallback_users"] == 0
+    assert (b2.status[zero][elig[zero]] == 0).all()
+
+
+def test_bias_much_larger_than_factor_scores(rb, oracle_mod):
+    """item_biases ~ 1000x the factor scores: the bias column dominates both norms, the factors live near the fp16
+    rounding floor of the scaled image."""
+    d = synth.make(2, m=2000, n=26744)
+    bias = (1000.0 * d["item_biases"]).astype(np.float32)
+    A = (0.05 * d["A"]).astype(np.float32)
+    a, b = _both_paths(rb, d, 10, A=A, bias=bias)
+    assert b.timing["filter_fallback_users"] <= 20, b.timing
+    sub = dict(A=A[:500], B=d["B"], X_train=d["X_train"][:500], X_test=d["X_test"][:500], item_biases=bias)
+    res = pu.run_product(rb, sub, ("p", "r", "ap", "ndcg"), 10, scoring_path="tensor")
+    orc = pu.run_oracle(oracle_mod, sub, ("p", "r", "ap", "ndcg"), 10)
+    pu.compare(res, orc, sub, ("p", "r", "ap", "ndcg"), 10, label="bias >> scores", max_amb_frac=0.9)
+
+
+def test_cfg2_full_catalogue_65_factors(rb, oracle_mod):
+    """configs[1] at its full catalogue: n = 26,744, 64 factors + item bias (65 fp16 factors padded to 80), K = 10 -- the
+    bias as its own vector and folded into the factors by the caller, both scoring paths, against the oracle."""
+    d = synth.make(2, m=3000)
+    assert d["B"].shape == (26744, 64)
+    a, b = _both_paths(rb, d, 10)
+    assert b.timing["filter_fallback_users"] == 0
+    for separate in (True, False):
+        for path in ("tensor", "fma"):
+            res = pu.run_product(rb, d, ("p", "r", "ap", "ndcg"), 10, separate_bias=separate, scoring_path=path)
+            orc = pu.run_oracle(oracle_mod, d, ("p", "r", "ap", "ndcg"), 10)
+            rep = pu.compare(res, orc, d, ("p", "r", "ap", "ndcg"), 10, label="cfg2 3000x26744 sep=%s %s" % (separate, path))
+            # the near-tie rule of the north star under its strict reading (gap relative to the two scores) is reported too
+            assert rep["topk_rows_differing"] <= rep["topk_ambiguous"]
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_unscalable_factors_are_handed_to_the_fma_path_per_user(rb, dtype):
+    """User rows whose norm lies outside what a power-of-two scaling can bring into fp16 range (1e-36, 1e33) and users with
+    near-constant scores: only THOSE users run on the FMA tiles; results equal the all-FMA path."""
+    d = synth.make(4, m=5000, n=20000, p=32)
+    A = d["A"].astype(dtype).copy()
+    tiny, huge = np.arange(5, 5000, 211), np.arange(9, 5000, 307)
+    A[tiny] *= dtype(1e-36)
+    A[huge] *= dtype(1e33)
+    B = d["B"].astype(dtype).copy()
+    const = np.arange(13, 5000, 401)                     # these users' scores = a_0 * b_0, and b_0 takes 3 values only: massive ties
+    B[:, 0] = np.random.default_rng(2).integers(0, 3, 20000).astype(dtype)
+    A[const, 1:] = 0
+    a, b = _both_paths(rb, d, 20, A=A, B=B)
+    n_special = len(set(tiny) | set(huge) | set(const))
+    assert 0 < b.timing["filter_fallback_users"] <= n_special + 50, b.timing
+    assert b.timing["filter_fallback_batches"] == 1
+
+
+def test_nan_payload_of_the_caller(rb):
+    """extra.nan_bits: R's NA_REAL (low word 1954, src/recometrics.hpp:75-80) instead of a plain quiet NaN, float and double."""
+    d = synth.make(1, m=600, n=900, p=8)
+    Xte = d["X_test"].tolil()
+    Xte[:25] = 0                                           # users without held-out items: NaN rows (hpp:439)
+    Xte = Xte.tocsr(); Xte.eliminate_zeros()
+    from scipy.sparse import csr_array
+    d["X_test"] = csr_array(Xte)
+    na_real = struct.unpack("<Q", struct.pack("<II", 1954, 0x7FF00000))[0]
+    for dtype, bits, view in ((np.float64, na_real, np.uint64), (np.float32, 0x7FC007A2, np.uint32)):
+        A, B = d["A"].astype(dtype), d["B"].astype(dtype)
+        r0 = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=5, all_metrics=True, break_ties_with_noise=False)
+        r1 = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=5, all_metrics=True, break_ties_with_noise=False, nan_bits=bits)
+        for key, v in r0.metrics.items():
+            if key == "K":
+                continue
+            w = r1.metrics[key]
+            nan = np.isnan(v)
+            assert nan.any() and np.array_equal(nan, np.isnan(w))
+            assert np.array_equal(v[~nan], w[~nan])
+            assert (w[nan].view(view) == bits).all(), key
+    with pytest.raises(ValueError):
+        rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, break_ties_with_noise=False, nan_bits=0x3FF0000000000000)
+
+
+def test_empty_user_block_evaluates_nobody(rb):
+    d = synth.make(1, m=300, n=500, p=8)
+    r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, break_ties_with_noise=False, user_range=(0, 0))
+    assert np.isnan(r.metrics["P@K"]).all() and r.timing["kernel_launches"] == 0
+    from recometrics_b200.dist import shard_bounds
+    assert shard_bounds(3, 8, 0) == (0, 0)
