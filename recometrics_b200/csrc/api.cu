@@ -749,14 +749,16 @@ int run_call(const CallArgs<T>& a)
             int r = 0;
             while (r < 4096) { cdf += term; r++; term *= lam / r; if (1.0 - cdf <= 1e-6) break; }
             if (const char* env = std::getenv("RMB200_SAMPLE_RANK")) { const int v = std::atoi(env); if (v >= 1) r = v; }
-            if (ns >= 8 && r + 128 <= C - 128) { f_sample_tiles = ns; f_sample_stride = stride; f_sample_rank = r; }
+            // (the guess is the r-th largest of up to min(C / 4, 128) group maxima of the sample, filter_select.cuh)
+            const int groups = (C / 4 < 128 ? C / 4 : 128) < ns ? (C / 4 < 128 ? C / 4 : 128) : ns;
+            if (ns >= 8 && 2 * r <= groups) { f_sample_tiles = ns; f_sample_stride = stride; f_sample_rank = r; }
         }
     }
     if (use_tensor) {
         CK(d_Ab.alloc((size_t)UB * KB * sizeof(__half)));
         CK(d_anorm.alloc((size_t)UB * sizeof(float)));
         CK(d_capx.alloc((size_t)UB * C * sizeof(uint2)));
-        CK(d_overflow.alloc(8 * sizeof(int)));     // [0] users handed back to the FMA path, [1] users that took the retry pass, [6] length of the hand-back list
+        CK(d_overflow.alloc(40 * sizeof(int)));    // [0] users handed back to the FMA path, [1] users that took the retry pass, [6] length of the hand-back list, [8..] cycle counters (stats builds)
         CK(d_fb_list.alloc((size_t)UB * sizeof(int)));
     }
     // upload of users [b0, b0 + UB) into staging buffer `slot`, on the prefetch stream
@@ -884,7 +886,7 @@ int run_call(const CallArgs<T>& a)
             pack_f16_kernel<T><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(Asrc, Ald, nb, a.k, (const T*)nullptr, a.bias ? 1 : 0,
                                                                                 d_anorm.as<float>(), nullptr, d_Ab.as<__half>(), nb_pad, KB);
             CK(cudaGetLastError());
-            CK(cudaMemsetAsync(d_overflow.p, 0, 8 * sizeof(int), st));
+            CK(cudaMemsetAsync(d_overflow.p, 0, 40 * sizeof(int), st));
             tm.kernel_launches += 2;
             pt.stop(tm.prep_ms);
             pt.start();
@@ -918,13 +920,20 @@ int run_call(const CallArgs<T>& a)
             CK(launch_exact_topk<T>(d_capx.as<uint2>(), d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, b0, d_At.as<T>(), p_pad, a.k,
                                     Bsrc, Bld, bias_d, d_flags.as<int>(), K, nz, es, st));
             tm.kernel_launches++;
-            int over_retry[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-            CK(cudaMemcpyAsync(over_retry, d_overflow.p, 8 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            int over_retry[40] = {0};
+            CK(cudaMemcpyAsync(over_retry, d_overflow.p, 40 * sizeof(int), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
 #if RMB_F_STATS
             std::fprintf(stderr, "[rmb200 stats] users %d: appends/user %.1f cuts/user %.2f slow-path entries/user %.1f cursor moves/user %.1f retries %d handed back %d (sample tiles %d stride %d rank %d)\n",
                          nb, over_retry[2] / (double)nb, over_retry[3] / (double)nb, over_retry[4] / (double)nb, over_retry[5] / (double)nb,
                          over_retry[1], over_retry[0], f_sample_tiles, f_sample_stride, f_sample_rank);
+            {
+                const unsigned long long* ck = reinterpret_cast<const unsigned long long*>(over_retry + 8);
+                const double nc = (double)(nb_pad / BM);
+                for (int ps = 0; ps < 2; ps++)
+                    std::fprintf(stderr, "[rmb200 stats]   pass %d, one epilogue warp, kcycles per CTA: wait acc %.0f, ld+fast %.0f, append %.0f, cursor %.0f, meet+cut %.0f, total %.0f\n",
+                                 ps, ck[ps * 6 + 0] / nc / 1e3, ck[ps * 6 + 1] / nc / 1e3, ck[ps * 6 + 2] / nc / 1e3, ck[ps * 6 + 3] / nc / 1e3, ck[ps * 6 + 4] / nc / 1e3, ck[ps * 6 + 5] / nc / 1e3);
+            }
 #endif
             const int n_over = over_retry[0];
             tm.filter_retry_rows += over_retry[1];

@@ -68,6 +68,15 @@ constexpr int F_CHUNK = 32;              // TMEM columns per tcgen05.ld
 #define RMB_F_CUT_MARGIN 48               // a row's regions are cut back together once they hold this many more than the last cut kept
 #endif
 constexpr int F_CUT_MARGIN = RMB_F_CUT_MARGIN;
+#ifndef RMB_F_MAIN_MARGIN
+#define RMB_F_MAIN_MARGIN 250              // ... in the pass that starts from the sampled guess: its thresholds are tight from the first tile on, a cut
+                                           // (which stalls its warp and soon the CTA's pipeline) buys little there (A/B on B200: 52 -> 47.4 ms per batch)
+#endif
+constexpr int F_MAIN_MARGIN = RMB_F_MAIN_MARGIN;
+#ifndef RMB_F_COMPACT_AT
+#define RMB_F_COMPACT_AT 0                // a cut compacts the row's regions only when one of them holds more than this (0: every cut compacts)
+#endif
+constexpr int F_COMPACT_AT = RMB_F_COMPACT_AT;
 #ifndef RMB_F_MAX_MEET
 #define RMB_F_MAX_MEET 64                 // most item tiles between two meetings of a quarter's warps
 #endif
@@ -87,8 +96,15 @@ constexpr int F_MAX_MEET = RMB_F_MAX_MEET;
 #endif
 #if RMB_F_STATS
 #define F_STAT(i, v) atomicAdd(&rs->stat[i], (v))
+#define F_CLK(var) const long long var = clock64()
+#define F_CLK_ADD(i, a, b) do { if (warp == RMB_F_STAT_WARP && lane == 0) clk[i] += (b) - (a); } while (0)
 #else
 #define F_STAT(i, v) do { } while (0)
+#define F_CLK(var) do { } while (0)
+#define F_CLK_ADD(i, a, b) do { } while (0)
+#endif
+#ifndef RMB_F_STAT_WARP
+#define RMB_F_STAT_WARP 5
 #endif
 
 struct FilterParams {
@@ -131,7 +147,6 @@ struct FilterRowState {      // per user row of the CTA, shared by the four epil
     int interval[F_EPI_WARPS];       // per warp: tiles between its last two meetings
     int retry;                       // some row of the CTA needs the retry pass
     int stat[4];                     // RMB_F_STATS: appends, cuts, slow-path entries (8-column groups), cursor moves
-    unsigned hist[F_EPI_WARPS][32];  // bucket counters of cut_regions, one set per epilogue warp
 };
 
 
@@ -213,102 +228,76 @@ __device__ __forceinline__ void tmem_ld32(const unsigned taddr, unsigned (&r)[32
 // error bound of an approximate score of a row (ca, efl) against an item of a chunk with largest norm cn, rounded up
 __device__ __forceinline__ float filter_err(const float ca, const float cn, const float efl) { return __fmaf_ru(ca, cn, efl); }
 
-// One warp: cut a row's candidates back to those that can still belong to the exact top K.  Every candidate's exact
-// score lies in [lb, ub] = [approx - e, approx + e] (e from its item's chunk norm).  tau' = the K-th best lower bound;
-// kept: KEEP_LB ? lb >= tau' (sample pass: the K best lower bounds themselves) : ub >= tau' (whatever can still reach
-// the exact top K).  The row's buffer is four regions of C/4 entries (one per epilogue warp of the quarter), region s
-// holding cnt4[s] entries; all of them are read into registers first, so the survivors can be written back in place:
-// CONTIG ? packed at the head of the buffer : dealt round-robin over the four regions.
-// tau' is found by ROUNDS rounds of a 32-bucket histogram (shared-memory counters, one bucket per lane, suffix sums by
-// shuffles) that narrow a window [lo, lo + span] of the key range around it.  The window's lower edge always satisfies
-// #(lb key >= lo) >= K, so it is a valid (slightly low: window width = key range / 32^ROUNDS) stand-in for tau';
-// ROUNDS = 7 exhausts 32-bit keys and makes it exact.  K <= total entries is required.
+// One warp: cut a row's candidates back to those that can still belong to the exact top K.  Every candidate carries the
+// LOWER bound lb = approx - e of its exact score (e from its item's chunk norm); its upper bound is lb + 2e.
+// tau' = the K-th best lower bound; kept: KEEP_LB ? lb >= tau' (sample pass: the K best lower bounds themselves) :
+// ub >= tau' (whatever can still reach the exact top K).  The row's buffer is four regions of C/4 entries (one per
+// epilogue warp of the quarter), region s holding cnt4[s] entries; all of them are read into registers first, so the
+// survivors can be written back in place: CONTIG ? packed at the head of the buffer : dealt round-robin over the regions.
+// tau' is found by bisection on the order-preserving keys: BITS halvings of [min key, max key], each one a count of the
+// keys at or above the probe (compare + warp REDUX).  The interval's lower end always satisfies #(lb key >= lo) >= K,
+// so it is a valid (slightly low: interval width = key range / 2^BITS) stand-in for tau'; BITS = 32 makes it exact.
+// A cut stalls its warp -- and, once the four accumulator buffers have run full, the whole CTA -- for its duration:
+// one load phase, no shared-memory traffic, no shuffles inside the search.  K <= total entries is required.
+// compact = false: only the bound is refreshed, the regions stay as they are.
 // Returns the number kept; *tau_out = (the stand-in for) tau'.
-#ifndef RMB_F_HIST_ROUNDS
-#define RMB_F_HIST_ROUNDS 2
+#ifndef RMB_F_CUT_BITS
+#define RMB_F_CUT_BITS 10
 #endif
-template <int C, int ROUNDS, bool CONTIG>
+template <int C, int BITS, bool CONTIG>
 __device__ __noinline__ int cut_regions(uint2* cd, const int c0, const int c1, const int c2, const int c3, const int K,
                                         const float ca, const float efl, const float* __restrict__ chunk_norm, const bool keep_lb,
-                                        const int lane, unsigned* hist, float* tau_out)
+                                        const bool compact, const int lane, float* tau_out)
 {
     constexpr int E = C / 32, RC = C / 4, EPR = E / 4;      // entries per lane, region capacity, per-lane entries per region
-    // (register budget: this function is called from the tile loop.  Only the lower-bound keys live through the rounds;
-    //  the entries are read again for the write-back, and only those below the cut need their error bound.)
     const int ns = (max(max(c0, c1), max(c2, c3)) + 31) >> 5;      // occupied 32-entry slots per region (warp-uniform): the rest is skipped
     unsigned lbk[E];                                        // lower-bound key, 0 = empty slot (the key of -inf is 0x007fffff)
+    int it[E];
     unsigned kmax = 0u, kmin = 0xffffffffu;
 #pragma unroll
     for (int e = 0; e < E; e++) {
-        lbk[e] = 0u;
+        lbk[e] = 0u; it[e] = 0;
         if ((e % EPR) < ns) {
             const int region = e / EPR, pos = (e % EPR) * 32 + lane;
             const int cr = region == 0 ? c0 : (region == 1 ? c1 : (region == 2 ? c2 : c3));
             if (pos < cr) {
-                lbk[e] = NumTraits<float>::key(__uint_as_float(cd[region * RC + pos].x));
+                const uint2 c = cd[region * RC + pos];
+                lbk[e] = NumTraits<float>::key(__uint_as_float(c.x));
+                it[e] = (int)c.y;
                 kmax = max(kmax, lbk[e]); kmin = min(kmin, lbk[e]);
             }
         }
     }
     kmax = __reduce_max_sync(FULL, kmax);
     kmin = __reduce_min_sync(FULL, kmin);
-    unsigned lo = kmin, span = kmax - kmin;     // window [lo, lo + span]; the need-th largest lb key inside it is wanted
-    int need = K;
+    unsigned lo = kmin, hi = kmax;              // #(key >= lo) >= K always; the K-th largest key lies in [lo, hi]
 #pragma unroll 1
-    for (int round = 0; round < ROUNDS; round++) {
-        const int sh = max(0, 27 - __clz(span));               // (key - lo) >> sh < 32 inside the window
-        hist[lane] = 0u;
-        __syncwarp();
+    for (int step = 0; step < BITS && lo < hi; step++) {
+        const unsigned mid = lo + ((hi - lo + 1u) >> 1);
+        int c = 0;
 #pragma unroll
-        for (int e = 0; e < E; e++) {
-            if ((e % EPR) < ns) {
-                const unsigned d = lbk[e] - lo;
-                if (lbk[e] != 0u && lbk[e] >= lo && d <= span) atomicAdd(&hist[d >> sh], 1u);
-            }
-        }
-        __syncwarp();
-        unsigned suf = hist[lane];                             // -> number of window keys in buckets >= lane
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_down_sync(FULL, suf, o);
-            if (lane + o < 32) suf += t;
-        }
-        const unsigned mask = __ballot_sync(FULL, (int)suf >= need);   // lane 0 always votes: the window holds >= need keys
-        const int b = 31 - __clz(mask);
-        const unsigned above = __shfl_sync(FULL, suf, (b + 1) & 31);
-        if (b < 31) need -= (int)above;
-        const unsigned off = (unsigned)b << sh;
-        lo += off;
-        span = min(span - off, (1u << sh) - 1u);
-        if (sh == 0) break;
+        for (int e = 0; e < E; e++)
+            if ((e % EPR) < ns) c += (lbk[e] >= mid) ? 1 : 0;
+        c = __reduce_add_sync(FULL, c);
+        if (c >= K) lo = mid; else hi = mid - 1u;
     }
     const float tau = NumTraits<float>::from_orderable((u64)lo);
+    *tau_out = tau;
+    if (!compact) { __syncwarp(); return c0 + c1 + c2 + c3; }      // bound refreshed, the regions stay as they are
     const unsigned cut = (tau == tau) ? lo : 1u;               // NaN bound (K NaN scores): keep everything
     // write-back: an entry whose lower bound reaches the cut stays; one below it stays iff its UPPER bound lb + 2e does
-    // (sample pass: lower bounds only).  Its item id is read again (and the error bound looked up) only then.
-    int it[E];
-    unsigned keepbits = 0u;
-#pragma unroll
-    for (int e = 0; e < E; e++) {
-        it[e] = 0;
-        if ((e % EPR) < ns && lbk[e] != 0u) {
-            const int region = e / EPR, pos = (e % EPR) * 32 + lane;
-            it[e] = (int)cd[region * RC + pos].y;
-            bool keep = lbk[e] >= cut;
-            if (!keep && !keep_lb) {
-                const float er = filter_err(ca, chunk_norm[(unsigned)it[e] >> 5], efl);
-                const float ub = __fadd_ru(NumTraits<float>::from_orderable((u64)lbk[e]), __fadd_ru(er, er));
-                keep = NumTraits<float>::key(ub) >= cut;
-            }
-            if (keep) keepbits |= 1u << e;
-        }
-    }
+    // (sample pass: lower bounds only) -- only those look their error bound up.
     int base = 0;
     __syncwarp();
 #pragma unroll
     for (int e = 0; e < E; e++) {
         if ((e % EPR) < ns) {
-            const bool keep = (keepbits >> e) & 1u;
+            bool keep = lbk[e] != 0u && lbk[e] >= cut;
+            if (!keep && !keep_lb && lbk[e] != 0u) {
+                const float er = filter_err(ca, chunk_norm[(unsigned)it[e] >> 5], efl);
+                const float ub = __fadd_ru(NumTraits<float>::from_orderable((u64)lbk[e]), __fadd_ru(er, er));
+                keep = NumTraits<float>::key(ub) >= cut;
+            }
             const unsigned mask = __ballot_sync(FULL, keep);
             if (keep) {
                 const int k = base + __popc(mask & ((1u << lane) - 1u));
@@ -318,7 +307,6 @@ __device__ __noinline__ int cut_regions(uint2* cd, const int c0, const int c1, c
             base += __popc(mask);
         }
     }
-    *tau_out = tau;
     __syncwarp();
     return base;
 }
@@ -507,7 +495,7 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 else if (pass == 1) { if (ranked) { tau0 = rs->guess[row]; if (!(tau0 == tau0)) tau0 = -CUDART_INF_F; } }
                 else if (ranked && (rs->flags[row] & 4)) tau0 = -CUDART_INF_F;
                 rs->tau[row] = tau0;
-                if (rs->trig[row] != -1) rs->trig[row] = Kp + F_CUT_MARGIN;
+                if (rs->trig[row] != -1) rs->trig[row] = Kp + (pass == 1 && P.sample_tiles > 0 ? F_MAIN_MARGIN : F_CUT_MARGIN);
                 if (tau0 != CUDART_INF_F || pass < 2) rs->cnt[row] = 0;   // (a row closed in the retry pass keeps what pass 1 found)
             }
             asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
@@ -527,11 +515,113 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 rs->tot_prev[slot][row] = 0;
                 if (lane == 0) rs->interval[warp] = 1;
             }
+            if (pass == 0) {
+                // ===== SAMPLE pass: the guess is the sample_rank-th largest of the row's GROUP MAXIMA.  The sample tiles are cut into
+                // up to F_GROUPS groups of consecutive tiles; a lane keeps the largest lower bound (chunk maximum - the chunk's error
+                // bound) its warp's columns reach in the current group -- one FADD and one FMNMX per tile on top of the fast path, no
+                // appends, no cuts, no meetings -- and stores it at the group's end.  The r largest group maxima are r different
+                // items of the sample, so the r-th largest of them is <= the r-th best lower bound of the sample: a valid (slightly
+                // lower) stand-in for it.  A chunk holding one of the row's train items is left out of the sample (hpp:494-495).
+                constexpr int F_GROUPS = RC < 128 ? RC : 128;
+                const int tpg = (ntiles + F_GROUPS - 1) / F_GROUPS;            // tiles per group
+                const float ca_r = rs->ca[row], efl_r = rs->efl[row];
+                uint2* const cdg = P.cand + ((size_t)ul * C + slot * RC);      // this warp's region holds its partial group maxima
+                float gmax = -CUDART_INF_F;
+                int tg = 0, g = 0;
+                int buf = it0 & (F_ACCBUFS - 1);
+                unsigned par = (unsigned)(it0 >> F_ACCSHIFT) & 1u;
+                int item_base = slot * F_CHUNK;
+                const int item_step = P.sample_stride * FN;
+                const unsigned taddr0 = tmem_base + ((unsigned)(q * 32) << 16) + (unsigned)(slot * F_CHUNK);
+#if RMB_F_STATS
+                const long long clk_pass0 = clock64();
+#endif
+#pragma unroll 1
+                for (int left = ntiles; left > 0; left--, item_base += item_step) {
+                    const int tile_end = item_base - slot * F_CHUNK + FN;
+                    const float cn = __ldg(P.chunk_norm + (item_base >> 5));
+                    mbar_wait(bar_accf + 8 * buf, par);
+                    tc_fence_after();
+                    unsigned v[32];
+                    tmem_ld32(taddr0 + (unsigned)(buf * FN), v);
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(bar_acce + 8 * buf);
+                    if (++buf == F_ACCBUFS) { buf = 0; par ^= 1u; }
+                    float m32 = __uint_as_float(v[0]);
+#pragma unroll
+                    for (int e = 1; e < 32; e++) m32 = max_nan(m32, __uint_as_float(v[e]));
+                    bool skip = false;
+                    if (t_nxt < tile_end) {
+                        asm volatile("cp.async.wait_all;" ::: "memory");
+                        skip = t_nxt >= item_base && t_nxt < item_base + F_CHUNK;
+                        int nxt = rs->nxt2_train[slot][row];
+                        int t_cur = rs->tcur[slot][row] + 1;
+                        const int t_end = rs->tend[row];
+                        while (nxt < tile_end) {
+                            skip = skip || (nxt >= item_base && nxt < item_base + F_CHUNK);
+                            t_cur++;
+                            nxt = t_cur < t_end ? P.tri[t_cur] : INT_MAX;
+                        }
+                        t_nxt = nxt;
+                        rs->tcur[slot][row] = t_cur;
+                        if (t_cur + 1 < t_end)
+                            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&rs->nxt2_train[slot][row])), "l"(P.tri + t_cur + 1) : "memory");
+                        else rs->nxt2_train[slot][row] = INT_MAX;
+                    }
+                    const float lbm = __fsub_rd(m32, filter_err(ca_r, cn, efl_r));
+                    if (!skip) gmax = max_nan(gmax, lbm);
+                    if (++tg == tpg || left == 1) {
+                        cdg[g] = make_uint2(__float_as_uint(gmax), 0u);
+                        g++; tg = 0; gmax = -CUDART_INF_F;
+                    }
+                }
+                const int ngroups = (ntiles + tpg - 1) / tpg;
+                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");       // the quarter's four warps have stored their partial maxima
+                for (int r = slot; r < 32; r += 4) {
+                    const int rr = q * 32 + r;
+                    const uint2* cr = P.cand + (size_t)(tile_u0 + rr) * C;
+                    unsigned k[F_GROUPS / 32];
+#pragma unroll
+                    for (int j = 0; j < F_GROUPS / 32; j++) {
+                        const int gg = j * 32 + lane;
+                        k[j] = 0u;                                                 // (no group: below every score)
+                        if (gg < ngroups) {
+                            const float m01 = max_nan(__uint_as_float(cr[gg].x), __uint_as_float(cr[RC + gg].x));
+                            const float m23 = max_nan(__uint_as_float(cr[2 * RC + gg].x), __uint_as_float(cr[3 * RC + gg].x));
+                            k[j] = NumTraits<float>::key(max_nan(m01, m23));
+                        }
+                    }
+                    unsigned lo = 0u, hi = 0xffffffffu;                           // the sample_rank-th largest key, by bisection (exact)
+#pragma unroll 1
+                    for (int step = 0; step < 32 && lo < hi; step++) {
+                        const unsigned mid = lo + ((hi - lo) >> 1) + 1u;
+                        int c = 0;
+#pragma unroll
+                        for (int j = 0; j < F_GROUPS / 32; j++) c += (k[j] >= mid) ? 1 : 0;
+                        c = __reduce_add_sync(FULL, c);
+                        if (c >= P.sample_rank) lo = mid; else hi = mid - 1u;
+                    }
+                    if (lane == 0) {
+                        const float gs = NumTraits<float>::from_orderable((u64)lo);
+                        rs->guess[rr] = (lo != 0u && gs == gs) ? gs : -CUDART_INF_F;   // too few groups / NaN scores: no guess
+                    }
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+#if RMB_F_STATS
+                if (warp == RMB_F_STAT_WARP && lane == 0 && P.retries)
+                    atomicAdd(reinterpret_cast<unsigned long long*>(P.retries + 7) + 5, (unsigned long long)(clock64() - clk_pass0));
+#endif
+            } else {
             // error bound in the tile loop: the sample pass compares the approximate scores themselves (the cut then keeps
             // the best LOWER bounds); the other passes test upper bounds, approx + e >= tau'
             const float ca_l = pass == 0 ? 0.f : rs->ca[row];
             float tau_m = pass == 0 ? tau : __fsub_rd(tau, rs->efl[row]);          // tau' minus the row's constant error term
             int meet_in = 0;                                // tiles until the next meeting
+#if RMB_F_STATS
+            long long clk[6] = {0, 0, 0, 0, 0, 0};          // one warp's cycles: waiting for the accumulator, tcgen05.ld + fast path, appends, cursor moves, meetings + cuts, pass total
+            const long long clk_pass0 = clock64();
+#endif
             // loop-carried pipeline state, kept incrementally (no per-tile index arithmetic): accumulator buffer and its phase
             // parity, first item id of this warp's 32-column chunk, the item step between two tiles of the pass
             int buf = it0 & (F_ACCBUFS - 1);
@@ -548,8 +638,11 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
 #else
                 const float cn = __ldg(P.chunk_norm + (item_base >> 5));       // largest item norm of this chunk (in flight while the warp waits)
 #endif
+                F_CLK(t_a);
                 mbar_wait(bar_accf + 8 * buf, par);
                 tc_fence_after();
+                F_CLK(t_b);
+                F_CLK_ADD(0, t_a, t_b);
                 unsigned v[32];
 #if RMB_F_DBG
                 if (!(P.dbg & 8))
@@ -574,8 +667,10 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     gm[g] = max_nan(max_nan(m01, m23), max_nan(m45, m67));
                 }
                 const float thr = __fmaf_rd(-ca_l, cn, tau_m);                     // approx < thr: the upper bound stays below tau'
+                F_CLK(t_c);
                 if (!(max_nan(max_nan(gm[0], gm[1]), max_nan(gm[2], gm[3])) < thr)) {
-                    uint2* const cd = P.cand + ((size_t)ul * C + slot * RC);      // this warp's region of the row's buffer
+                    uint2* cd = P.cand + ((size_t)ul * C + slot * RC);            // this warp's region of the row's buffer
+                    asm volatile("" : "+l"(cd));                                  // (one pointer, indexed by the fill: keeps the address math to one IMAD.WIDE per store)
                     const float err = filter_err(rs->ca[row], cn, rs->efl[row]);  // candidates are stored with their lower bound
 #if RMB_F_FAST_APPEND
                     if (!has_train && tile_end <= P.n && mycnt <= RC - F_CHUNK) {
@@ -588,10 +683,19 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                                 const int before = mycnt;
 #pragma unroll
                                 for (int e8 = 0; e8 < 8; e8++) {
+#if RMB_F_FAST_APPEND == 2
+                                    // branch-free: every score of the group is stored at the region's end, the fill only moves
+                                    // past the ones that pass (what lies beyond the fill is never read; the region has room for
+                                    // the whole chunk).  A divergent branch costs this warp more than seven wasted stores.
+                                    const float sc = __uint_as_float(v[8 * g + e8]);
+                                    cd[mycnt] = make_uint2(__float_as_uint(__fsub_rd(sc, err)), (unsigned)(item_base + 8 * g + e8));
+                                    mycnt += (sc < thr) ? 0 : 1;
+#else
                                     if (!(__uint_as_float(v[8 * g + e8]) < thr)) {
                                         cd[mycnt] = make_uint2(__float_as_uint(__fsub_rd(__uint_as_float(v[8 * g + e8]), err)), (unsigned)(item_base + 8 * g + e8));
                                         mycnt++;
                                     }
+#endif
                                 }
                                 F_STAT(0, mycnt - before);
                                 (void)before;
@@ -616,6 +720,9 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                     }
                     }
                 }
+                F_CLK(t_d);
+                F_CLK_ADD(1, t_b, t_c);
+                F_CLK_ADD(2, t_c, t_d);
                 // move the train cursor past this tile: the id after t_nxt was prefetched into shared memory when the cursor last moved
                 if (has_train) {
                     F_STAT(3, 1);
@@ -630,6 +737,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                         asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(&rs->nxt2_train[slot][row])), "l"(P.tri + t_cur + 1) : "memory");
                     else rs->nxt2_train[slot][row] = INT_MAX;
                 }
+                F_CLK(t_e);
+                F_CLK_ADD(3, t_d, t_e);
                 if (--meet_in >= 0 && left > 1) continue;
 #if RMB_F_DBG
                 if (P.dbg & 4) continue;
@@ -650,17 +759,21 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                         if ((r & 3) != slot) continue;                         // the quarter's warps share the work
                         const int rr = q * 32 + r;
                         float tau_r;
-                        const int kept = cut_regions<C, RMB_F_HIST_ROUNDS, false>(P.cand + (size_t)(tile_u0 + rr) * C, rs->cnt4[0][rr], rs->cnt4[1][rr],
+                        // compact only when the regions run short of room; otherwise just refresh the row's bound
+                        const bool compact = max(max(rs->cnt4[0][rr], rs->cnt4[1][rr]), max(rs->cnt4[2][rr], rs->cnt4[3][rr])) > F_COMPACT_AT;
+                        const int kept = cut_regions<C, RMB_F_CUT_BITS, false>(P.cand + (size_t)(tile_u0 + rr) * C, rs->cnt4[0][rr], rs->cnt4[1][rr],
                                                                                   rs->cnt4[2][rr], rs->cnt4[3][rr], Kp, rs->ca[rr], rs->efl[rr], P.chunk_norm,
-                                                                                  keep_lb, lane, rs->hist[warp], &tau_r);
+                                                                                  keep_lb, compact, lane, &tau_r);
                         if (lane == 0) {
                             F_STAT(1, 1);
                             float t_new = fmaxf(tau_r, rs->tau[rr]);            // an earlier (valid) bound may be the sharper one; a NaN bound is ignored
-                            if (kept > 4 * (RC - 32)) { rs->flags[rr] |= 2; t_new = CUDART_INF_F; }     // the kept band does not fit
+                            if (compact && kept > 4 * (RC - 32)) { rs->flags[rr] |= 2; t_new = CUDART_INF_F; }     // the kept band does not fit
                             rs->tau[rr] = t_new;
-                            rs->trig[rr] = kept + F_CUT_MARGIN;
+                            rs->trig[rr] = kept + (pass == 1 && P.sample_tiles > 0 ? F_MAIN_MARGIN : F_CUT_MARGIN);
+                            if (compact) {
 #pragma unroll
-                            for (int sgm = 0; sgm < 4; sgm++) rs->cnt4[sgm][rr] = (kept + 3 - sgm) >> 2;
+                                for (int sgm = 0; sgm < 4; sgm++) rs->cnt4[sgm][rr] = (kept + 3 - sgm) >> 2;
+                            }
                         }
                     }
                     asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
@@ -679,6 +792,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 nxt_iv = __reduce_min_sync(FULL, nxt_iv);
                 nxt_iv = nxt_iv < 1 ? 1 : (nxt_iv > F_MAX_MEET ? F_MAX_MEET : nxt_iv);
                 meet_in = nxt_iv - 1;
+                F_CLK(t_f);
+                F_CLK_ADD(4, t_e, t_f);
                 rs->tot_prev[slot][row] = tot;
                 if (lane == 0) rs->interval[warp] = nxt_iv;
             }
@@ -692,8 +807,8 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 float tau_r = -CUDART_INF_F;
                 const bool have_k = nv >= Kp && !(rs->flags[rr] & 2);
                 if (nv > 0 && !(rs->flags[rr] & 2)) {
-                    const int kept = cut_regions<C, 7, true>(P.cand + (size_t)(tile_u0 + rr) * C, c0, c1, c2, c3, have_k ? Kp : nv, rs->ca[rr], rs->efl[rr],
-                                                             P.chunk_norm, keep_lb, lane, rs->hist[warp], &tau_r);
+                    const int kept = cut_regions<C, 32, true>(P.cand + (size_t)(tile_u0 + rr) * C, c0, c1, c2, c3, have_k ? Kp : nv, rs->ca[rr], rs->efl[rr],
+                                                             P.chunk_norm, keep_lb, true, lane, &tau_r);
                     if (lane == 0 && pass > 0) rs->cnt[rr] = kept;      // last cut: the exact stage gets only what can still be in the top K
                 }
                 if (lane == 0) {
@@ -708,6 +823,13 @@ filter_select_kernel(const __grid_constant__ FilterParams P)
                 }
             }
             asm volatile("bar.sync %0, 128;" ::"r"(qbar) : "memory");
+#if RMB_F_STATS
+            if (warp == RMB_F_STAT_WARP && lane == 0 && P.retries) {
+                clk[5] = clock64() - clk_pass0;
+                for (int i = 0; i < 6; i++) atomicAdd(reinterpret_cast<unsigned long long*>(P.retries + 7) + (pass == 0 ? 0 : 6) + i, (unsigned long long)clk[i]);
+            }
+#endif
+            }   // (passes 1 and 2)
         }
         it0 += ntiles;
         if (pass == 0) continue;         // the sample's result is consumed by the epilogue warps alone
