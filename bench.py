@@ -7,8 +7,10 @@
 A "step" is one pass of the hot path (one calc_metrics call) over one batch of synthetic input: the
 users of the configuration named in config.workload (default: BASELINE configs[3], the 1M x 1M
 catalogue the north-star quotes its target on; it fits one B200).  One process per GPU; under
-torchrun every rank evaluates its own block of `--users` users against its own replica of B
-("weak" scaling, no data-path collective: the path has no exchange step).
+torchrun the configuration's users are block-partitioned over the ranks ("strong" scaling, the default:
+BASELINE configs[3] is "1M users x 1M items, user-sharded at 1/2/4/8 B200") or, with `--scaling weak`,
+every rank evaluates its own `--users` users; either way against its own replica of B and with no
+data-path collective: the path has no exchange step.
 
   value     users/s with A, B, the CSR matrices and the outputs resident in HBM when the timed
             region starts (C-ABI call with inputs_on_device=1), CUDA events, max over ranks.
@@ -21,10 +23,15 @@ torchrun every rank evaluates its own block of `--users` users against its own r
             (ROC/PR-AUC) runs the FMA tiles (score_select_kernel): bound "fp32_fma"/"fp64_fma", peak = the FMA
             microbenchmark run live before the timed region.  traffic = DRAM bytes of one launch from the committed ncu
             capture (profiles/roofline_traffic.json).
+  e2e_pageable  e2e with ordinary (pageable) numpy buffers -- what the reference's callers pass: the library's
+            host-thread upload pipeline is then inside the timed region.
   cpu_baseline  the reference's own OpenMP/SIMD implementation (oracle/_ref; the C port if absent)
             on this box's host cores, on a bounded prefix of the same users.
+  parity    the metric rows the CPU baseline computed for that prefix against the rows the timed e2e call wrote for the
+            same users: {users, rows compared, mismatches beyond 1e-6 / NaN pattern, largest difference}.
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -51,8 +58,8 @@ def env_int(name, default):
         return default
 
 
-def workload_name(cfg, users):
-    return "%s; users/GPU=%d" % (cfg.name, users)
+def workload_name(cfg, users_total, gpus, scaling):
+    return "%s; %d users in all, block-partitioned over %d GPU(s) (%s scaling)" % (cfg.name, users_total, gpus, scaling)
 
 
 # ----------------------------------------------------------------------------- CPU arms
@@ -65,16 +72,38 @@ def cpu_arm_callable():
     return "port", oracle
 
 
-def run_cpu(kind, oracle, d, cfg, nthreads):
+def run_cpu(kind, oracle, d, cfg, nthreads, want_rows=False):
     A, B = synth.fold_biases(d["A"], d["B"], d["item_biases"])   # what the reference front-end does
     kw = dict(metrics=cfg.metrics, cumulative=cfg.cumulative, nthreads=nthreads, min_pos_test=cfg.min_pos_test,
               dtype=cfg.dtype)
     t0 = time.perf_counter()
     if kind == "reference":
-        oracle.ref_calc(A, B, d["X_train"], d["X_test"], cfg.k, **kw)
+        rows = oracle.ref_calc(A, B, d["X_train"], d["X_test"], cfg.k, **kw)
     else:
-        oracle.oracle_calc(A, B, d["X_train"], d["X_test"], cfg.k, fix_quirks=False, **kw)
+        rows = oracle.oracle_calc(A, B, d["X_train"], d["X_test"], cfg.k, fix_quirks=False, **kw)
+    if want_rows:
+        return time.perf_counter() - t0, rows
     return time.perf_counter() - t0
+
+
+def cpu_model():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("model name"):
+                return ln.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def sources_hash():
+    """Identifies the build the committed ncu traffic figure belongs to (profiles/roofline_traffic.json)."""
+    h = hashlib.sha1()
+    src = os.path.join(ROOT, "recometrics_b200", "csrc")
+    for name in sorted(os.listdir(src)):
+        if name.endswith((".cu", ".cuh")):
+            h.update(open(os.path.join(src, name), "rb").read())
+    return h.hexdigest()[:12]
 
 
 def cpu_sample_size(kind, oracle, cfg, cores, target_s, n_items):
@@ -103,11 +132,12 @@ def reference_arm(args, cfg, rank):
     sample = "first %d users of the workload per step (users are independent; OpenMP schedule(dynamic))" % users
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32" if cfg.dtype == np.float32 else "f64", "data": "synthetic",
-        "config": {"workload": workload_name(cfg, args.users), "items": args.items, "k_metrics": cfg.k,
+        "config": {"workload": workload_name(cfg, args.users_total, args.gpus, args.scaling), "items": args.items, "k_metrics": cfg.k,
                    "factors": cfg.p, "metrics": list(cfg.metrics), "cpu_sample_users_per_step": users},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample, "cpu": cpu_model(),
+                         "build": getattr(oracle, "ref_build_note", lambda: None)()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -183,8 +213,10 @@ def product_arm(args, cfg, rank, world, local_rank):
 
     T = cfg.dtype
     tdt = torch.float32 if T == np.float32 else torch.float64
-    users = args.users
-    d = synth.make(cfg.cfg_id, m=users, n=args.items, seed_shift=rank)   # every rank: its own users, same B shape
+    # this rank's block of the workload's users (strong: the configuration's users split over the ranks; weak: --users each);
+    # rank r draws its users from its own streams, the item factors are the same on every rank (B is replicated)
+    users = args.users_total * (rank + 1) // world - args.users_total * rank // world
+    d = synth.make(cfg.cfg_id, m=users, n=args.items, seed_shift=rank, shared_items=True)
     A, B, bias = d["A"], d["B"], d["item_biases"]
     Xtr, Xte = d["X_train"], d["X_test"]
     m, n, p = A.shape[0], B.shape[0], A.shape[1]
@@ -259,7 +291,7 @@ def product_arm(args, cfg, rank, world, local_rank):
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
-    value = world * m * args.steps / (dev_ms * 1e-3)
+    value = args.users_total * args.steps / (dev_ms * 1e-3)
 
     # ---- end-to-end through the host-pointer C-ABI (H2D of inputs + D2H of metric rows inside)
     call(False, tm)   # one warm-up
@@ -275,7 +307,30 @@ def product_arm(args, cfg, rank, world, local_rank):
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * m * args.steps / e2e_s
+    e2e_value = args.users_total * args.steps / e2e_s
+
+    # ---- the same with ordinary (pageable) numpy buffers, what the reference's callers pass (upload pipeline inside)
+    def call_pageable():
+        ex = _capi.make_extra(device=local_rank, inputs_on_device=False, timing=tm)
+        rc = _capi.calc_metrics(T, A, p, B, p, m, n, p, Xtr.indptr, Xtr.indices, Xte.indptr, Xte.indices, pg_tev,
+                                K, cfg.cumulative, False, pg_outs, True, 2, cfg.min_pos_test, item_biases=bias, extra=ex)
+        _capi.raise_for_status(rc)
+    pg_tev = np.ascontiguousarray(Xte.data, dtype=T)
+    pg_outs = {q: np.empty(m * (rs if q in _capi.TOPK_METRICS else 1), dtype=T) for q in cfg.metrics}
+    call_pageable()
+    barrier()
+    t0 = time.perf_counter()
+    pg_steps = min(args.steps, 3)
+    for _ in range(pg_steps):
+        call_pageable()
+    barrier()
+    pg_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([pg_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        pg_s = float(t.item())
+    e2e_pageable = {"value": args.users_total * pg_steps / pg_s, "unit": UNIT, "ms_per_step": pg_s * 1e3 / pg_steps, "steps": pg_steps,
+                    "note": "host inputs and outputs in pageable numpy memory (the reference's callers): the library's host-thread upload pipeline is inside"}
 
     # ---- roofline of the dominant kernel (score_select): algorithmic flops / CUDA-event kernel time
     ach = flops * args.steps / (kernel_ms * 1e-3) / 1e12
@@ -286,6 +341,8 @@ def product_arm(args, cfg, rank, world, local_rank):
             traffic = json.load(open(tpath)).get(str(cfg.cfg_id))
             if isinstance(traffic, dict):      # DRAM bytes of one launch of the dominant kernel, from the committed ncu capture
                 traffic_note = "%s; %s" % (traffic.get("per"), traffic.get("source"))
+                if traffic.get("sources_hash") not in (None, sources_hash()):
+                    traffic_note += "; NOTE: captured on build %s, this build is %s (kernel sources changed since the capture)" % (traffic.get("sources_hash"), sources_hash())
                 traffic = int(traffic["dram_bytes_read"]) + int(traffic["dram_bytes_write"])
         except Exception:
             traffic = None
@@ -325,30 +382,50 @@ def product_arm(args, cfg, rank, world, local_rank):
         pass
 
     # ---- CPU baseline: the reference's implementation on this box's cores (rank 0, N=1 only)
-    cpu = None
+    cpu, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         kind, oracle = cpu_arm_callable()
         cores = os.cpu_count() or 1
         cu = cpu_sample_size(kind, oracle, cfg, cores, 12.0, args.items)
+        cu = min(cu, m)
         dd = synth.make(cfg.cfg_id, m=cu, n=args.items)
-        sec = run_cpu(kind, oracle, dd, cfg, cores)
-        cpu = {"value": cu / sec, "unit": UNIT, "cores": cores, "kind": kind,
+        sec, cpu_rows = run_cpu(kind, oracle, dd, cfg, cores, want_rows=True)
+        cpu = {"value": cu / sec, "unit": UNIT, "cores": cores, "kind": kind, "cpu": cpu_model(),
+               "build": getattr(oracle, "ref_build_note", lambda: None)(),
                "sample": "first %d users of the workload, %d threads, %.1f s" % (cu, cores, sec)}
+        # the rows the timed e2e call wrote for the same users (synth is block-reproducible: the prefix is bit-identical)
+        bad_users = np.zeros(cu, dtype=bool)
+        worst, rows_cmp = 0.0, 0
+        for q in cfg.metrics:
+            w = rs if q in _capi.TOPK_METRICS else 1
+            g = houts[q].numpy()[: cu * w].reshape(cu, w).astype(np.float64)
+            c = np.asarray(cpu_rows[q]).reshape(cu, w).astype(np.float64)
+            both_nan = np.isnan(g) & np.isnan(c)
+            diff = np.where(both_nan, 0.0, np.abs(g - c))
+            diff = np.where(np.isnan(diff), np.inf, diff)          # NaN on one side only
+            bad_users |= (diff > 1e-6).any(axis=1)
+            worst = max(worst, float(diff.max()) if diff.size else 0.0)
+            rows_cmp += cu
+        parity = {"users": int(cu), "metric_rows": int(rows_cmp), "mismatched_users": int(bad_users.sum()), "tolerance": 1e-6,
+                  "max_abs_diff": worst, "nan_rows_cpu": int(np.isnan(np.asarray(cpu_rows[cfg.metrics[0]]).reshape(cu, -1)[:, 0]).sum()),
+                  "against": "cpu_baseline rows (%s) vs the rows of the timed e2e call, same users" % kind}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "f32" if T == np.float32 else "f64", "data": "synthetic",
-            "config": {"workload": workload_name(cfg, users), "users_per_gpu": m, "items": n, "factors": p,
+            "config": {"workload": workload_name(cfg, args.users_total, world, args.scaling), "users_total": args.users_total,
+                       "users_per_gpu": m, "items": n, "factors": p,
                        "k_metrics": K, "metrics": list(cfg.metrics), "cumulative": bool(cfg.cumulative),
                        "l2": "inputs (A+B+CSR = %.0f MB) larger than the 126 MB L2; no flush" % (
                            (A.nbytes + B.nbytes + Xtr.indices.nbytes + Xte.indices.nbytes) / 1e6),
                        "scoring_path": {1: "fma", 2: "tensor filter + exact re-score"}.get(path, "?"),
                        "parallelism": "users block-partitioned, B replicated, no data-path collective"},
-            "roofline": roofline, "cpu_baseline": cpu,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_s * 1e3 / args.steps},
+            "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
+                    "ms_per_step": e2e_s * 1e3 / args.steps, "host_buffers": "pinned"},
+            "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches), "clocks": clocks,
             "phases_ms_per_step": {k: round(v, 3) for k, v in phases.items()},
         }
@@ -364,7 +441,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", type=int, default=4, help="BASELINE.json configs index + 1 (default 4: 1M x 1M, K=100)")
-    ap.add_argument("--users", type=int, default=0, help="users per GPU (default: the configuration's m)")
+    ap.add_argument("--users", type=int, default=0, help="users: in all (strong scaling) / per GPU (weak); default: the configuration's m")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: split the configuration's users over the GPUs (strong, default) or give every GPU that many (weak)")
     ap.add_argument("--items", type=int, default=0, help="items (default: the configuration's n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -373,6 +452,7 @@ def main():
     args.users = args.users or cfg.m
     args.items = args.items or cfg.n
     rank, world, local_rank = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    args.users_total = args.users * (max(world, args.gpus) if args.scaling == "weak" else 1)
     if world == 1 and args.gpus > 1 and args.impl == "b200":
         # convenience: re-launch under torchrun, one rank per GPU
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),

@@ -74,6 +74,8 @@ typedef struct rmb200_timing {
     int64_t filter_fallback_users;   /* users the tensor-core filter handed back to the FMA path (only they are re-run)          */
     double filter_err_ratio_max;     /* extra.filter_stats: largest |approximate - exact| / error bound over all re-scored       */
                                      /* candidates of the call (the bound holds iff this is <= 1)                                 */
+    int64_t devices_used;            /* GPUs the call ran on (1 unless rmb200_extra_t::devices / RMB200_DEVICES spread it); on a  */
+                                     /* multi-GPU call the *_ms fields are the maximum over the devices, counters are sums        */
 } rmb200_timing_t;
 
 /* Optional extension block (pass NULL for reference behaviour).  Zero-initialise, then set

@@ -36,6 +36,7 @@ class Timing(ctypes.Structure):
         ("scoring_path", ctypes.c_int64), ("filter_fallback_batches", ctypes.c_int64),
         ("dominant_kernel_ms", ctypes.c_double), ("filter_retry_rows", ctypes.c_int64),
         ("filter_fallback_users", ctypes.c_int64), ("filter_err_ratio_max", ctypes.c_double),
+        ("devices_used", ctypes.c_int64),
     ]
 
     def as_dict(self):

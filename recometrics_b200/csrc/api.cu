@@ -6,8 +6,10 @@
 // /root/reference/src/recometrics.hpp:387-393 (clamps) and :426 / :488 / :964 (SIGINT latch).
 #include "../../include/recometrics_b200.h"
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cmath>
 #include <csignal>
 #include <cstdio>
@@ -30,6 +32,7 @@ namespace {
 thread_local std::string g_err;
 std::atomic<int> g_interrupt{0};
 std::mutex g_call_mutex;   // one call at a time per process (the SIGINT latch is process-wide)
+constexpr int MAX_DEVICES = 16;   // GPUs one call can be spread over
 
 void set_err(const char* what, const char* detail = nullptr)
 {
@@ -44,8 +47,9 @@ extern "C" void rmb200_sigint_handler(int) { g_interrupt.store(1); }
 struct SignalLatch {
     void (*old_handler)(int) = SIG_DFL;
     bool active = false;
-    SignalLatch()
+    explicit SignalLatch(bool engage = true)
     {
+        if (!engage) return;
         g_interrupt.store(0);
         old_handler = std::signal(SIGINT, rmb200_sigint_handler);
         active = (old_handler != SIG_ERR);
@@ -163,8 +167,40 @@ __global__ void rebase_indptr_kernel(const int* __restrict__ src, const int lo, 
     if (i < cnt) dst[i] = src[i] - lo;
 }
 
+// One call spread over several GPUs (rmb200_extra_t::devices / RMB200_DEVICES): every device runs run_call() on its own
+// contiguous block of users from its own host thread.  The only thing the devices share is the item-factor matrix: device
+// g uploads the g-th slice of its rows over its own PCIe link and fetches the other slices from its peers' memory
+// (NVLink), instead of G uploads of the whole matrix.  The threads meet twice: slices uploaded / slices fetched.
+struct MultiCtx {
+    int G = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived[2] = {0, 0};
+    int departed = 0;
+    bool failed = false;
+    void* Bptr[MAX_DEVICES] = {};
+    int Bdev[MAX_DEVICES] = {};
+    // false: a peer failed (the caller gives up as well)
+    bool meet(int phase)
+    {
+        std::unique_lock<std::mutex> lk(mu);
+        arrived[phase]++;
+        cv.notify_all();
+        cv.wait(lk, [&] { return arrived[phase] + departed >= G; });
+        return !failed;
+    }
+    void depart(bool fail)          // the device's thread is done (a thread that fails early stands in for its later meetings)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        departed++;
+        if (fail) failed = true;
+        cv.notify_all();
+    }
+};
+
 template <typename T>
 struct CallArgs {
+    MultiCtx* mc = nullptr; int mc_rank = 0;
     const T* A; size_t lda; const T* B; size_t ldb;
     int m, n, k;
     const int32_t *trp, *tri, *tep, *tei; const T* tev;
@@ -293,17 +329,20 @@ struct UploadPool {
     int lanes = 0;
     bool ok = false;
 };
-UploadPool g_up;                 // (calls are serialised by the library's mutex)
+UploadPool g_ups[MAX_DEVICES];   // one per device: calls are serialised by the library's mutex, and inside a multi-GPU call
+                                 // every device has its own host thread
+thread_local int g_upload_share = 1;   // a multi-GPU call divides the host's copy threads among its devices
 
 int upload_threads()
 {
     int v = (int)std::thread::hardware_concurrency() / 2;      // measured on a 16-core box: 60 ms plain, 32 ms with 4 threads, 25 ms with 8
     if (v < 1) v = 1;
     if (const char* e = std::getenv("RMB200_UPLOAD_THREADS")) v = std::atoi(e);
+    if (v > 1 && g_upload_share > 1) { v /= g_upload_share; if (v < 1) v = 1; }
     return v < 0 ? 0 : (v > UP_MAX_THREADS ? UP_MAX_THREADS : v);
 }
 
-void upload_pool_release()
+void upload_pool_release(UploadPool& g_up)
 {
     if (g_up.dev < 0) return;
     int cur = 0;
@@ -323,22 +362,29 @@ void upload_pool_release()
     cudaSetDevice(cur);
 }
 
+void upload_pool_release_all()
+{
+    for (int d = 0; d < MAX_DEVICES; d++) upload_pool_release(g_ups[d]);
+}
+
 bool upload_pool_ready(int dev, int nthreads)
 {
+    if (dev < 0 || dev >= MAX_DEVICES) return false;
+    UploadPool& g_up = g_ups[dev];
     if (g_up.ok && g_up.dev == dev && g_up.lanes >= nthreads) return true;
-    upload_pool_release();
+    upload_pool_release(g_up);
     g_up.dev = dev;
     g_up.lanes = nthreads;
     for (int t = 0; t < nthreads; t++) {
         UploadLane& L = g_up.lane[t];
-        if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); upload_pool_release(); return false; }
+        if (cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); upload_pool_release(g_up); return false; }
         for (int b = 0; b < 2; b++) {
             if (cudaHostAlloc(&L.buf[b], UP_CHUNK, cudaHostAllocDefault) != cudaSuccess ||
-                cudaEventCreateWithFlags(&L.ev[b], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); upload_pool_release(); return false; }
+                cudaEventCreateWithFlags(&L.ev[b], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); upload_pool_release(g_up); return false; }
         }
-        if (cudaEventCreateWithFlags(&g_up.done[t], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); upload_pool_release(); return false; }
+        if (cudaEventCreateWithFlags(&g_up.done[t], cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); upload_pool_release(g_up); return false; }
     }
-    if (cudaEventCreateWithFlags(&g_up.start, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); upload_pool_release(); return false; }
+    if (cudaEventCreateWithFlags(&g_up.start, cudaEventDisableTiming) != cudaSuccess) { cudaGetLastError(); upload_pool_release(g_up); return false; }
     g_up.ok = true;
     return true;
 }
@@ -366,6 +412,7 @@ cudaError_t upload_rows(void* dst, const void* src, size_t src_pitch, size_t row
         if (src_pitch == row_bytes) return cudaMemcpyAsync(dst, src, total, cudaMemcpyHostToDevice, st);
         return cudaMemcpy2DAsync(dst, row_bytes, src, src_pitch, row_bytes, rows, cudaMemcpyHostToDevice, st);
     }
+    UploadPool& g_up = g_ups[dev];
     // what is already queued on `st` (e.g. kernels still reading dst's previous contents) comes first
     cudaEvent_t start = g_up.start;
     cudaError_t e = cudaEventRecord(start, st);
@@ -491,8 +538,10 @@ int run_call(const CallArgs<T>& a)
     if (dev >= ndev) { set_err("bad argument", "device ordinal out of range"); return RMB200_ERR_BAD_ARG; }
     CK(cudaSetDevice(dev));
 
-    std::lock_guard<std::mutex> lock(g_call_mutex);
-    SignalLatch latch;
+    const bool nested = a.mc != nullptr;                   // one device's share of a multi-GPU call: run_multi() holds the mutex and the latch
+    std::unique_lock<std::mutex> lock(g_call_mutex, std::defer_lock);
+    if (!nested) lock.lock();
+    SignalLatch latch(!nested);
     cudaStream_t st = nullptr;   // legacy default stream: ordered after the caller's default-stream work
     PhaseTimer pt(st), pk(st);   // phases; the dominant scoring kernel alone
 
@@ -612,8 +661,32 @@ int run_call(const CallArgs<T>& a)
     if (!on_dev) {
         CK(d_Brow.alloc((size_t)a.n * a.k * sizeof(T)));
         pt.start();
-        int rc = stage_rows<T>(a.B, a.ldb, a.n, a.k, false, d_Brow, &Bsrc, &Bld, st, tm);
-        if (rc) return rc;
+        if (!nested) {
+            int rc = stage_rows<T>(a.B, a.ldb, a.n, a.k, false, d_Brow, &Bsrc, &Bld, st, tm);
+            if (rc) return rc;
+        } else {
+            // this device's slice of the rows from the host, the other slices from the peers' copies (see MultiCtx)
+            MultiCtx& mc = *a.mc;
+            const int G = mc.G, g = a.mc_rank;
+            auto slice = [&](int h) { return (long long)a.n * h / G; };
+            const size_t row_bytes = (size_t)a.k * sizeof(T);
+            unsigned char* base = static_cast<unsigned char*>(d_Brow.p);
+            if (slice(g + 1) > slice(g))
+                CK(upload_rows(base + (size_t)slice(g) * row_bytes, a.B + (size_t)slice(g) * a.ldb, a.ldb * sizeof(T), row_bytes,
+                               (size_t)(slice(g + 1) - slice(g)), st));
+            tm.h2d_bytes += (int64_t)(slice(g + 1) - slice(g)) * (int64_t)row_bytes;
+            CK(cudaStreamSynchronize(st));
+            mc.Bptr[g] = d_Brow.p; mc.Bdev[g] = dev;
+            if (!mc.meet(0)) { set_err("multi-GPU call", "another device failed"); return RMB200_ERR_CUDA; }
+            for (int h = 1; h < G; h++) {
+                const int src = (g + h) % G;
+                const size_t off = (size_t)slice(src) * row_bytes, bytes = (size_t)(slice(src + 1) - slice(src)) * row_bytes;
+                if (bytes) CK(cudaMemcpyPeerAsync(base + off, dev, static_cast<unsigned char*>(mc.Bptr[src]) + off, mc.Bdev[src], bytes, st));
+            }
+            CK(cudaStreamSynchronize(st));
+            if (!mc.meet(1)) { set_err("multi-GPU call", "another device failed"); return RMB200_ERR_CUDA; }   // nobody frees its copy before everybody has fetched
+            Bsrc = d_Brow.as<T>(); Bld = (size_t)a.k;
+        }
         pt.stop(tm.h2d_ms);
     } else { Bsrc = a.B; Bld = a.ldb; }
     bool have_Bt = false;
@@ -1067,13 +1140,186 @@ int run_call(const CallArgs<T>& a)
     CK(cudaStreamSynchronize(st));
 
     tm.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    tm.devices_used = 1;
     if (ex && ex->timing) *ex->timing = tm;
 
     if (g_interrupt.load()) {   // hpp:167-173: restore the handler, re-raise, report
         latch.restore();
+        if (!nested) std::raise(SIGINT);
+        set_err("interrupted", "procedure was interrupted");
+        return RMB200_ERR_INTERRUPTED;
+    }
+    return RMB200_OK;
+}
+
+inline const rmb200_extra_t* ex_or_default(const rmb200_extra_t* ex)
+{
+    static const rmb200_extra_t dflt = []() {
+        rmb200_extra_t e;
+        std::memset(&e, 0, sizeof(e));
+        e.struct_size = (int32_t)sizeof(e);
+        e.device = -1;
+        return e;
+    }();
+    return ex ? ex : &dflt;
+}
+
+// Which GPUs the call runs on: rmb200_extra_t::devices, else (no explicit `device`) env RMB200_DEVICES = "all" | "0,1,2,...".
+// An empty list = the single-device rules of run_call().
+int resolve_devices(const rmb200_extra_t* ex, std::vector<int>& devs)
+{
+    devs.clear();
+    if (ex && ex->struct_size != (int32_t)sizeof(rmb200_extra_t)) return RMB200_OK;      // (run_call reports it)
+    if (ex && ex->n_devices > 0) {
+        if (!ex->devices) { set_err("bad argument", "n_devices > 0 but devices is NULL"); return RMB200_ERR_BAD_ARG; }
+        devs.assign(ex->devices, ex->devices + ex->n_devices);
+    } else if (!(ex && ex->device >= 0) && !(ex && ex->inputs_on_device)) {
+        const char* env = std::getenv("RMB200_DEVICES");
+        if (!env || !env[0]) return RMB200_OK;
+        if (!std::strcmp(env, "all")) {
+            int ndev = 0;
+            if (cudaGetDeviceCount(&ndev) != cudaSuccess) { cudaGetLastError(); ndev = 0; }
+            for (int d = 0; d < ndev && d < MAX_DEVICES; d++) devs.push_back(d);
+        } else {
+            for (const char* c = env; *c;) {
+                char* end = nullptr;
+                const long v = std::strtol(c, &end, 10);
+                if (end == c) { set_err("bad argument", "RMB200_DEVICES is neither \"all\" nor a comma-separated list of ordinals"); return RMB200_ERR_BAD_ARG; }
+                devs.push_back((int)v);
+                c = (*end == ',') ? end + 1 : end;
+                if (*end && *end != ',') { set_err("bad argument", "RMB200_DEVICES is neither \"all\" nor a comma-separated list of ordinals"); return RMB200_ERR_BAD_ARG; }
+            }
+        }
+    }
+    if (devs.empty()) return RMB200_OK;
+    if ((int)devs.size() > MAX_DEVICES) { set_err("bad argument", "more than 16 devices"); return RMB200_ERR_BAD_ARG; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) {
+        cudaGetLastError();
+        set_err("no CUDA device", "librecometrics_b200 has no CPU fallback");
+        return RMB200_ERR_NO_DEVICE;
+    }
+    for (size_t i = 0; i < devs.size(); i++) {
+        if (devs[i] < 0 || devs[i] >= ndev) { set_err("bad argument", "device ordinal out of range"); return RMB200_ERR_BAD_ARG; }
+        for (size_t j = 0; j < i; j++)
+            if (devs[j] == devs[i]) { set_err("bad argument", "a device is listed twice"); return RMB200_ERR_BAD_ARG; }
+    }
+    if (devs.size() > 1 && ex && ex->inputs_on_device) { set_err("unsupported", "a multi-GPU call takes host pointers (device-resident inputs live on one GPU)"); return RMB200_ERR_UNSUPPORTED; }
+    return RMB200_OK;
+}
+
+// /root/reference/src/recometrics.hpp:428-437: the reference's one call spreads the users over every core
+// (`#pragma omp parallel for schedule(dynamic) num_threads(nthreads)`); this spreads them over every listed GPU.
+template <typename T>
+int run_multi(const CallArgs<T>& a0, const std::vector<int>& devs_in)
+{
+    const auto t_begin = std::chrono::steady_clock::now();
+    const rmb200_extra_t* ex = ex_or_default(a0.ex);
+    if (a0.m <= 0) { set_err("bad argument", "m, n, k and k_metrics must be positive"); return RMB200_ERR_BAD_ARG; }
+    int ub = 0, ue = a0.m;
+    if (ex->user_end < 0) return RMB200_OK;
+    if (ex->user_begin != 0 || ex->user_end != 0) { ub = ex->user_begin; ue = ex->user_end; }
+    if (ub < 0 || ue > a0.m || ub > ue) { set_err("bad argument", "user range outside [0, m]"); return RMB200_ERR_BAD_ARG; }
+    // contiguous blocks in units of one CTA's 128 users; devices left without a unit sit the call out
+    const int units = (ue - ub + rmb::BM - 1) / rmb::BM;
+    std::vector<int> devs, lo, hi;
+    {
+        const int G0 = (int)devs_in.size();
+        for (int g = 0; g < G0; g++) {
+            const int u0 = (int)((long long)units * g / G0), u1 = (int)((long long)units * (g + 1) / G0);
+            if (u1 <= u0) continue;
+            devs.push_back(devs_in[g]);
+            lo.push_back(ub + u0 * rmb::BM);
+            hi.push_back(std::min(ue, ub + u1 * rmb::BM));
+        }
+    }
+    const int G = (int)devs.size();
+    if (G == 0) return RMB200_OK;
+
+    std::unique_lock<std::mutex> lock(g_call_mutex);
+    SignalLatch latch;
+    MultiCtx mc;
+    mc.G = G;
+    const bool want_means = ex->metric_means || ex->metric_counts;
+    const int W = a0.cumulative ? a0.K : 1;
+    const size_t cells = (size_t)10 * (size_t)(W > 0 ? W : 1);
+    std::vector<rmb200_extra_t> exs((size_t)G, *ex);
+    std::vector<rmb200_timing_t> tms((size_t)G);
+    std::vector<std::vector<double>> means((size_t)G);
+    std::vector<std::vector<long long>> counts((size_t)G);
+    std::vector<int> rcs((size_t)G, RMB200_OK);
+    std::vector<std::string> errs((size_t)G);
+    std::vector<std::thread> workers;
+    for (int g = 0; g < G; g++) {
+        std::memset(&tms[g], 0, sizeof(rmb200_timing_t));
+        rmb200_extra_t& e = exs[g];
+        e.device = devs[g]; e.devices = nullptr; e.n_devices = 0;
+        e.user_begin = lo[g]; e.user_end = hi[g];
+        e.timing = &tms[g];
+        if (want_means) {
+            means[g].assign(cells, 0.0); counts[g].assign(cells, 0);
+            e.metric_means = means[g].data(); e.metric_counts = reinterpret_cast<int64_t*>(counts[g].data());
+        }
+        workers.emplace_back([&, g]() {
+            g_err.clear();
+            g_upload_share = G;
+            int rc;
+            try {
+                // peers' memory directly over NVLink where the hardware allows it (else the copies are staged by the driver)
+                if (cudaSetDevice(devs[g]) == cudaSuccess)
+                    for (int h = 0; h < G; h++) {
+                        int can = 0;
+                        if (h != g && cudaDeviceCanAccessPeer(&can, devs[g], devs[h]) == cudaSuccess && can) cudaDeviceEnablePeerAccess(devs[h], 0);
+                        cudaGetLastError();
+                    }
+                CallArgs<T> a = a0;
+                a.ex = &exs[g]; a.mc = &mc; a.mc_rank = g;
+                rc = run_call<T>(a);
+            } catch (const std::bad_alloc&) {
+                set_err("host allocation failed"); rc = RMB200_ERR_OOM;
+            } catch (...) {
+                set_err("unexpected C++ exception"); rc = RMB200_ERR_CUDA;
+            }
+            rcs[g] = rc; errs[g] = g_err;
+            mc.depart(rc != RMB200_OK);
+        });
+    }
+    for (auto& w : workers) w.join();
+
+    int rc = RMB200_OK;
+    for (int g = 0; g < G && rc == RMB200_OK; g++)
+        if (rcs[g] != RMB200_OK && rcs[g] != RMB200_ERR_INTERRUPTED) { rc = rcs[g]; g_err = errs[g]; }
+    if (rc == RMB200_OK && g_interrupt.load()) {
+        latch.restore();
         std::raise(SIGINT);
         set_err("interrupted", "procedure was interrupted");
         return RMB200_ERR_INTERRUPTED;
+    }
+    if (rc != RMB200_OK) return rc;
+
+    if (want_means) {       // means of the call = the devices' means weighted by their user counts
+        for (size_t c = 0; c < cells; c++) {
+            double s = 0.0; long long cnt = 0;
+            for (int g = 0; g < G; g++) if (counts[g][c] > 0) { s += means[g][c] * (double)counts[g][c]; cnt += counts[g][c]; }
+            if (ex->metric_means) ex->metric_means[c] = cnt ? s / (double)cnt : std::numeric_limits<double>::quiet_NaN();
+            if (ex->metric_counts) ex->metric_counts[c] = cnt;
+        }
+    }
+    if (ex->timing) {
+        rmb200_timing_t t = tms[0];
+        for (int g = 1; g < G; g++) {
+            const rmb200_timing_t& o = tms[g];
+            t.h2d_ms = std::max(t.h2d_ms, o.h2d_ms); t.prep_ms = std::max(t.prep_ms, o.prep_ms);
+            t.score_select_ms = std::max(t.score_select_ms, o.score_select_ms); t.metrics_ms = std::max(t.metrics_ms, o.metrics_ms);
+            t.d2h_ms = std::max(t.d2h_ms, o.d2h_ms); t.dominant_kernel_ms = std::max(t.dominant_kernel_ms, o.dominant_kernel_ms);
+            t.kernel_launches += o.kernel_launches; t.h2d_bytes += o.h2d_bytes; t.d2h_bytes += o.d2h_bytes;
+            t.filter_fallback_batches += o.filter_fallback_batches; t.filter_retry_rows += o.filter_retry_rows;
+            t.filter_fallback_users += o.filter_fallback_users;
+            t.filter_err_ratio_max = std::max(t.filter_err_ratio_max, o.filter_err_ratio_max);
+        }
+        t.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+        t.devices_used = G;
+        *ex->timing = t;
     }
     return RMB200_OK;
 }
@@ -1095,6 +1341,16 @@ int entry(const T* A, size_t lda, const T* B, size_t ldb, int32_t m, int32_t n, 
     a.consider_cold_start = ccs ? 1 : 0; a.min_items_pool = mip; a.min_pos_test = mpt; a.seed = seed;
     a.bias = bias; a.ex = ex;
     try {
+        std::vector<int> devs;
+        int rc = resolve_devices(ex, devs);
+        if (rc) return rc;
+        if (devs.size() > 1) return run_multi<T>(a, devs);
+        if (devs.size() == 1) {                 // a list of one: that device
+            rmb200_extra_t one = *ex_or_default(ex);
+            one.device = devs[0]; one.devices = nullptr; one.n_devices = 0;
+            a.ex = &one;
+            return run_call<T>(a);
+        }
         return run_call<T>(a);
     } catch (const std::bad_alloc&) {
         set_err("host allocation failed");
@@ -1195,7 +1451,7 @@ void rmb200_request_interrupt(void) { g_interrupt.store(1); }
 void rmb200_release_workspace(void)
 {
     std::lock_guard<std::mutex> call(g_call_mutex);      // not while a call is using them
-    upload_pool_release();
+    upload_pool_release_all();
     std::lock_guard<std::mutex> lk(g_pool_mutex);
     pool_trim_locked(-1);
 }

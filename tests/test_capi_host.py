@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(rb):
 def test_extra_struct_layout_matches_header(rb):
     """ctypes mirror of rmb200_extra_t / rmb200_timing_t has the C layout (LP64)."""
     from recometrics_b200 import _capi
-    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 9 * 8
+    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 10 * 8
     assert ctypes.sizeof(_capi.Extra) == 6 * 4 + 5 * 8 + 2 * 4 + 2 * 8 + 2 * 4 + 8 + 8 + 2 * 4
     assert _capi.Extra.nan_bits.offset == 96 and _capi.Extra.devices.offset == 104
     assert _capi.Extra.topk_items.offset == 24
@@ -57,6 +57,23 @@ def test_no_device_means_error_not_fallback(rb):
     from tools import synth
     d = synth.make(1, m=40, n=60, p=4, k=3)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=3, break_ties_with_noise=False)
+
+
+def test_no_device_multi_gpu_call_fails_the_same_way(rb, monkeypatch):
+    """A device list (or RMB200_DEVICES) does not open a CPU path either."""
+    from recometrics_b200 import _capi
+    if _capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from tools import synth
+    d = synth.make(1, m=40, n=60, p=4, k=3)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=3, break_ties_with_noise=False, devices=[0, 1])
+    monkeypatch.setenv("RMB200_DEVICES", "0,1")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=3, break_ties_with_noise=False)
+    monkeypatch.setenv("RMB200_DEVICES", "zero")
+    with pytest.raises(ValueError, match="RMB200_DEVICES"):
         rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=3, break_ties_with_noise=False)
 
 

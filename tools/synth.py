@@ -73,8 +73,9 @@ def _user_block(cfg, block, rows, n):
     return tr_cnt, it[~is_test], te_cnt, it[is_test], vals[is_test]
 
 
-def make(cfg_id, m=None, n=None, p=None, k=None, seed_shift=0):
-    """Generate (a prefix of) a BASELINE configuration.  m/n/p/k override the sizes (tests use small ones)."""
+def make(cfg_id, m=None, n=None, p=None, k=None, seed_shift=0, shared_items=False):
+    """Generate (a prefix of) a BASELINE configuration.  m/n/p/k override the sizes (tests use small ones).
+    seed_shift: another set of users (rank r of a multi-GPU run); shared_items: ... with the SAME item factors."""
     base = CONFIGS[cfg_id]
     cfg = Config(**{**base.__dict__})
     if m is not None:
@@ -89,11 +90,12 @@ def make(cfg_id, m=None, n=None, p=None, k=None, seed_shift=0):
     T = cfg.dtype
     mm, nn = cfg.m, cfg.n
 
-    rngB = np.random.default_rng([cfg.cfg_id, 10 ** 6])
+    items_id = base.cfg_id if shared_items else cfg.cfg_id
+    rngB = np.random.default_rng([items_id, 10 ** 6])
     B = rngB.standard_normal((nn, cfg.p), dtype=np.float32 if T == np.float32 else np.float64).astype(T, copy=False)
     bias = None
     if cfg.item_biases:
-        bias = (0.5 * np.random.default_rng([cfg.cfg_id, 10 ** 6 + 100]).standard_normal(nn)).astype(T)
+        bias = (0.5 * np.random.default_rng([items_id, 10 ** 6 + 100]).standard_normal(nn)).astype(T)
 
     A = np.empty((mm, cfg.p), dtype=T)
     tr_cnts, tr_idx, te_cnts, te_idx, te_val = [], [], [], [], []
