@@ -15,6 +15,7 @@ ap.add_argument("--factors", type=int, default=0)
 ap.add_argument("--k", type=int, default=0)
 ap.add_argument("--f64", action="store_true")
 ap.add_argument("--noise", action="store_true", help="break_ties_with_noise=True (the reference default)")
+ap.add_argument("--devices", default="", help="comma-separated CUDA ordinals: spread this ONE call over them")
 a = ap.parse_args()
 cfg = synth.CONFIGS[a.config]
 d = synth.make(a.config, m=a.users, n=a.items or cfg.n, p=a.factors or None)
@@ -28,9 +29,10 @@ if a.f64:
 F = synth.algorithmic_flops(cfg, d["X_train"], d["X_test"])
 for i in range(a.reps):
     r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], A, B, k=a.k or cfg.k, item_biases=d["item_biases"],
-                                cumulative=cfg.cumulative, break_ties_with_noise=a.noise, min_pos_test=cfg.min_pos_test, **kw)
+                                cumulative=cfg.cumulative, break_ties_with_noise=a.noise, min_pos_test=cfg.min_pos_test,
+                                devices=[int(x) for x in a.devices.split(",")] if a.devices else None, **kw)
     t = r.timing
     print(json.dumps({"rep": i, "dom_ms": round(t["dominant_kernel_ms"], 3), "users": a.users, "kernel_ms": t["score_select_ms"], "tflops": F / t["score_select_ms"] / 1e9,
                       "prep_ms": t["prep_ms"], "metrics_ms": t["metrics_ms"], "h2d_ms": t["h2d_ms"], "d2h_ms": t["d2h_ms"],
-                      "total_ms": t["total_ms"], "users_per_s_kernel": a.users / t["score_select_ms"] * 1e3,
+                      "total_ms": t["total_ms"], "devices_used": t["devices_used"], "users_per_s_e2e": a.users / t["total_ms"] * 1e3, "users_per_s_kernel": a.users / t["score_select_ms"] * 1e3,
                       "dom_ms": t["dominant_kernel_ms"], "retry_rows": t.get("filter_retry_rows"), "fallback": t.get("filter_fallback_batches")}))
