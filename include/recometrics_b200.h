@@ -54,7 +54,8 @@ enum rmb200_status {
     RMB200_ERR_UNSUPPORTED = 6   /* valid request outside what this build implements          */
 };
 
-/* Largest k_metrics the fused top-K selection handles in this build. */
+/* Largest k_metrics the fused top-K selection kernels handle.  Larger values (the reference's only bound is k_metrics <= n,
+ * src/recometrics.hpp:391) are computed as well, on the full-order path: every candidate scored and sorted in HBM. */
 #define RMB200_MAX_K 384
 
 /* Per-call timing breakdown (milliseconds, CUDA events on the call's stream). */
@@ -67,13 +68,15 @@ typedef struct rmb200_timing {
     double d2h_ms;          /* device->host result copies                                       */
     int64_t kernel_launches;/* kernels of this library launched by the call                     */
     int64_t h2d_bytes, d2h_bytes;
-    int64_t scoring_path;   /* which scoring kernel ran: 1 = FMA tiles, 2 = tensor-core filter + exact re-score */
+    int64_t scoring_path;   /* which scoring kernel ran: 1 = FMA tiles, 2 = tensor-core filter + exact re-score, 3 = full order */
     int64_t filter_fallback_batches; /* user batches the tensor-core filter handed back to the FMA path         */
     double dominant_kernel_ms; /* the scoring kernel alone (filter_select_kernel / score_select_kernel), all batches */
     int64_t filter_retry_rows; /* users whose sampled threshold guess failed its check (their CTA walked the catalogue twice) */
     int64_t filter_fallback_users;   /* users the tensor-core filter handed back to the FMA path (only they are re-run)          */
     double filter_err_ratio_max;     /* extra.filter_stats: largest |approximate - exact| / error bound over all re-scored       */
                                      /* candidates of the call (the bound holds iff this is <= 1)                                 */
+    int64_t noise_handback_users;    /* break_ties_with_noise with ROC/PR-AUC: users for whom the noise decides a rank (another candidate  */
+                                     /* within its reach of a held-out item) -- re-ranked on the full-order path with their noise          */
     int64_t devices_used;            /* GPUs the call ran on (1 unless rmb200_extra_t::devices / RMB200_DEVICES spread it); on a  */
                                      /* multi-GPU call the *_ms fields are the maximum over the devices, counters are sums        */
 } rmb200_timing_t;
@@ -100,8 +103,10 @@ typedef struct rmb200_extra {
     rmb200_timing_t *timing;    /* optional out                                                        */
     int32_t scoring_path;       /* 0 = automatic; 1 = FP32/FP64 FMA tiles for every score; 2 = tensor-core     */
                                 /* (fp16 tcgen05) candidate filter + exact FMA re-scoring of the survivors:    */
-                                /* same top-K, same scores; not available with ROC/PR-AUC (rank counting).     */
-                                /* Env RMB200_PATH=fma|tensor overrides 0.                                     */
+                                /* same top-K, same scores; not available with ROC/PR-AUC (rank counting);     */
+                                /* 3 = full order: every candidate scored, given its tie-breaking noise and    */
+                                /* sorted in HBM (what the reference does literally; any k_metrics <= n; slow). */
+                                /* Env RMB200_PATH=fma|tensor|full overrides 0.                                */
     int32_t skip_row_copy;      /* 1 (host-pointer calls): the per-user rows of every requested metric are computed  */
                                 /* in device memory but NOT copied back -- the non-NULL output pointers only say    */
                                 /* which metrics are wanted and are left untouched; use with metric_means           */

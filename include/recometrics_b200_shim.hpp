@@ -71,8 +71,20 @@ inline int call(const double *A, size_t lda, const double *B, size_t ldb, int32_
                 double *p, double *tp, double *r, double *ap, double *tap, double *ndcg, double *hit, double *rr,
                 double *roc, double *pr, bool ccs, int32_t mip, int32_t mpt, int32_t nthreads, uint64_t seed)
 {
+#ifdef RMB200_SHIM_NAN_BITS
+    /* R builds: undefined metrics are NA_REAL, not a plain NaN (src/recometrics.hpp:75-80 under _FOR_R).  Compile the
+     * wrapper with -DRMB200_SHIM_NAN_BITS=0x7FF00000000007A2ull (the bit pattern of NA_REAL). */
+    rmb200_extra_t ex = rmb200_extra_t();
+    ex.struct_size = (int32_t)sizeof(ex);
+    ex.device = -1;
+    ex.has_nan_bits = 1;
+    ex.nan_bits = (uint64_t)(RMB200_SHIM_NAN_BITS);
+    return rmb200_calc_metrics_ex_f64(A, lda, B, ldb, m, n, k, trp, tri, tep, tei, tev, k_metrics, cumulative, noise,
+                                      p, tp, r, ap, tap, ndcg, hit, rr, roc, pr, ccs, mip, mpt, nthreads, seed, NULL, &ex);
+#else
     return rmb200_calc_metrics_f64(A, lda, B, ldb, m, n, k, trp, tri, tep, tei, tev, k_metrics, cumulative, noise,
                                    p, tp, r, ap, tap, ndcg, hit, rr, roc, pr, ccs, mip, mpt, nthreads, seed);
+#endif
 }
 
 }  // namespace rmb200_shim

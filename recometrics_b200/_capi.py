@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("RMB200_LIB") or os.path.join(_HERE, "librecometrics_b200.so")
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_INTERRUPTED, ERR_UNSUPPORTED = range(7)
-MAX_K = 384
+MAX_K = 384     # largest k_metrics of the selection kernels; above it the call takes the full-order path
 
 # order of the ten outputs in the C signature (src/recometrics_signatures.hpp:56-65 of the reference)
 METRIC_ORDER = ("p", "tp", "r", "ap", "tap", "ndcg", "hit", "rr", "roc", "pr")
@@ -36,7 +36,7 @@ class Timing(ctypes.Structure):
         ("scoring_path", ctypes.c_int64), ("filter_fallback_batches", ctypes.c_int64),
         ("dominant_kernel_ms", ctypes.c_double), ("filter_retry_rows", ctypes.c_int64),
         ("filter_fallback_users", ctypes.c_int64), ("filter_err_ratio_max", ctypes.c_double),
-        ("devices_used", ctypes.c_int64),
+        ("noise_handback_users", ctypes.c_int64), ("devices_used", ctypes.c_int64),
     ]
 
     def as_dict(self):
@@ -179,7 +179,7 @@ def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, stri
     ex.user_end = int(user_end)
     ex.inputs_on_device = int(bool(inputs_on_device))
     ex.strict_min_pos_test = int(bool(strict_min_pos_test))
-    ex.scoring_path = {"auto": 0, "fma": 1, "tensor": 2}.get(scoring_path, scoring_path)
+    ex.scoring_path = {"auto": 0, "fma": 1, "tensor": 2, "full": 3}.get(scoring_path, scoring_path)
     ex.topk_items = _vp(topk_items)
     ex.topk_scores = _vp(topk_scores)
     ex.pos_rank = _vp(pos_rank)

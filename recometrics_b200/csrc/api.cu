@@ -26,6 +26,7 @@
 #include "prep.cuh"
 #include "score_select.cuh"
 #include "filter_select.cuh"
+#include "full_order.h"
 
 namespace {
 
@@ -213,13 +214,13 @@ struct CallArgs {
 };
 
 template <typename T, int C, bool AUC>
-cudaError_t launch_score_select_inst(const rmb::ScoreSelectParams<T>& P, int n_user_tiles, cudaStream_t st)
+cudaError_t launch_score_select_inst(const rmb::ScoreSelectParams<T>& P, int n_rows, cudaStream_t st)
 {
     auto kern = rmb::score_select_kernel<T, C, AUC>;
     const size_t smem = rmb::score_select_smem_bytes<T, AUC>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<n_user_tiles, rmb::NTHREADS, smem, st>>>(P);
+    kern<<<(n_rows + rmb::BM - 1) / rmb::BM, AUC ? rmb::AUC_THREADS : rmb::NTHREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
 
@@ -508,7 +509,6 @@ int run_call(const CallArgs<T>& a)
     if (!a.A || !a.B || !a.trp || !a.tep) { set_err("bad argument", "A, B, Xtrain_csr_p and Xtest_csr_p are required"); return RMB200_ERR_BAD_ARG; }
     if (a.lda < (size_t)a.k || a.ldb < (size_t)a.k) { set_err("bad argument", "lda/ldb smaller than k"); return RMB200_ERR_BAD_ARG; }
     if (a.out[5] && !a.tev) { set_err("bad argument", "NDCG requested but Xtest_csr (values) is NULL"); return RMB200_ERR_BAD_ARG; }
-    if (a.K > RMB200_MAX_K) { set_err("unsupported", "k_metrics larger than RMB200_MAX_K (384)"); return RMB200_ERR_UNSUPPORTED; }
     if (ex && ex->struct_size != (int32_t)sizeof(rmb200_extra_t)) { set_err("bad argument", "rmb200_extra_t::struct_size mismatch"); return RMB200_ERR_BAD_ARG; }
     bool any_out = false;
     for (int q = 0; q < 10; q++) any_out |= (a.out[q] != nullptr);
@@ -573,8 +573,12 @@ int run_call(const CallArgs<T>& a)
     // ---- which scoring path: tensor-core filter + exact re-scoring (top-K only), or FMA tiles ----
     int path_req = ex ? ex->scoring_path : 0;                       // 0 auto, 1 fma, 2 tensor
     if (path_req == 0) if (const char* env = std::getenv("RMB200_PATH")) {
-        if (!std::strcmp(env, "fma")) path_req = 1; else if (!std::strcmp(env, "tensor")) path_req = 2;
+        if (!std::strcmp(env, "fma")) path_req = 1; else if (!std::strcmp(env, "tensor")) path_req = 2; else if (!std::strcmp(env, "full")) path_req = 3;
     }
+    // k_metrics beyond what the selection kernels' candidate buffers hold: the full-order path (full_order.cu)
+    bool use_full = path_req == 3 || K > RMB200_MAX_K;
+    if (use_full && ex && (ex->scoring_path == 1 || ex->scoring_path == 2)) { set_err("unsupported", "scoring_path fma / tensor need k_metrics <= RMB200_MAX_K (384)"); return RMB200_ERR_UNSUPPORTED; }
+    if (use_full) path_req = 3;                                      // (an RMB200_PATH preference does not apply)
     const int KB = round_up(a.k + (a.bias ? 1 : 0), 16);            // fp16 factors per row (bias = one more factor)
     int f_stages = 0;
     {
@@ -587,16 +591,24 @@ int run_call(const CallArgs<T>& a)
     // With rank counting (ROC/PR-AUC) every score has to be exact: the FMA tiles do everything.  Exception: with the
     // reference's tie-breaking noise the ranked top-K comes from the tensor path as well (its exact stage is where the
     // noise is applied, tie_noise.cuh), after the FMA pass has counted the ranks.
-    const bool tensor_shape_ok = f_stages >= 2 && K <= 256;
+    const bool tensor_shape_ok = f_stages >= 2 && K <= 256 && !use_full;
     const bool tensor_ok = tensor_shape_ok && (!count_ranks || a.noise);
     if (path_req == 2 && !tensor_ok) { set_err("unsupported", "scoring_path=tensor needs no ROC/PR-AUC (rank counting), k <= ~400 and k_metrics <= 256"); return RMB200_ERR_UNSUPPORTED; }
     const bool use_tensor = tensor_ok && path_req != 1;
+    // break_ties_with_noise (the reference's default) where the tensor path's exact stage cannot apply it -- shapes only the FMA
+    // tiles handle (k_metrics 257..384, more than ~400 factors) or an RMB200_PATH=fma preference: the full-order path, which
+    // adds every candidate's draw before sorting.  Only an explicit scoring_path = 1 keeps the FMA tiles (noise-free order).
+    if (a.noise && !use_tensor && !use_full && !(ex && ex->scoring_path == 1)) { use_full = true; path_req = 3; }
     const bool fma_counts_first = use_tensor && count_ranks;
-    tm.scoring_path = use_tensor ? 2 : 1;
+    // ... and inside the rank counts (ROC/PR-AUC with the noise): the FMA tiles count on the noise-free scores and report, per
+    // held-out item, the candidates within the noise's reach; users for whom the noise decides a rank are handed to the full-order path
+    const bool noise_handback = a.noise && count_ranks && !use_full;
+    tm.scoring_path = use_full ? 3 : (use_tensor ? 2 : 1);
 #ifndef RMB_F_CMID
 #define RMB_F_CMID 512
 #endif
     if (use_tensor) C = (K <= 32) ? 256 : (K <= 128 ? RMB_F_CMID : 1024);
+    if (use_full) C = round_up(K < a.n ? K : a.n, 32);              // row pitch of the ranked lists
 
     // ---- CSR slices of users [ub, ue), index pointers re-based to the slice ----
     int lo_hi[4];   // trp[ub], trp[ue], tep[ub], tep[ue]
@@ -750,7 +762,7 @@ int run_call(const CallArgs<T>& a)
     }
 
     // ---- per-user state ----
-    DevBuf d_status, d_flags, d_umin, d_pos_raw, d_pos_sorted, d_pos_perm, d_auc, d_log2, d_pos_rank;
+    DevBuf d_status, d_flags, d_umin, d_pos_raw, d_pos_sorted, d_pos_perm, d_pos_item, d_auc, d_log2, d_pos_rank;
     CK(d_status.alloc((size_t)mr * sizeof(int)));
     CK(d_flags.alloc((size_t)mr * sizeof(int)));
     if (count_ranks) {
@@ -758,10 +770,12 @@ int run_call(const CallArgs<T>& a)
         CK(d_pos_raw.alloc(nnz_te * sizeof(T)));
         CK(d_pos_sorted.alloc(nnz_te * sizeof(T)));
         CK(d_pos_perm.alloc(nnz_te * sizeof(int)));
+        CK(d_pos_item.alloc(nnz_te * sizeof(int)));
         CK(d_auc.alloc(nnz_te * sizeof(unsigned int)));
         CK(cudaMemsetAsync(d_auc.p, 0, nnz_te * sizeof(unsigned int) + (nnz_te ? 0 : 16), st));
         CK(cudaMemsetAsync(d_pos_sorted.p, 0, nnz_te * sizeof(T) + (nnz_te ? 0 : 16), st));
         CK(cudaMemsetAsync(d_pos_perm.p, 0, nnz_te * sizeof(int) + (nnz_te ? 0 : 16), st));
+        CK(cudaMemsetAsync(d_pos_item.p, 0, nnz_te * sizeof(int) + (nnz_te ? 0 : 16), st));
     }
     long long* pos_rank_d = nullptr;
     if (ex && ex->pos_rank) {
@@ -796,7 +810,28 @@ int run_call(const CallArgs<T>& a)
     const int wave_users = nsm * BM;                       // one CTA (128 users) per SM
     int UB = 8 * wave_users;                               // users per batch (8 full waves)
     if (const char* env = std::getenv("RMB200_BATCH_USERS")) { const int v = std::atoi(env); if (v > 0) UB = round_up(v, BM); }
+    int fo_chunk = 0; size_t fo_bytes = 0;
+    if (use_full) {
+        // ranked lists (K entries per user) and cumulative rows (K columns per metric) of a batch within ~2 GB
+        const long long per_user = (long long)C * (long long)(sizeof(T) + 4) + (a.cumulative ? 8ll * K * (long long)sizeof(T) : 0);
+        long long cap = (2ll << 30) / (per_user > 0 ? per_user : 1);
+        cap = cap / BM * BM;
+        if (cap < BM) cap = BM;
+        if (UB > cap) UB = (int)cap;
+    }
     if (UB > round_up(mr, BM)) UB = round_up(mr, BM);
+    DevBuf d_fo, d_near, d_nz_mark, d_nz_list, d_nz_cnt, d_At_nz;
+    if (use_full) {
+        full_order_plan(a.n, (int)sizeof(T), UB, &fo_chunk, &fo_bytes);
+        CK(d_fo.alloc(fo_bytes));
+    }
+    if (noise_handback) {
+        CK(d_near.alloc(nnz_te * sizeof(unsigned)));
+        CK(cudaMemsetAsync(d_near.p, 0, nnz_te * sizeof(unsigned) + (nnz_te ? 0 : 16), st));
+        CK(d_nz_mark.alloc((size_t)UB * sizeof(int)));
+        CK(d_nz_list.alloc((size_t)UB * sizeof(int)));
+        CK(d_nz_cnt.alloc(16));
+    }
 
     DevBuf d_At, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
     CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
@@ -808,7 +843,9 @@ int run_call(const CallArgs<T>& a)
     int f_sample_tiles = 0, f_sample_stride = 1, f_sample_rank = 0;
     if (use_tensor) {
         const int NT = (a.n + 127) / 128;
-        bool on = NT >= 512;
+        int min_tiles = 512;
+        if (const char* env = std::getenv("RMB200_SAMPLE_MIN_TILES")) { const int v = std::atoi(env); if (v >= 16) min_tiles = v; }   // developer
+        bool on = NT >= min_tiles;
         if (const char* env = std::getenv("RMB200_SAMPLE")) on = on && std::atoi(env) != 0;
         if (on) {
             double frac = 7.0 / K;
@@ -904,16 +941,17 @@ int run_call(const CallArgs<T>& a)
             pack_tiles_kernel<T, BM><<<grid, block, 0, st>>>(Asrc, Ald, nb, a.k, d_At.as<T>(), nb_pad, p_pad);
             CK(cudaGetLastError());
             tm.kernel_launches++;
+
             if (!use_tensor) { int rc = staged_rows_consumed(); if (rc) return rc; }
         }
-        if (count_ranks) {
+        if (count_ranks && !use_full) {
             if (pf.test_rows_pending) { CK(cudaStreamWaitEvent(st, pf.test_rows, 0)); pf.test_rows_pending = false; }
             const int blocks = (nb + 7) / 8 < 8 * nsm ? (nb + 7) / 8 : 8 * nsm;
-            score_entries_kernel<T><<<blocks, 256, 0, st>>>(d_At.as<T>(), d_Bt.as<T>(), bias_d, p_pad, b0, nb,
+            score_entries_kernel<T, BM><<<blocks, 256, 0, st>>>(d_At.as<T>(), d_Bt.as<T>(), bias_d, p_pad, b0, nb,
                                                              tep_d, tei_d, d_status.as<int>(), d_pos_raw.as<T>());
             CK(cudaGetLastError());
-            sort_positives_kernel<T><<<blocks, 256, 0, st>>>(b0, nb, tep_d, d_status.as<int>(), d_pos_raw.as<T>(),
-                                                              d_pos_sorted.as<T>(), d_pos_perm.as<int>());
+            sort_positives_kernel<T><<<blocks, 256, 0, st>>>(b0, nb, tep_d, tei_d, d_status.as<int>(), d_pos_raw.as<T>(),
+                                                              d_pos_sorted.as<T>(), d_pos_perm.as<int>(), d_pos_item.as<int>());
             CK(cudaGetLastError());
             tm.kernel_launches += 2;
         }
@@ -922,7 +960,7 @@ int run_call(const CallArgs<T>& a)
         bool pk_pending = false;
         // fused score / exclude / select (/ rank counting) on the FMA pipe: the whole batch, or (umap) the listed users only
         auto run_fma = [&](const T* At_ptr, int n_rows, const int* umap, bool with_counts, bool timed) -> int {
-            ScoreSelectParams<T> sp;
+            ScoreSelectParams<T> sp = ScoreSelectParams<T>();       // (every field defined: optional ones stay null)
             sp.At = At_ptr; sp.Bt = d_Bt.as<T>(); sp.bias = bias_d;
             sp.p_pad = p_pad; sp.n = a.n; sp.mb = n_rows; sp.user0 = b0;
             sp.trp = trp_d; sp.tri = tri_d; sp.tep = tep_d; sp.ustatus = d_status.as<int>();
@@ -930,12 +968,25 @@ int run_call(const CallArgs<T>& a)
             sp.uflags = d_flags.as<int>(); sp.K = K;
             sp.pos_sorted = with_counts ? d_pos_sorted.as<T>() : nullptr;
             sp.auc_cnt = with_counts ? d_auc.as<unsigned int>() : nullptr;
+            sp.pos_item = with_counts ? d_pos_item.as<int>() : nullptr;
+            sp.auc_near = (with_counts && noise_handback) ? d_near.as<unsigned>() : nullptr;
             sp.umin = with_counts ? d_umin.as<unsigned long long>() : nullptr;
             sp.umap = umap;
+            if (const char* env = std::getenv("RMB200_AUC_DBG")) sp.dbg = std::atoi(env);      // developer: timing experiments (wrong results)
+            DevBuf d_clk;
+            if (with_counts && (sp.dbg & 64)) { CK(d_clk.alloc(64)); CK(cudaMemsetAsync(d_clk.p, 0, 64, st)); sp.dbg_clk = d_clk.as<unsigned long long>(); }
             if (timed) cudaEventRecord(pk.a, st);
-            CK(launch_score_select<T>(sp, C, with_counts, round_up(n_rows, BM) / BM, st));
+            CK(launch_score_select<T>(sp, C, with_counts, n_rows, st));
             if (timed) { cudaEventRecord(pk.b, st); pk_pending = true; }
             tm.kernel_launches++;
+            if (sp.dbg_clk) {
+                unsigned long long h[8];
+                CK(cudaMemcpyAsync(h, d_clk.p, 64, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                const double c = (double)(h[5] ? h[5] : 1);
+                std::fprintf(stderr, "[rmb200 auc clk] counting warp %d, kcycles per CTA: wait %.0f, mask %.0f, minima %.0f, count %.0f; held-out entries per warp %.1f\n",
+                             (sp.dbg >> 8) & 7, h[0] / c / 1e3, h[1] / c / 1e3, h[2] / c / 1e3, h[3] / c / 1e3, h[4] / c);
+            }
             return RMB200_OK;
         };
         auto run_fma_batch = [&]() -> int {
@@ -1031,14 +1082,75 @@ int run_call(const CallArgs<T>& a)
                 rc = run_fma(d_At_fb.as<T>(), n_over, d_fb_list.as<int>(), false, false);
                 if (rc) return rc;
             }
+        } else if (use_full) {
+            // every candidate scored, (noise,) sorted: ranked top-K, smallest candidate score and held-out ranks off the sorted lists
+            pt.start();
+            if (pf.test_rows_pending) { CK(cudaStreamWaitEvent(st, pf.test_rows, 0)); pf.test_rows_pending = false; }
+            FullOrderArgs<T> fo;
+            fo.At = d_At.as<T>(); fo.Bt = d_Bt.as<T>(); fo.bias = bias_d; fo.p_pad = p_pad; fo.n = a.n; fo.K = K; fo.C = C;
+            fo.user0 = b0; fo.nb = nb; fo.umap = nullptr;
+            fo.trp = trp_d; fo.tri = tri_d; fo.tep = tep_d; fo.tei = tei_d; fo.ustatus = d_status.as<int>(); fo.uflags = d_flags.as<int>();
+            fo.cand_score = d_cs.as<T>(); fo.cand_item = d_ci.as<int>(); fo.cand_count = d_cc.as<int>();
+            fo.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
+            fo.auc_cnt = count_ranks ? d_auc.as<unsigned int>() : nullptr;
+            fo.pos_perm = count_ranks ? d_pos_perm.as<int>() : nullptr;
+            fo.noise = a.noise; fo.seed_user0 = (unsigned long long)a.seed + (unsigned long long)(ub + b0);
+            fo.scratch = d_fo.p; fo.scratch_bytes = fo_bytes; fo.chunk_users = fo_chunk;
+            cudaEventRecord(pk.a, st);
+            long long nl = 0;
+            CK(full_order_run<T>(fo, st, &nl));
+            cudaEventRecord(pk.b, st);
+            pk_pending = true;
+            tm.kernel_launches += nl;
+            { int rc = prefetch_next_users(); if (rc) return rc; }
         } else {
             pt.start();
             int rc = run_fma_batch();
             if (rc) return rc;
         }
-        CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
-        tm.kernel_launches++;
-        if (a.noise && !use_tensor && !count_ranks) {
+        if (!use_full) {
+            CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
+            tm.kernel_launches++;
+        }
+        if (noise_handback) {
+            // users for whom the tie-breaking noise decides a rank: their ranked top-K and ranks from the full-order path
+            mark_noise_users_kernel<<<(nb + 255) / 256, 256, 0, st>>>(tep_d, d_near.as<unsigned>(), d_status.as<int>(), b0, nb, d_nz_mark.as<int>());
+            CK(cudaGetLastError());
+            CK(cudaMemsetAsync(d_nz_cnt.p, 0, 16, st));
+            collect_flagged_kernel<<<1, 1024, 0, st>>>(d_nz_mark.as<int>(), nb, d_nz_list.as<int>(), d_nz_cnt.as<int>());
+            CK(cudaGetLastError());
+            tm.kernel_launches += 2;
+            int n_nz = 0;
+            CK(cudaMemcpyAsync(&n_nz, d_nz_cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (n_nz > 0) {
+                tm.noise_handback_users += n_nz;
+                int rc = pack_Bt();
+                if (rc) return rc;
+                const int n_pad_u = round_up(n_nz, BM);
+                CK(d_At_nz.alloc((size_t)p_pad * n_pad_u * sizeof(T)));
+                dim3 grid(n_pad_u / 32, (p_pad + 31) / 32), block(32, 8);
+                pack_tiles_gather_kernel<T, BM><<<grid, block, 0, st>>>(Asrc, Ald, d_nz_list.as<int>(), n_nz, a.k, d_At_nz.as<T>(), n_pad_u, p_pad);
+                CK(cudaGetLastError());
+                tm.kernel_launches++;
+                { int rc2 = staged_rows_consumed(); if (rc2) return rc2; }
+                int chunk = 0; size_t bytes = 0;
+                full_order_plan(a.n, (int)sizeof(T), n_nz, &chunk, &bytes);
+                CK(d_fo.alloc(bytes));
+                FullOrderArgs<T> fo;
+                fo.At = d_At_nz.as<T>(); fo.Bt = d_Bt.as<T>(); fo.bias = bias_d; fo.p_pad = p_pad; fo.n = a.n; fo.K = K; fo.C = C;
+                fo.user0 = b0; fo.nb = n_nz; fo.umap = d_nz_list.as<int>();
+                fo.trp = trp_d; fo.tri = tri_d; fo.tep = tep_d; fo.tei = tei_d; fo.ustatus = d_status.as<int>(); fo.uflags = d_flags.as<int>();
+                fo.cand_score = d_cs.as<T>(); fo.cand_item = d_ci.as<int>(); fo.cand_count = d_cc.as<int>();
+                fo.umin = d_umin.as<unsigned long long>(); fo.auc_cnt = d_auc.as<unsigned int>(); fo.pos_perm = d_pos_perm.as<int>();
+                fo.noise = 1; fo.seed_user0 = (unsigned long long)a.seed + (unsigned long long)(ub + b0);
+                fo.scratch = d_fo.p; fo.scratch_bytes = bytes; fo.chunk_users = chunk;
+                long long nl = 0;
+                CK(full_order_run<T>(fo, st, &nl));
+                tm.kernel_launches += nl;
+            }
+        }
+        if (a.noise && !use_tensor && !use_full && !count_ranks) {
             all_equal_check_kernel<T><<<nb, 128, 0, st>>>(d_cs.as<T>(), d_cc.as<int>(), C, b0, K, a.n, trp_d, tri_d, d_status.as<int>(),
                                                            d_At.as<T>(), d_Bt.as<T>(), bias_d, p_pad, d_flags.as<int>());
             CK(cudaGetLastError());
@@ -1314,7 +1426,7 @@ int run_multi(const CallArgs<T>& a0, const std::vector<int>& devs_in)
             t.d2h_ms = std::max(t.d2h_ms, o.d2h_ms); t.dominant_kernel_ms = std::max(t.dominant_kernel_ms, o.dominant_kernel_ms);
             t.kernel_launches += o.kernel_launches; t.h2d_bytes += o.h2d_bytes; t.d2h_bytes += o.d2h_bytes;
             t.filter_fallback_batches += o.filter_fallback_batches; t.filter_retry_rows += o.filter_retry_rows;
-            t.filter_fallback_users += o.filter_fallback_users;
+            t.filter_fallback_users += o.filter_fallback_users; t.noise_handback_users += o.noise_handback_users;
             t.filter_err_ratio_max = std::max(t.filter_err_ratio_max, o.filter_err_ratio_max);
         }
         t.total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();

@@ -53,6 +53,21 @@ __global__ void pack_tiles_gather_kernel(const T* __restrict__ src, const size_t
     }
 }
 
+// break_ties_with_noise + rank counting: mark (-1) the users of the batch with a held-out item that has another candidate within
+// the noise's reach (near[e] counts the item itself as well): the noise decides one of their ranks.
+__global__ void mark_noise_users_kernel(const int* __restrict__ tep, const unsigned* __restrict__ near, const int* __restrict__ ustatus,
+                                        const int user0, const int nb, int* __restrict__ mark)
+{
+    const int ul = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ul >= nb) return;
+    const int u = user0 + ul;
+    int m = 0;
+    if (ustatus[u] == 0)
+        for (int e = tep[u]; e < tep[u + 1]; e++)
+            if (near[e] >= 2u) { m = -1; break; }
+    mark[ul] = m;
+}
+
 // Users of a batch the filter flagged (cand_count == -1), in ascending order: list[0 .. *count).  One block; the batch
 // has at most a few hundred thousand users and flagged ones are rare.
 __global__ void collect_flagged_kernel(const int* __restrict__ cand_count, const int nb, int* __restrict__ list, int* __restrict__ count)
@@ -116,7 +131,7 @@ __global__ void user_status_kernel(const StatusParams P)
 // One warp per user: score every held-out item of the user.  The accumulation is the sequential
 // fma chain over k = 0..p_pad-1 (then + bias) that score_select_kernel performs for the same
 // (user,item) pair, so both kernels produce bit-identical values.  At / Bt are the tiled slabs.
-template <typename T>
+template <typename T, int W>      // W: width of the user-factor tiles (BM, or AUC_UM for the rank-counting kernel's copy)
 __global__ void score_entries_kernel(const T* __restrict__ At, const T* __restrict__ Bt,
                                      const T* __restrict__ bias, const int p_pad, const int user0, const int mb,
                                      const int* __restrict__ tep, const int* __restrict__ tei,
@@ -129,25 +144,27 @@ __global__ void score_entries_kernel(const T* __restrict__ At, const T* __restri
         if (ustatus[u] != 0) continue;
         const int e0 = tep[u], e1 = tep[u + 1];
         constexpr int BN = NumTraits<T>::BN;
-        const T* a = At + (size_t)(ul / BM) * p_pad * BM + (ul % BM);
+        const T* a = At + (size_t)(ul / W) * p_pad * W + (ul % W);
         for (int e = e0 + lane; e < e1; e += 32) {
             const int item = tei[e];
             const T* b = Bt + (size_t)(item / BN) * p_pad * BN + (item % BN);
             T acc = (T)0;
             for (int k = 0; k < p_pad; k++)
-                acc = NumTraits<T>::fma(a[(size_t)k * BM], b[(size_t)k * BN], acc);
+                acc = NumTraits<T>::fma(a[(size_t)k * W], b[(size_t)k * BN], acc);
             if (bias != nullptr) acc += bias[item];
             pos_raw[e] = acc;
         }
     }
 }
 
-// One warp per user: rank-by-counting sort (ascending, stable) of the user's held-out scores.
-// pos_perm[sorted position] = entry offset inside the row.
+// One warp per user: rank-by-counting sort of the user's held-out scores, ascending; among equal scores the LARGER
+// item id first, so that a walk from the top meets tied items in ascending item id -- the order of the top-K selection
+// (ranks_before) and of the rank counts (score_select_kernel).
+// pos_perm[sorted position] = entry offset inside the row, pos_item[sorted position] = its item id.
 template <typename T>
-__global__ void sort_positives_kernel(const int user0, const int mb, const int* __restrict__ tep,
+__global__ void sort_positives_kernel(const int user0, const int mb, const int* __restrict__ tep, const int* __restrict__ tei,
                                       const int* __restrict__ ustatus, const T* __restrict__ pos_raw,
-                                      T* __restrict__ pos_sorted, int* __restrict__ pos_perm)
+                                      T* __restrict__ pos_sorted, int* __restrict__ pos_perm, int* __restrict__ pos_item)
 {
     const int warps_per_block = blockDim.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -161,10 +178,11 @@ __global__ void sort_positives_kernel(const int user0, const int mb, const int* 
             int rank = 0;
             for (int j = 0; j < npos; j++) {
                 const T w = pos_raw[e0 + j];
-                rank += (w < v) || (w == v && j < e);
+                rank += (w < v) || (w == v && j > e);          // (the row's item ids ascend with the entry offset)
             }
             pos_sorted[e0 + rank] = v;
             pos_perm[e0 + rank] = e;
+            pos_item[e0 + rank] = tei[e0 + e];
         }
     }
 }

@@ -28,9 +28,13 @@
 //     order-preserving integer image of the scores (warp REDUX counts; ties at the cut resolved by
 //     item id), which refreshes tau.  rank_topk_kernel finally orders the K survivors.
 //   * AUC mode (ROC/PR requested): the warp stages its 16 x BN score block in shared memory, masks
-//     train items there, and every lane counts, for the held-out items it owns, the candidates
-//     scoring strictly higher (compare + add, no atomics).  Scores of held-out items are
-//     pre-computed with the same FMA order (prep.cuh) so comparisons are exact.
+//     train items there, and counts for every held-out item of its rows the candidates of the tile
+//     that rank before it (score above, or equal with a smaller item id).  The held-out entries of
+//     the warp's 16 rows form one list dealt out to the 32 lanes, so the work is the sum of the
+//     rows' held-out counts, not 16 x their maximum; per score one compare on the ALU pipe and half
+//     a packed add on the FMA pipe; counters in global memory, one owner each (no atomics).
+//     Scores of held-out items are pre-computed with the same FMA order (prep.cuh) so comparisons
+//     are exact.
 //   * Everything outside the FMA loop is written as rolled loops / out-of-line calls: the epilogue
 //     runs once per item tile and must not evict the FMA loop from the instruction cache.
 #pragma once
@@ -47,6 +51,9 @@
 #ifndef RMB_UNROLL
 #define RMB_UNROLL 8        // factors per unrolled block of the FMA loop (multiple of KPAD)
 #endif
+#ifndef RMB_AUC_CLK
+#define RMB_AUC_CLK 0       // 1: developer build with cycle counters in the counting warps (score_select.cuh, auc_count_role)
+#endif
 #ifndef RMB_EARLYTRY
 #define RMB_EARLYTRY 0      // 1: probe the next stage's mbarrier one block before it is needed
 #endif
@@ -56,6 +63,14 @@ namespace rmb {
 constexpr int BM = 128;             // users per CTA tile (items per tile: NumTraits<T>::BN)
 constexpr int NCWARPS = 8;          // compute warps (16 user rows each)
 constexpr int NTHREADS = (NCWARPS + 1) * 32;   // + 1 producer warp
+// Rank-counting (AUC) mode is warp-specialised: next to the 8 FMA warps and the producer warp the CTA has 8 COUNTING warps.
+// FMA warp w hands the 16 x BN score block of every item tile to counting warp w through shared memory (one block per pair,
+// full / empty mbarriers) and goes on with the next tile's FMAs; the counting warp masks the train items, tracks the row
+// minima and counts the held-out items' ranks on the ALU pipe while the FMA pipe keeps running.  Registers are moved to
+// where they are needed with setmaxnreg (FMA warps 152 / counting warps 72 in float, 160 / 64 in double, producer warp group 32: exactly the 640 x 96 registers the CTA is launched with --
+// setmaxnreg only redistributes the CTA's own allocation).
+constexpr int AUC_THREADS = 640;    // 8 FMA warps + 8 counting warps + 1 producer warp (+ 3 idle warps: setmaxnreg works on groups of 4)
+constexpr int AUC_PCAP = 384;       // held-out entries per counting warp whose score / item id are staged in shared memory (the rest: global)
 constexpr int KPAD = 8;             // factors are zero-padded to a multiple of this
 constexpr unsigned FULL = 0xffffffffu;
 typedef unsigned long long u64;
@@ -184,9 +199,16 @@ struct ScoreSelectParams {
     int K;
     // rank counting (AUC mode)
     const T* __restrict__ pos_sorted;   // [nnz_test] held-out item scores, ascending per user
-    unsigned int* auc_cnt;              // [nnz_test] number of candidates scoring strictly above
-                                        // the j-th smallest held-out score of the row (zeroed)
+    const int* __restrict__ pos_item;   // [nnz_test] their item ids
+    unsigned int* auc_cnt;              // [nnz_test] number of candidates ranked before the j-th smallest held-out item
+                                        // of the row: scoring above it, or equal with a smaller item id (zeroed)
+    unsigned int* auc_near;             // optional [nnz_test] (break_ties_with_noise): number of candidates, the item itself included,
+                                        // whose score lies within the reach of the tie-breaking noise of the held-out item's
+                                        // (>= 2: the noise decides a rank of this user, api.cu hands the user to the full-order path)
     u64* umin;                          // [m] orderable(min candidate score), init ~0
+    unsigned long long* dbg_clk;        // developer (RMB200_AUC_DBG & 64): cycles of one counting warp per phase, summed over the CTAs
+    int dbg;                            // developer (RMB200_AUC_DBG, timing experiments only -- results are wrong): 1 counting warps skip the
+                                        // counting, 2 they skip masking / minima as well, 4 no hand-over of score blocks at all
     const int* __restrict__ umap;       // optional [mb]: row r of this launch is batch-local user umap[r] (CSR rows, status, flags and
                                         // candidate buffers are those of the mapped user; At holds the launch's rows in order).  Used
                                         // to re-run only the users the tensor-core filter handed back (api.cu)
@@ -383,27 +405,30 @@ struct RowState {
     int urow[BM];       // batch-local user of the row (its candidate buffer, status, flags): the row itself unless ScoreSelectParams::umap
 };
 
-template <typename T>
+template <typename T, bool AUC>
 struct SmemLayout {
-    static constexpr int S = NumTraits<T>::STAGES, BK = NumTraits<T>::BK, BN = NumTraits<T>::BN;
+    static constexpr int S = NumTraits<T>::STAGES, BN = NumTraits<T>::BN, BK = NumTraits<T>::BK;
     static constexpr size_t a_off = 0;                                            // [S][BK][BM]
     static constexpr size_t b_off = (size_t)S * BK * BM * sizeof(T);              // [S][BK][BN]
     static constexpr size_t rs_off = b_off + (size_t)S * BK * BN * sizeof(T);
-    static constexpr size_t bar_off = rs_off + ((sizeof(RowState<T>) + 15) & ~size_t(15));   // full[S], empty[S]
+    static constexpr size_t bar_off = rs_off + ((sizeof(RowState<T>) + 15) & ~size_t(15));   // full[S], empty[S] (AUC: + blk_full[NCWARPS], blk_empty[NCWARPS])
     static constexpr size_t plain_bytes = bar_off + 2 * S * sizeof(u64);
     // AUC mode only
-    static constexpr size_t blk_off = plain_bytes;                                // [NCWARPS][16][BN] score blocks
-    static constexpr size_t pj_off = blk_off + (size_t)NCWARPS * 16 * BN * sizeof(T);    // [BM][16] thresholds
-    static constexpr size_t cj_off = pj_off + (size_t)BM * 16 * sizeof(T);               // [BM][16] counters
-    static constexpr size_t auc_bytes = cj_off + (size_t)BM * 16 * sizeof(unsigned);
+    static constexpr int BNP = BN + 16 / (int)sizeof(T);                          // row pitch of a staged score block: consecutive rows
+                                                                                  // start 16 bytes apart in the banks (lanes of the
+                                                                                  // counting loop read several rows at once)
+    static constexpr size_t blk_off = plain_bytes + 2 * NCWARPS * sizeof(u64);    // [NCWARPS][16][BNP] score blocks
+    static constexpr size_t pref_off = blk_off + (size_t)NCWARPS * 16 * BNP * sizeof(T);  // [NCWARPS][20] held-out entries before row r of the warp
+    static constexpr size_t pthr_off = (pref_off + (size_t)2 * NCWARPS * 20 * sizeof(int) + 15) & ~size_t(15);   // (+ [NCWARPS][20] work units before row r); [NCWARPS][AUC_PCAP] held-out scores
+    static constexpr size_t pitem_off = pthr_off + (size_t)NCWARPS * AUC_PCAP * sizeof(T);     // [NCWARPS][AUC_PCAP] their item ids
+    static constexpr size_t auc_bytes = pitem_off + (size_t)NCWARPS * AUC_PCAP * sizeof(int);
 };
 
 template <typename T, bool AUC>
-inline size_t score_select_smem_bytes() { return AUC ? SmemLayout<T>::auc_bytes : SmemLayout<T>::plain_bytes; }
+inline size_t score_select_smem_bytes() { return AUC ? SmemLayout<T, AUC>::auc_bytes : SmemLayout<T, AUC>::plain_bytes; }
 
 extern __shared__ __align__(128) unsigned char smem_raw[];
-template <typename T>
-__device__ __forceinline__ RowState<T>* row_state() { return reinterpret_cast<RowState<T>*>(smem_raw + SmemLayout<T>::rs_off); }
+
 
 // ------------------------------------------------------------------ selection: out-of-line slow paths
 // One warp: cut the first nv (>= K) entries of a user's candidate buffer back to the best K
@@ -505,11 +530,10 @@ __device__ __forceinline__ void insert_candidate(RowState<T>* rs, T* cs, int* ci
 // A thread's scores of one user row in one item tile, at least one of which is not below tau.
 // item_lo = id of the first of the four columns.
 template <typename T>
-__device__ __noinline__ void row_slow(T* cs, int* ci, const int* __restrict__ tri, const int n, const T tau, const int row,
+__device__ __noinline__ void row_slow(RowState<T>* rs, T* cs, int* ci, const int* __restrict__ tri, const int n, const T tau, const int row,
                                       const int item_lo, const int item_end,
                                       const T s0, const T s1, const T s2, const T s3)
 {
-    RowState<T>* rs = row_state<T>();
     if (tau == NumTraits<T>::inf()) return;                     // row is not ranked (padding / NaN-row user)
     if (!(s0 < tau)) insert_candidate<T>(rs, cs, ci, tri, n, s0, row, item_lo, item_end);
     if (!(s1 < tau)) insert_candidate<T>(rs, cs, ci, tri, n, s1, row, item_lo + 1, item_end);
@@ -517,63 +541,364 @@ __device__ __noinline__ void row_slow(T* cs, int* ci, const int* __restrict__ tr
     if (!(s3 < tau)) insert_candidate<T>(rs, cs, ci, tri, n, s3, row, item_lo + 3, item_end);
 }
 
-// number of a / b / c / d strictly above p, subtracted as 0 / -1 masks (SASS: FSET + IADD3)
+// ---- rank counting: how many of the BN staged scores of a row lie strictly above a threshold ----
+// float: the compare leaves 1.0f / 0.0f (FSET.BF, the only ALU-pipe instruction per score) and the ones are added as packed
+// pairs on the FMA pipe (add.f32x2), four independent accumulators; a tile adds at most BN to each, exact in fp32.
+__device__ __forceinline__ float gt_one(const float a, const float p)
+{
+    float r;
+    asm("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(p));
+    return r;
+}
+__device__ __forceinline__ u64 add2(const u64 a, const u64 b)
+{
+    u64 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// NT thresholds at once: every 16-byte load of the row is compared with all of them (4 x NT independent compares per load).
+template <int NT>
+__device__ __forceinline__ void count_above(const float* __restrict__ src, const float (&thr)[NT], unsigned (&cnt)[NT])
+{
+    constexpr int BN = NumTraits<float>::BN;
+    u64 acc[NT][2];
+#pragma unroll
+    for (int t = 0; t < NT; t++) { acc[t][0] = 0ull; acc[t][1] = 0ull; }
+    float4 v = *reinterpret_cast<const float4*>(src);
+#pragma unroll 4
+    for (int x = 0; x < BN; x += 4) {
+        const float4 nv = *reinterpret_cast<const float4*>(src + ((x + 4) & (BN - 1)));      // next load in flight (wraps on the last one)
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            acc[t][0] = add2(acc[t][0], pack2(gt_one(v.x, thr[t]), gt_one(v.y, thr[t])));
+            acc[t][1] = add2(acc[t][1], pack2(gt_one(v.z, thr[t]), gt_one(v.w, thr[t])));
+        }
+        v = nv;
+    }
+#pragma unroll
+    for (int t = 0; t < NT; t++) {
+        float lo, hi;
+        unpack2(add2(acc[t][0], acc[t][1]), lo, hi);
+        cnt[t] = (unsigned)(lo + hi);
+    }
+}
 __device__ __forceinline__ unsigned gt_mask(const float a, const float p)
 {
     unsigned r;
     asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(p));
     return r;
 }
+// (developer variant: masks subtracted on the ALU pipe instead of packed adds on the FMA pipe)
+template <int NT>
+__device__ __forceinline__ void count_above_alu(const float* __restrict__ src, const float (&thr)[NT], unsigned (&cnt)[NT])
+{
+    constexpr int BN = NumTraits<float>::BN;
+    unsigned c0[NT], c1[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) { c0[t] = 0; c1[t] = 0; }
+#pragma unroll 2
+    for (int x = 0; x < BN; x += 4) {
+        const float4 v = *reinterpret_cast<const float4*>(src + x);
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            c0[t] -= gt_mask(v.x, thr[t]) + gt_mask(v.y, thr[t]);
+            c1[t] -= gt_mask(v.z, thr[t]) + gt_mask(v.w, thr[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; t++) cnt[t] = c0[t] + c1[t];
+}
+template <int NT>
+__device__ __forceinline__ void count_above_alu(const double* __restrict__ src, const double (&thr)[NT], unsigned (&cnt)[NT]);
 __device__ __forceinline__ unsigned gt_mask(const double a, const double p)
 {
     unsigned r;
     asm("set.gt.u32.f64 %0, %1, %2;" : "=r"(r) : "d"(a), "d"(p));
     return r;
 }
+template <int NT>
+__device__ __forceinline__ void count_above(const double* __restrict__ src, const double (&thr)[NT], unsigned (&cnt)[NT])
+{
+    constexpr int BN = NumTraits<double>::BN;
+    unsigned c0[NT], c1[NT];
+#pragma unroll
+    for (int t = 0; t < NT; t++) { c0[t] = 0; c1[t] = 0; }
+#pragma unroll 2
+    for (int x = 0; x < BN; x += 2) {
+        const double2 v = *reinterpret_cast<const double2*>(src + x);
+#pragma unroll
+        for (int t = 0; t < NT; t++) { c0[t] -= gt_mask(v.x, thr[t]); c1[t] -= gt_mask(v.y, thr[t]); }
+    }
+#pragma unroll
+    for (int t = 0; t < NT; t++) cnt[t] = c0[t] + c1[t];
+}
+template <int NT>
+__device__ __forceinline__ void count_above_alu(const double* __restrict__ src, const double (&thr)[NT], unsigned (&cnt)[NT]) { count_above<NT>(src, thr, cnt); }
+// How far apart two scores must be for the reference's tie-breaking noise (uniform in [-1e-12, 1e-12) added to each,
+// hpp:531-534) to be unable to swap them, as seen from a held-out score p: 0 where adding the noise gives the score back
+// (float: |p| >= 2^-13, double: |p| >= 2^16), else twice the noise plus the rounding of the two sums.
+__device__ __forceinline__ float noise_reach(const float p) { return fabsf(p) < 1.220703125e-4f ? fmaf(fabsf(p), 4.8e-7f, 2.0e-12f) : 0.f; }
+__device__ __forceinline__ double noise_reach(const double p) { return fabs(p) < 65536. ? fma(fabs(p), 8.9e-16, 2.0e-12) : 0.; }
 
-// AUC counting of one staged row (BN scores at src) against up to 4 thresholds per lane.
-template <typename T, int NT>
-__device__ __forceinline__ void count_above(const T* __restrict__ src, const T (&thr)[NT], unsigned (&cnt)[NT])
+// The largest value below x (IEEE nextafter towards -inf; x finite): "s >= x" is "s > next_below(x)".
+template <typename T>
+__device__ __forceinline__ T next_below(const T x)
+{
+    if (x == (T)0) return -NumTraits<T>::from_orderable(NumTraits<T>::orderable((T)0) + 1);     // -denorm_min (covers -0.0 as well)
+    return NumTraits<T>::from_orderable(NumTraits<T>::orderable(x) - 1);
+}
+
+// Producer: one thread runs the TMA ring over (item tile, k chunk).
+template <typename T, int S, int BK>
+__device__ __forceinline__ void tma_producer_role(const ScoreSelectParams<T>& P, T* As, T* Bs, const unsigned bar_full, const unsigned bar_empty,
+                                                  const int KC, const int total)
 {
     constexpr int BN = NumTraits<T>::BN;
-    constexpr int VEC = 16 / (int)sizeof(T);
+    const T* gA = P.At + (size_t)blockIdx.x * P.p_pad * BM;
+    int tile = 0, kc = 0;
+    for (int it = 0; it < total; it++) {
+        const int s = it % S;
+        if (it >= S) mbar_wait(bar_empty + 8 * s, ((it / S) - 1) & 1);
+        const int k0 = kc * BK;
+        const int kcount = (P.p_pad - k0) < BK ? (P.p_pad - k0) : BK;
+        const unsigned bytes_a = (unsigned)(kcount * BM * sizeof(T)), bytes_b = (unsigned)(kcount * BN * sizeof(T));
+        mbar_arrive_expect_tx(bar_full + 8 * s, bytes_a + bytes_b);
+        tma_bulk_g2s(smem_u32(As + (size_t)s * BK * BM), gA + (size_t)k0 * BM, bytes_a, bar_full + 8 * s);
+        tma_bulk_g2s(smem_u32(Bs + (size_t)s * BK * BN), P.Bt + ((size_t)tile * P.p_pad + k0) * BN, bytes_b, bar_full + 8 * s);
+        if (++kc == KC) { kc = 0; tile++; }
+    }
+}
+
+// break_ties_with_noise: a held-out entry the noise can move takes a pass of its own -- its rank count, and the candidates of the
+// tile inside [p - reach, p + reach] (auc_near: >= 2 over the catalogue = the noise decides a rank of this user, api.cu).
+template <typename T>
+__device__ __noinline__ void auc_count_banded(const ScoreSelectParams<T>& P, const T* __restrict__ src, const size_t e, const T p,
+                                              const int colp)
+{
+    constexpr int BN = NumTraits<T>::BN;
+    const T reach = noise_reach(p);
+    const unsigned before1 = P.auc_cnt[e], near0 = P.auc_near[e];
+    const T thr3[3] = {colp >= BN ? next_below<T>(p) : p, next_below<T>(p - reach), p + reach};
+    unsigned c3[3];
+    count_above<3>(src, thr3, c3);
+    unsigned ct = c3[0];
+    if (colp > 0 && colp < BN)
+        for (int x = 0; x < colp; x++) ct += (src[x] == p);
+    P.auc_cnt[e] = before1 + ct;
+    P.auc_near[e] = near0 + (c3[1] - c3[2]);
+}
+
+// Counting warp cw of the rank-counting kernel: for every item tile, the score block FMA warp cw staged for its 16 rows.
+//   * what is not a candidate is masked with NaN (never above a threshold, ignored by fmin): the train items of rows whose
+//     train row intersects the tile (own cursors, lane r <-> row r) and the padding columns of the last tile;
+//   * the smallest candidate score of every row (the full-order validity rule, hpp:555-562) is tracked;
+//   * for every held-out entry of the rows: the candidates of the tile that rank before it -- scoring above it, or equal
+//     with a smaller item id (the tie order of the top-K selection).  Tiles wholly before the entry's own item count
+//     "s >= score" (as "s > next_below(score)"), tiles after it "s > score"; the item's own tile "s > score" plus the
+//     equal scores in the columns before the item.  The held-out entries of the 16 rows form ONE list (pref[r] = entries
+//     before row r), cut into work units of up to four consecutive entries of one row; unit u belongs to lane u % 32 for
+//     the whole kernel (it alone updates the entries' counters in global memory: plain read-modify-write).  A unit is one
+//     pass over its row's BN scores, every 16-byte load compared with the unit's (up to) four thresholds: the work of a
+//     warp is the sum of its rows' held-out counts, spread evenly over the lanes.
+template <typename T>
+__device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowState<T>* rs, T* blk_all, int* pref_all, T* pthr_all, int* pitem_all,
+                                            const unsigned bar_blkf, const unsigned bar_blke, const int cw, const int lane,
+                                            const int tile_u0, const int NT)
+{
+    constexpr int BN = NumTraits<T>::BN;
+    constexpr int BNP = SmemLayout<T, true>::BNP;
+    const int wrow0 = cw * 16;
+    T* blk = blk_all + (size_t)cw * 16 * BNP;
+    int* pref = pref_all + cw * 20;
+    T* pthr = pthr_all + cw * AUC_PCAP;
+    int* pitem = pitem_all + cw * AUC_PCAP;
+
+    // the list of held-out entries, the first AUC_PCAP of them staged in shared memory
+    {
+        int v = lane < 16 ? rs->npos[wrow0 + lane] : 0;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int w = __shfl_up_sync(FULL, v, o);
+            if (lane >= o) v += w;
+        }
+        if (lane < 16) pref[lane + 1] = v;
+        if (lane == 0) pref[0] = 0;
+        __syncwarp();
+        const int staged = pref[16] < AUC_PCAP ? pref[16] : AUC_PCAP;
+        int row_l = 0;
+        for (int q = lane; q < staged; q += 32) {
+            while (q >= pref[row_l + 1]) row_l++;
+            const size_t e = (size_t)rs->tp0[wrow0 + row_l] + (size_t)(q - pref[row_l]);
+            pthr[q] = P.pos_sorted[e];
+            pitem[q] = P.pos_item[e];
+        }
+        __syncwarp();
+    }
+    // Work units: up to UN (four; double: two) consecutive entries of ONE row (a row with npos entries makes ceil(npos / UN)
+    // units); unit u belongs to lane u % 32 for the whole kernel.  upref[r] = units before row r.
+    constexpr int UN = sizeof(T) == 4 ? 4 : 2;
+    int* upref = pref + 20 * NCWARPS;                            // (second half of the prefix area)
+    {
+        int v = lane < 16 ? (rs->npos[wrow0 + lane] + UN - 1) / UN : 0;
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) {
+            const int w = __shfl_up_sync(FULL, v, o);
+            if (lane >= o) v += w;
+        }
+        if (lane < 16) upref[lane + 1] = v;
+        if (lane == 0) upref[0] = 0;
+        __syncwarp();
+    }
+    const int n_units = upref[16];
+    int unit_row[4];                                             // rows of the lane's first four units (further ones are looked up)
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        const int u = lane + 32 * j;
+        int r = 0;
+        while (r < 15 && u >= upref[r + 1]) r++;
+        unit_row[j] = r;
+    }
+    // own train cursor of row `lane` (lanes 0..15), minimum of half a row (row lane >> 1, columns (lane & 1) * BN / 2 ...)
+    int t_cur = 0, t_end = 0, t_nxt = INT_MAX;
+    if (lane < 16 && tile_u0 + wrow0 + lane < P.mb && rs->npos[wrow0 + lane] > 0) {      // (ranked rows have held-out items)
+        const int u = P.user0 + rs->urow[wrow0 + lane];
+        t_cur = P.trp[u]; t_end = P.trp[u + 1];
+        if (t_cur < t_end) t_nxt = P.tri[t_cur];
+    }
+    T rmin = NumTraits<T>::inf();
+
+    if (P.dbg & 4) return;
+#if RMB_AUC_CLK      // developer build: cycles per phase of one counting warp (RMB200_AUC_DBG & 64)
+    long long ck[6] = {0, 0, 0, 0, 0, 0};
+    const bool clk_on = P.dbg_clk != nullptr;
+#define AUC_CLK(i) if (clk_on) { const long long t_ = clock64(); ck[i] += t_ - t_prev; t_prev = t_; }
+    long long t_prev = clk_on ? clock64() : 0;
+#else
+#define AUC_CLK(i)
+#endif
+    for (int tile = 0; tile < NT; tile++) {
+        const int item0 = tile * BN;
+        mbar_wait(bar_blkf + 8 * cw, (unsigned)tile & 1u);
+        AUC_CLK(0)
+        if (P.dbg & 2) { __syncwarp(); if (lane == 0) mbar_arrive(bar_blke + 8 * cw); continue; }
+        if (lane < 16) {
+            T* dst = blk + (size_t)lane * BNP;
+            while (t_nxt < item0 + BN) {
+                dst[t_nxt - item0] = NumTraits<T>::nan();
+                t_cur++;
+                t_nxt = t_cur < t_end ? P.tri[t_cur] : INT_MAX;
+            }
+            if (item0 + BN > P.n)
+                for (int x = (P.n > item0 ? P.n - item0 : 0); x < BN; x++) dst[x] = NumTraits<T>::nan();
+        }
+        __syncwarp();
+        AUC_CLK(1)
+        {
+            const T* src = blk + (size_t)(lane >> 1) * BNP + (lane & 1) * (BN / 2);
+            constexpr int VEC = 16 / (int)sizeof(T);
+            T m0 = NumTraits<T>::inf(), m1 = NumTraits<T>::inf();
 #pragma unroll 4
-    for (int x = 0; x < BN; x += VEC) {
-        T v[VEC];
-        lds_vec(src + x, v);
+            for (int x = 0; x < BN / 2; x += 2 * VEC) {
+                T v[VEC], w[VEC];
+                lds_vec(src + x, v);
+                lds_vec(src + x + VEC, w);
 #pragma unroll
-        for (int q = 0; q < NT; q++)
+                for (int e = 0; e < VEC; e++) { m0 = fmin(m0, v[e]); m1 = fmin(m1, w[e]); }     // fmin ignores NaN
+            }
+            rmin = fmin(rmin, fmin(m0, m1));
+        }
+        AUC_CLK(2)
+        if (!(P.dbg & 1)) {
+            for (int j = 0, u = lane; u < n_units; j++, u += 32) {
+                int row_l;
+                if (j < 4) row_l = j == 0 ? unit_row[0] : (j == 1 ? unit_row[1] : (j == 2 ? unit_row[2] : unit_row[3]));
+                else { row_l = 0; while (row_l < 15 && u >= upref[row_l + 1]) row_l++; }
+                const int q = pref[row_l] + UN * (u - upref[row_l]);               // first entry of the unit
+                const int run = min(pref[row_l + 1] - q, UN);
+                const size_t e0 = (size_t)rs->tp0[wrow0 + row_l] + (size_t)(q - pref[row_l]);
+                const T* src = blk + (size_t)row_l * BNP;
+                T thr[UN], eff[UN];
+                int col[UN];
+                unsigned before[UN], c[UN];
+                unsigned banded = 0;                                          // entries within the noise's reach of other candidates: below
 #pragma unroll
-            for (int e = 0; e < VEC; e++) cnt[q] -= gt_mask(v[e], thr[q]);
+                for (int t = 0; t < UN; t++) {
+                    bool on = t < run;
+                    thr[t] = !on ? NumTraits<T>::inf() : (q + t < AUC_PCAP ? pthr[q + t] : P.pos_sorted[e0 + t]);
+                    if (on && P.auc_near != nullptr && noise_reach(thr[t]) > (T)0) { banded |= 1u << t; on = false; }
+                    before[t] = on ? P.auc_cnt[e0 + t] : 0u;
+                    col[t] = !on ? 0 : (q + t < AUC_PCAP ? pitem[q + t] : P.pos_item[e0 + t]) - item0;
+                    eff[t] = !on ? NumTraits<T>::inf() : (col[t] >= BN ? next_below<T>(thr[t]) : thr[t]);
+                }
+                if (sizeof(T) == 4 && (P.dbg & 16)) count_above_alu<UN>(src, eff, c);
+                else count_above<UN>(src, eff, c);
+#pragma unroll
+                for (int t = 0; t < UN; t++) {
+                    if (t < run && !((banded >> t) & 1u)) {
+                        unsigned ct = c[t];
+                        if (col[t] > 0 && col[t] < BN)
+                            for (int x = 0; x < col[t]; x++) ct += (src[x] == thr[t]);
+                        P.auc_cnt[e0 + t] = before[t] + ct;
+                    }
+                }
+                while (banded) {
+                    const int t = __ffs(banded) - 1;
+                    banded &= banded - 1;
+                    auc_count_banded<T>(P, src, e0 + t, t == 0 ? thr[0] : (t == 1 ? thr[1] : (UN > 2 && t == 2 ? thr[UN > 2 ? 2 : 0] : thr[UN - 1])),
+                                        (q + t < AUC_PCAP ? pitem[q + t] : P.pos_item[e0 + t]) - item0);
+                }
+            }
+        }
+        __syncwarp();
+        AUC_CLK(3)
+        if (lane == 0) mbar_arrive(bar_blke + 8 * cw);           // the FMA warp may stage its next block
+    }
+#if RMB_AUC_CLK
+    if (clk_on && lane == 0 && cw == (P.dbg >> 8 & 7)) {
+        for (int i = 0; i < 4; i++) atomicAdd(P.dbg_clk + i, (unsigned long long)ck[i]);
+        atomicAdd(P.dbg_clk + 4, (unsigned long long)pref[16]);
+        atomicAdd(P.dbg_clk + 5, 1ull);
+    }
+#endif
+#undef AUC_CLK
+    // smallest candidate score of every ranked row
+    rmin = fmin(rmin, __shfl_xor_sync(FULL, rmin, 1));
+    if ((lane & 1) == 0) {
+        const int row = wrow0 + (lane >> 1);
+        if (tile_u0 + row < P.mb && rs->npos[row] > 0 && rmin != NumTraits<T>::inf())
+            atomicMin(&P.umin[P.user0 + rs->urow[row]], NumTraits<T>::orderable(rmin));
     }
 }
 
 template <typename T, int C, bool AUC>
-__global__ void __launch_bounds__(NTHREADS, 1)
+__global__ void __launch_bounds__(AUC ? AUC_THREADS : NTHREADS, 1)
 score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 {
-    typedef SmemLayout<T> L;
-    constexpr int S = NumTraits<T>::STAGES;
-    constexpr int BK = NumTraits<T>::BK;
+    typedef SmemLayout<T, AUC> L;
+    constexpr int S = L::S;
+    constexpr int BK = L::BK;
     constexpr int BN = NumTraits<T>::BN;
+    constexpr int UM = BM;                           // users of this CTA
+    constexpr int NW = NCWARPS;                      // FMA warps
+    constexpr int NTHR = AUC ? AUC_THREADS : NTHREADS;
     constexpr int NC = MicroTile<T>::NC;            // item columns per thread
 
     T* As = reinterpret_cast<T*>(smem_raw + L::a_off);
     T* Bs = reinterpret_cast<T*>(smem_raw + L::b_off);
-    RowState<T>* rs = row_state<T>();
+    RowState<T>* rs = reinterpret_cast<RowState<T>*>(smem_raw + L::rs_off);
     const unsigned bar_full = smem_u32(smem_raw + L::bar_off), bar_empty = bar_full + 8 * S;
-    T* pj_s = reinterpret_cast<T*>(smem_raw + L::pj_off);                 // AUC only
-    unsigned* cj_s = reinterpret_cast<unsigned*>(smem_raw + L::cj_off);   // AUC only
+    const unsigned bar_blkf = bar_empty + 8 * S, bar_blke = bar_blkf + 8 * NCWARPS;      // AUC: score block of warp w handed over / taken
+    constexpr int BNP = L::BNP;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int tile_u0 = blockIdx.x * BM;            // first user (batch-local) of this CTA
+    const int tile_u0 = blockIdx.x * UM;            // first user (batch-local) of this CTA
     const int KC = (P.p_pad + BK - 1) / BK;
     const int NT = (P.n + BN - 1) / BN;
     const int total = NT * KC;
 
     // ---- one-time setup: per-row selection state, train cursors, barriers ----
-    for (int r = tid; r < BM; r += NTHREADS) {
+    for (int r = tid; r < UM; r += NTHR) {
         const int ul0 = tile_u0 + r;
         const int ul = (ul0 < P.mb && P.umap != nullptr) ? P.umap[ul0] : ul0;
         const bool ranked = (ul0 < P.mb) && (P.ustatus[P.user0 + ul] == 0);
@@ -592,51 +917,41 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
         rs->nxt_train[r] = cur < end ? P.tri[cur] : INT_MAX;
         rs->tp0[r] = tp0;
         rs->npos[r] = npos;
-        if (AUC) {
-            for (int j = 0; j < 16; j++) {
-                pj_s[r * 16 + j] = j < npos ? P.pos_sorted[tp0 + j] : NumTraits<T>::inf();
-                cj_s[r * 16 + j] = 0;
-            }
-        }
     }
     if (tid == 0) {
-        for (int s = 0; s < S; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, NCWARPS); }
+        for (int s = 0; s < S; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, NW); }
+        if (AUC)
+            for (int w = 0; w < NCWARPS; w++) { mbar_init(bar_blkf + 8 * w, 1); mbar_init(bar_blke + 8 * w, 1); }
         mbar_fence_init();
     }
     __syncthreads();   // the only CTA-wide barrier
 
-    if (warp == NCWARPS) {
-        // ===================== producer: TMA ring over (item tile, k chunk) =====================
-        if (lane == 0) {
-            const T* gA = P.At + (size_t)blockIdx.x * P.p_pad * BM;
-            int tile = 0, kc = 0;
-            for (int it = 0; it < total; it++) {
-                const int s = it % S;
-                if (it >= S) mbar_wait(bar_empty + 8 * s, ((it / S) - 1) & 1);
-                const int k0 = kc * BK;
-                const int kcount = (P.p_pad - k0) < BK ? (P.p_pad - k0) : BK;
-                const unsigned bytes_a = (unsigned)(kcount * BM * sizeof(T)), bytes_b = (unsigned)(kcount * BN * sizeof(T));
-                mbar_arrive_expect_tx(bar_full + 8 * s, bytes_a + bytes_b);
-                tma_bulk_g2s(smem_u32(As + (size_t)s * BK * BM), gA + (size_t)k0 * BM, bytes_a, bar_full + 8 * s);
-                tma_bulk_g2s(smem_u32(Bs + (size_t)s * BK * BN), P.Bt + ((size_t)tile * P.p_pad + k0) * BN, bytes_b,
-                             bar_full + 8 * s);
-                if (++kc == KC) { kc = 0; tile++; }
-            }
+    if (AUC) {
+        // registers to where they are needed (every warp of a group of four executes the same setmaxnreg)
+        if (warp >= 2 * NCWARPS) {
+            asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
+            if (warp == 2 * NCWARPS && lane == 0) tma_producer_role<T, S, BK>(P, As, Bs, bar_full, bar_empty, KC, total);
+            return;
         }
+        if (warp >= NCWARPS) {
+            if (sizeof(T) == 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
+            else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+            auc_count_role<T>(P, rs, reinterpret_cast<T*>(smem_raw + L::blk_off), reinterpret_cast<int*>(smem_raw + L::pref_off),
+                              reinterpret_cast<T*>(smem_raw + L::pthr_off), reinterpret_cast<int*>(smem_raw + L::pitem_off),
+                              bar_blkf, bar_blke, warp - NCWARPS, lane, tile_u0, NT);
+            return;
+        }
+        if (sizeof(T) == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
+    } else if (warp == NCWARPS) {
+        if (lane == 0) tma_producer_role<T, S, BK>(P, As, Bs, bar_full, bar_empty, KC, total);
         return;
     }
 
     // ===================== compute warps =====================
     const int ly = lane >> 4, lx = lane & 15;
     const int wrow0 = warp * 16;                    // first CTA row of this warp
-    T* blk = reinterpret_cast<T*>(smem_raw + L::blk_off) + (size_t)warp * 16 * BN;   // AUC only: [16][BN]
-
-    T rowmin[AUC ? 8 : 1];                          // AUC: smallest candidate score seen per thread row
-    if (AUC) {
-#pragma unroll
-        for (int i = 0; i < 8; i++) rowmin[i] = NumTraits<T>::inf();
-    }
-
+    T* blk = reinterpret_cast<T*>(smem_raw + L::blk_off) + (size_t)warp * 16 * BNP;   // AUC only: [16][BNP]
     MicroTile<T> mt;
     typename MicroTile<T>::Frag frag[2];            // operand registers, double buffered across k
     int it = 0;
@@ -649,7 +964,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
             if (!ready) mbar_wait(bar_full + 8 * s, (it / S) & 1);
             const int k0 = kc * BK;
             const int kcount = (P.p_pad - k0) < BK ? (P.p_pad - k0) : BK;
-            const T* sA = As + (size_t)s * BK * BM + wrow0;
+            const T* sA = As + (size_t)s * BK * UM + wrow0;
             const T* sB = Bs + (size_t)s * BK * BN;
 #if RMB_SWPIPE
             MicroTile<T>::load(frag[0], sA, sB, ly, lx);
@@ -661,7 +976,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 #pragma unroll
                 for (int kk = 0; kk < KPAD; kk++) {
                     if (kk + 1 < KPAD || kk0 + KPAD < kcount)
-                        MicroTile<T>::load(frag[(kk + 1) & 1], sA + (kk0 + kk + 1) * BM, sB + (kk0 + kk + 1) * BN, ly, lx);
+                        MicroTile<T>::load(frag[(kk + 1) & 1], sA + (kk0 + kk + 1) * UM, sB + (kk0 + kk + 1) * BN, ly, lx);
                     mt.compute(frag[kk & 1]);
                 }
             }
@@ -674,7 +989,8 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 #pragma unroll
                 for (int kk = 0; kk < RMB_UNROLL; kk++) {
                     if (RMB_UNROLL > KPAD && kk0 + kk >= kcount) break;     // only the tail chunk of a k that is not a multiple of the unroll
-                    MicroTile<T>::load(frag[0], sA + (kk0 + kk) * BM, sB + (kk0 + kk) * BN, ly, lx);
+                    if (AUC && (P.dbg & 8) && kk > 0) continue;             // (developer: one k step per block -- the counting warps set the pace)
+                    MicroTile<T>::load(frag[0], sA + (kk0 + kk) * UM, sB + (kk0 + kk) * BN, ly, lx);
                     mt.compute(frag[0]);
                 }
             }
@@ -690,9 +1006,8 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 #pragma unroll
             for (int c = 0; c < NC; c++) biasv[c] = P.bias[item0 + lx * 4 + (c & 3) + (c >> 2) * 64];
         }
-        const bool tile_has_padding = item0 + BN > P.n;
         bool inserted = false;
-        unsigned remask = 0;                         // AUC: thread rows whose minimum must be re-read after masking
+        if (AUC && tile > 0 && !(P.dbg & 4)) mbar_wait(bar_blke + 8 * warp, (unsigned)(tile - 1) & 1u);      // the counting warp is done with the previous block
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const int row_l = ly * 4 + (i & 3) + (i >> 2) * 8;
@@ -709,90 +1024,19 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
             if (!(m < tau)) {
                 T* cs = P.cand_score + (size_t)rs->urow[row] * C;
                 int* ci = P.cand_item + (size_t)rs->urow[row] * C;
-                row_slow<T>(cs, ci, P.tri, P.n, tau, row, item0 + lx * 4, item0 + BN, s[0], s[1], s[2], s[3]);
+                row_slow<T>(rs, cs, ci, P.tri, P.n, tau, row, item0 + lx * 4, item0 + BN, s[0], s[1], s[2], s[3]);
                 if (NC == 8)
-                    row_slow<T>(cs, ci, P.tri, P.n, tau, row, item0 + 64 + lx * 4, item0 + BN, s[NC - 4], s[NC - 3], s[NC - 2], s[NC - 1]);
+                    row_slow<T>(rs, cs, ci, P.tri, P.n, tau, row, item0 + 64 + lx * 4, item0 + BN, s[NC - 4], s[NC - 3], s[NC - 2], s[NC - 1]);
                 inserted = true;
             }
-            if (AUC) {
-                if (tile_has_padding || rs->nxt_train[row] < item0 + BN) {
-                    remask |= 1u << i;               // some of these are not candidates: exact minimum below
-                } else {
-                    T mn = fmin(fmin(s[0], s[1]), fmin(s[2], s[3]));      // fmin ignores NaN
-                    if (NC == 8) mn = fmin(mn, fmin(fmin(s[NC - 4], s[NC - 3]), fmin(s[NC - 2], s[NC - 1])));
-                    rowmin[i] = fmin(rowmin[i], mn);
-                }
-                T* dst = blk + (size_t)row_l * BN + lx * 4;
+            if (AUC && !(P.dbg & 4)) {
+                T* dst = blk + (size_t)row_l * BNP + lx * 4;
                 sts4(dst, &s[0]);
                 if (NC == 8) sts4(dst + 64, &s[NC - 4]);
             }
         }
         __syncwarp();
-
-        if (AUC) {
-            // mask (with NaN: never above a threshold, ignored by fmin) what is not a candidate in the
-            // staged block: train items of rows whose train row intersects this tile, and the padding
-            // columns of the last tile (lane r <-> row r)
-            if (lane < 16) {
-                const int row = wrow0 + lane;
-                T* dst = blk + (size_t)lane * BN;
-                if (rs->nxt_train[row] < item0 + BN) {
-                    const int end = rs->end_train[row];
-                    for (int c = rs->cur_train[row]; c < end; c++) {
-                        const int item = P.tri[c];
-                        if (item >= item0 + BN) break;
-                        dst[item - item0] = NumTraits<T>::nan();
-                    }
-                }
-                if (tile_has_padding)
-                    for (int x = (P.n > item0 ? P.n - item0 : 0); x < BN; x++) dst[x] = NumTraits<T>::nan();
-            }
-            __syncwarp();
-            if (__any_sync(FULL, remask != 0)) {
-#pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (remask & (1u << i)) {
-                        const int row_l = ly * 4 + (i & 3) + (i >> 2) * 8;
-                        const T* src = blk + (size_t)row_l * BN + lx * 4;
-                        T mn = NumTraits<T>::inf();
-#pragma unroll
-                        for (int c = 0; c < NC; c++) {
-                            const T v = src[(c & 3) + (c >> 2) * 64];
-                            mn = fmin(mn, v);                             // masked entries are NaN: ignored
-                        }
-                        rowmin[i] = fmin(rowmin[i], mn);
-                    }
-                }
-            }
-            // count: lane (ly, lx) owns held-out slots lx, lx+16, ... of rows 2*rp + ly
-            for (int rp = 0; rp < 8; rp++) {
-                const int row_l = 2 * rp + ly;
-                const int row = wrow0 + row_l;
-                const T* src = blk + (size_t)row_l * BN;
-                {
-                    const T thr[1] = {pj_s[row * 16 + lx]};
-                    unsigned c[1] = {0};
-                    count_above<T, 1>(src, thr, c);
-                    cj_s[row * 16 + lx] += c[0];
-                }
-                // rows with more than 16 held-out items: further slots, 4 at a time, counters in global memory
-                const int npos = rs->npos[row];
-                if (npos > 16) {
-                    const int tp0 = rs->tp0[row];
-                    for (int j0 = 16 + lx; j0 < npos; j0 += 64) {
-                        T thr[4];
-                        unsigned c[4] = {0, 0, 0, 0};
-#pragma unroll
-                        for (int q = 0; q < 4; q++) thr[q] = (j0 + 16 * q < npos) ? P.pos_sorted[tp0 + j0 + 16 * q] : NumTraits<T>::inf();
-                        count_above<T, 4>(src, thr, c);
-#pragma unroll
-                        for (int q = 0; q < 4; q++)
-                            if (c[q]) P.auc_cnt[(size_t)tp0 + j0 + 16 * q] += c[q];     // single owner: plain read-modify-write
-                    }
-                }
-            }
-            __syncwarp();
-        }
+        if (AUC && lane == 0 && !(P.dbg & 4)) mbar_arrive(bar_blkf + 8 * warp);      // the tile's score block is the counting warp's now
 
         // advance the train cursors of the warp's rows past this tile (lanes 0..15, rare)
         if (lane < 16) {
@@ -832,18 +1076,6 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
                 P.cand_count[ul] = rs->cnt[row];
                 if (rs->nan[row]) atomicOr(&P.uflags[P.user0 + ul], 1);
             }
-        }
-    }
-    if (AUC) {
-        for (int e = lane; e < 16 * 16; e += 32) {
-            const int row = wrow0 + (e >> 4), j = e & 15;
-            if (j < rs->npos[row]) P.auc_cnt[(size_t)rs->tp0[row] + j] = cj_s[row * 16 + j];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const int row = wrow0 + ly * 4 + (i & 3) + (i >> 2) * 8;
-            if (tile_u0 + row < P.mb && rs->npos[row] > 0 && rowmin[i] != NumTraits<T>::inf())
-                atomicMin(&P.umin[P.user0 + rs->urow[row]], NumTraits<T>::orderable(rowmin[i]));
         }
     }
 }

@@ -7,6 +7,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cmath>
+#include <cstring>
 #include <stdexcept>
 #ifdef HAVE_REFERENCE_HEADER
 #include "recometrics_signatures.hpp"
@@ -48,6 +49,21 @@ int main()
         // users 0 and 1 rank their held-out item first, user 2 ranks item 3 (score 1) behind items 0..2? scores: 1, 1, 1, 1 -> tie row
         std::printf("ok p=%g,%g ndcg=%g,%g pd=%g\n", p[0], p[1], ndcg[0], ndcg[1], pd[0]);
         if (!(std::fabs(p[0] - 0.5f) < 1e-6f && std::fabs(p[1] - 0.5f) < 1e-6f && std::fabs(pd[0] - 0.5) < 1e-12)) return 3;
+#ifdef RMB200_SHIM_NAN_BITS
+        {
+            // R build of the shim: a user without held-out items gets NA_REAL rows (src/recometrics.hpp:75-80), bit for bit
+            const int32_t tep2[4] = {0, 1, 1, 2};              // user 1 holds nothing out
+            int32_t tei2[2] = {0, 3};
+            const double tev2[2] = {1., 1.};
+            double q[3] = {0., 0., 0.};
+            calc_metrics<double>(Ad, 2, Bd, 2, 3, 4, 2, trp, nullptr, tep2, tei2, tev2, 2, false, false, q, nullptr, nullptr, nullptr, nullptr,
+                                 nullptr, nullptr, nullptr, nullptr, nullptr, true, 2, 1, 1, 1);
+            uint64_t bits;
+            std::memcpy(&bits, &q[1], 8);
+            std::printf("na_bits=%s (%llx)\n", bits == (uint64_t)(RMB200_SHIM_NAN_BITS) ? "ok" : "WRONG", (unsigned long long)bits);
+            if (bits != (uint64_t)(RMB200_SHIM_NAN_BITS) || !(std::fabs(q[0] - 0.5) < 1e-12)) return 4;
+        }
+#endif
     } catch (const std::runtime_error& e) {
         threw = 1;
         std::printf("threw runtime_error: %s\n", e.what());

@@ -38,7 +38,7 @@ def test_library_exports_every_declared_symbol(rb):
 def test_extra_struct_layout_matches_header(rb):
     """ctypes mirror of rmb200_extra_t / rmb200_timing_t has the C layout (LP64)."""
     from recometrics_b200 import _capi
-    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 10 * 8
+    assert ctypes.sizeof(_capi.Timing) == 6 * 8 + 11 * 8
     assert ctypes.sizeof(_capi.Extra) == 6 * 4 + 5 * 8 + 2 * 4 + 2 * 8 + 2 * 4 + 8 + 8 + 2 * 4
     assert _capi.Extra.nan_bits.offset == 96 and _capi.Extra.devices.offset == 104
     assert _capi.Extra.topk_items.offset == 24
@@ -156,12 +156,16 @@ def test_cpp_shim_is_a_drop_in_for_the_reference_declarations(tmp_path):
     ref_src = "/root/reference/src"
     if os.path.exists(os.path.join(ref_src, "recometrics_signatures.hpp")):
         cmd += ["-DHAVE_REFERENCE_HEADER", "-I", ref_src]
-    cmd += [os.path.join(root, "tests", "shim", "shim_dropin.cpp"), "-o", exe, "-L", libdir, "-lrecometrics_b200", "-Wl,-rpath," + libdir]
-    subprocess.run(cmd, check=True, capture_output=True, text=True)
-    run = subprocess.run([exe], capture_output=True, text=True, timeout=120)
-    assert run.returncode == 0, run.stdout + run.stderr
-    if rb.device_count() == 0:
-        assert "threw runtime_error" in run.stdout
+    tail = [os.path.join(root, "tests", "shim", "shim_dropin.cpp"), "-L", libdir, "-lrecometrics_b200", "-Wl,-rpath," + libdir]
+    # as the Python build would use it, and as an R build would (undefined metrics written as NA_REAL, hpp:75-80)
+    for tag, extra in (("py", []), ("r", ["-DRMB200_SHIM_NAN_BITS=0x7FF00000000007A2ull"])):
+        subprocess.run(cmd + extra + tail + ["-o", exe + tag], check=True, capture_output=True, text=True)
+        run = subprocess.run([exe + tag], capture_output=True, text=True, timeout=120)
+        assert run.returncode == 0, run.stdout + run.stderr
+        if rb.device_count() == 0:
+            assert "threw runtime_error" in run.stdout
+        elif tag == "r":
+            assert "na_bits=ok" in run.stdout, run.stdout
 
 
 _CY_PROBE = r"""

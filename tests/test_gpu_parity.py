@@ -526,9 +526,13 @@ def test_sigint_stops_the_call_between_user_batches(scoring_path):
 
 
 def test_unsupported_requests_fail_loudly(rb):
+    """k_metrics beyond the selection kernels' buffers is computed (full-order path, tests/test_gpu_full_order.py) unless
+    the caller insists on a selection path."""
     d = synth.make(1, m=100, n=900, p=8)
+    df = rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=500, break_ties_with_noise=False)
+    assert df.shape[0] == 100
     with pytest.raises(NotImplementedError):
-        rb.calc_reco_metrics(d["X_train"], d["X_test"], d["A"], d["B"], k=500, break_ties_with_noise=False)
+        rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=500, break_ties_with_noise=False, scoring_path="tensor")
 
 
 def test_tensor_filter_path_equals_fma_path_bit_for_bit(rb):

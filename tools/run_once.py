@@ -15,11 +15,12 @@ ap.add_argument("--factors", type=int, default=0)
 ap.add_argument("--k", type=int, default=0)
 ap.add_argument("--f64", action="store_true")
 ap.add_argument("--noise", action="store_true", help="break_ties_with_noise=True (the reference default)")
+ap.add_argument("--no-auc", action="store_true", help="drop ROC/PR-AUC from the configuration's metrics")
 ap.add_argument("--devices", default="", help="comma-separated CUDA ordinals: spread this ONE call over them")
 a = ap.parse_args()
 cfg = synth.CONFIGS[a.config]
 d = synth.make(a.config, m=a.users, n=a.items or cfg.n, p=a.factors or None)
-flags = {q: (q in cfg.metrics) for q in synth.ALL10}
+flags = {q: (q in cfg.metrics) and not (a.no_auc and q in ("roc", "pr")) for q in synth.ALL10}
 kw = dict(precision=flags["p"], trunc_precision=flags["tp"], recall=flags["r"], average_precision=flags["ap"],
           trunc_average_precision=flags["tap"], ndcg=flags["ndcg"], hit=flags["hit"], rr=flags["rr"],
           roc_auc=flags["roc"], pr_auc=flags["pr"])
