@@ -973,20 +973,10 @@ int run_call(const CallArgs<T>& a)
             sp.umin = with_counts ? d_umin.as<unsigned long long>() : nullptr;
             sp.umap = umap;
             if (const char* env = std::getenv("RMB200_AUC_DBG")) sp.dbg = std::atoi(env);      // developer: timing experiments (wrong results)
-            DevBuf d_clk;
-            if (with_counts && (sp.dbg & 64)) { CK(d_clk.alloc(64)); CK(cudaMemsetAsync(d_clk.p, 0, 64, st)); sp.dbg_clk = d_clk.as<unsigned long long>(); }
             if (timed) cudaEventRecord(pk.a, st);
             CK(launch_score_select<T>(sp, C, with_counts, n_rows, st));
             if (timed) { cudaEventRecord(pk.b, st); pk_pending = true; }
             tm.kernel_launches++;
-            if (sp.dbg_clk) {
-                unsigned long long h[8];
-                CK(cudaMemcpyAsync(h, d_clk.p, 64, cudaMemcpyDeviceToHost, st));
-                CK(cudaStreamSynchronize(st));
-                const double c = (double)(h[5] ? h[5] : 1);
-                std::fprintf(stderr, "[rmb200 auc clk] counting warp %d, kcycles per CTA: wait %.0f, mask %.0f, minima %.0f, count %.0f; held-out entries per warp %.1f\n",
-                             (sp.dbg >> 8) & 7, h[0] / c / 1e3, h[1] / c / 1e3, h[2] / c / 1e3, h[3] / c / 1e3, h[4] / c);
-            }
             return RMB200_OK;
         };
         auto run_fma_batch = [&]() -> int {

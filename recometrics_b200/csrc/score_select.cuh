@@ -51,9 +51,6 @@
 #ifndef RMB_UNROLL
 #define RMB_UNROLL 8        // factors per unrolled block of the FMA loop (multiple of KPAD)
 #endif
-#ifndef RMB_AUC_CLK
-#define RMB_AUC_CLK 0       // 1: developer build with cycle counters in the counting warps (score_select.cuh, auc_count_role)
-#endif
 #ifndef RMB_EARLYTRY
 #define RMB_EARLYTRY 0      // 1: probe the next stage's mbarrier one block before it is needed
 #endif
@@ -206,9 +203,8 @@ struct ScoreSelectParams {
                                         // whose score lies within the reach of the tie-breaking noise of the held-out item's
                                         // (>= 2: the noise decides a rank of this user, api.cu hands the user to the full-order path)
     u64* umin;                          // [m] orderable(min candidate score), init ~0
-    unsigned long long* dbg_clk;        // developer (RMB200_AUC_DBG & 64): cycles of one counting warp per phase, summed over the CTAs
     int dbg;                            // developer (RMB200_AUC_DBG, timing experiments only -- results are wrong): 1 counting warps skip the
-                                        // counting, 2 they skip masking / minima as well, 4 no hand-over of score blocks at all
+                                        // counting, 2 they skip masking / minima as well, 4 no hand-over of score blocks at all, 8 the FMA warps do a quarter of their FMAs
     const int* __restrict__ umap;       // optional [mb]: row r of this launch is batch-local user umap[r] (CSR rows, status, flags and
                                         // candidate buffers are those of the mapped user; At holds the launch's rows in order).  Used
                                         // to re-run only the users the tensor-core filter handed back (api.cu)
@@ -418,8 +414,8 @@ struct SmemLayout {
                                                                                   // start 16 bytes apart in the banks (lanes of the
                                                                                   // counting loop read several rows at once)
     static constexpr size_t blk_off = plain_bytes + 2 * NCWARPS * sizeof(u64);    // [NCWARPS][16][BNP] score blocks
-    static constexpr size_t pref_off = blk_off + (size_t)NCWARPS * 16 * BNP * sizeof(T);  // [NCWARPS][20] held-out entries before row r of the warp
-    static constexpr size_t pthr_off = (pref_off + (size_t)2 * NCWARPS * 20 * sizeof(int) + 15) & ~size_t(15);   // (+ [NCWARPS][20] work units before row r); [NCWARPS][AUC_PCAP] held-out scores
+    static constexpr size_t pref_off = blk_off + (size_t)NCWARPS * 16 * BNP * sizeof(T);  // [BM + 4] held-out entries before row r, [BM + 4] work units before row r
+    static constexpr size_t pthr_off = (pref_off + (size_t)2 * (BM + 4) * sizeof(int) + 15) & ~size_t(15);      // [NCWARPS * AUC_PCAP] held-out scores
     static constexpr size_t pitem_off = pthr_off + (size_t)NCWARPS * AUC_PCAP * sizeof(T);     // [NCWARPS][AUC_PCAP] their item ids
     static constexpr size_t auc_bytes = pitem_off + (size_t)NCWARPS * AUC_PCAP * sizeof(int);
 };
@@ -557,6 +553,27 @@ __device__ __forceinline__ u64 add2(const u64 a, const u64 b)
     return r;
 }
 // NT thresholds at once: every 16-byte load of the row is compared with all of them (4 x NT independent compares per load).
+// Only two counting warps share a scheduler, so latencies are not hidden by other warps: the instruction ORDER is pinned
+// (volatile asm keeps program order) -- the next 16-byte load first, then all compares of the current one, then the packed
+// adds, each of which then finds its compare results (~20 cycles of latency on FSET.BF) long finished.
+__device__ __forceinline__ float gt_one_v(const float a, const float p)
+{
+    float r;
+    asm volatile("set.gt.f32.f32 %0, %1, %2;" : "=f"(r) : "f"(a), "f"(p));
+    return r;
+}
+__device__ __forceinline__ u64 add2_v(const u64 a, const float lo, const float hi)
+{
+    u64 r;
+    asm volatile("{\n\t.reg .b64 t;\n\tmov.b64 t, {%2, %3};\n\tadd.rn.f32x2 %0, %1, t;\n\t}" : "=l"(r) : "l"(a), "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float4 lds128_v(const float* p)
+{
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_u32(p)));
+    return v;
+}
 template <int NT>
 __device__ __forceinline__ void count_above(const float* __restrict__ src, const float (&thr)[NT], unsigned (&cnt)[NT])
 {
@@ -564,14 +581,20 @@ __device__ __forceinline__ void count_above(const float* __restrict__ src, const
     u64 acc[NT][2];
 #pragma unroll
     for (int t = 0; t < NT; t++) { acc[t][0] = 0ull; acc[t][1] = 0ull; }
-    float4 v = *reinterpret_cast<const float4*>(src);
-#pragma unroll 4
+    float4 v = lds128_v(src);
+#pragma unroll 2
     for (int x = 0; x < BN; x += 4) {
-        const float4 nv = *reinterpret_cast<const float4*>(src + ((x + 4) & (BN - 1)));      // next load in flight (wraps on the last one)
+        const float4 nv = lds128_v(src + ((x + 4) & (BN - 1)));      // next load in flight (wraps on the last one)
+        float m[NT][4];
 #pragma unroll
         for (int t = 0; t < NT; t++) {
-            acc[t][0] = add2(acc[t][0], pack2(gt_one(v.x, thr[t]), gt_one(v.y, thr[t])));
-            acc[t][1] = add2(acc[t][1], pack2(gt_one(v.z, thr[t]), gt_one(v.w, thr[t])));
+            m[t][0] = gt_one_v(v.x, thr[t]); m[t][1] = gt_one_v(v.y, thr[t]);
+            m[t][2] = gt_one_v(v.z, thr[t]); m[t][3] = gt_one_v(v.w, thr[t]);
+        }
+#pragma unroll
+        for (int t = 0; t < NT; t++) {
+            acc[t][0] = add2_v(acc[t][0], m[t][0], m[t][1]);
+            acc[t][1] = add2_v(acc[t][1], m[t][2], m[t][3]);
         }
         v = nv;
     }
@@ -582,34 +605,6 @@ __device__ __forceinline__ void count_above(const float* __restrict__ src, const
         cnt[t] = (unsigned)(lo + hi);
     }
 }
-__device__ __forceinline__ unsigned gt_mask(const float a, const float p)
-{
-    unsigned r;
-    asm("set.gt.u32.f32 %0, %1, %2;" : "=r"(r) : "f"(a), "f"(p));
-    return r;
-}
-// (developer variant: masks subtracted on the ALU pipe instead of packed adds on the FMA pipe)
-template <int NT>
-__device__ __forceinline__ void count_above_alu(const float* __restrict__ src, const float (&thr)[NT], unsigned (&cnt)[NT])
-{
-    constexpr int BN = NumTraits<float>::BN;
-    unsigned c0[NT], c1[NT];
-#pragma unroll
-    for (int t = 0; t < NT; t++) { c0[t] = 0; c1[t] = 0; }
-#pragma unroll 2
-    for (int x = 0; x < BN; x += 4) {
-        const float4 v = *reinterpret_cast<const float4*>(src + x);
-#pragma unroll
-        for (int t = 0; t < NT; t++) {
-            c0[t] -= gt_mask(v.x, thr[t]) + gt_mask(v.y, thr[t]);
-            c1[t] -= gt_mask(v.z, thr[t]) + gt_mask(v.w, thr[t]);
-        }
-    }
-#pragma unroll
-    for (int t = 0; t < NT; t++) cnt[t] = c0[t] + c1[t];
-}
-template <int NT>
-__device__ __forceinline__ void count_above_alu(const double* __restrict__ src, const double (&thr)[NT], unsigned (&cnt)[NT]);
 __device__ __forceinline__ unsigned gt_mask(const double a, const double p)
 {
     unsigned r;
@@ -632,8 +627,6 @@ __device__ __forceinline__ void count_above(const double* __restrict__ src, cons
 #pragma unroll
     for (int t = 0; t < NT; t++) cnt[t] = c0[t] + c1[t];
 }
-template <int NT>
-__device__ __forceinline__ void count_above_alu(const double* __restrict__ src, const double (&thr)[NT], unsigned (&cnt)[NT]) { count_above<NT>(src, thr, cnt); }
 // How far apart two scores must be for the reference's tie-breaking noise (uniform in [-1e-12, 1e-12) added to each,
 // hpp:531-534) to be unable to swap them, as seen from a held-out score p: 0 where adding the noise gives the score back
 // (float: |p| >= 2^-13, double: |p| >= 2^16), else twice the noise plus the rounding of the two sums.
@@ -688,77 +681,71 @@ __device__ __noinline__ void auc_count_banded(const ScoreSelectParams<T>& P, con
     P.auc_near[e] = near0 + (c3[1] - c3[2]);
 }
 
-// Counting warp cw of the rank-counting kernel: for every item tile, the score block FMA warp cw staged for its 16 rows.
-//   * what is not a candidate is masked with NaN (never above a threshold, ignored by fmin): the train items of rows whose
-//     train row intersects the tile (own cursors, lane r <-> row r) and the padding columns of the last tile;
-//   * the smallest candidate score of every row (the full-order validity rule, hpp:555-562) is tracked;
-//   * for every held-out entry of the rows: the candidates of the tile that rank before it -- scoring above it, or equal
-//     with a smaller item id (the tie order of the top-K selection).  Tiles wholly before the entry's own item count
-//     "s >= score" (as "s > next_below(score)"), tiles after it "s > score"; the item's own tile "s > score" plus the
-//     equal scores in the columns before the item.  The held-out entries of the 16 rows form ONE list (pref[r] = entries
-//     before row r), cut into work units of up to four consecutive entries of one row; unit u belongs to lane u % 32 for
-//     the whole kernel (it alone updates the entries' counters in global memory: plain read-modify-write).  A unit is one
-//     pass over its row's BN scores, every 16-byte load compared with the unit's (up to) four thresholds: the work of a
-//     warp is the sum of its rows' held-out counts, spread evenly over the lanes.
+// The eight counting warps of the rank-counting kernel.  For every item tile:
+//   * counting warp cw waits for the score block FMA warp cw staged for its 16 rows and masks (NaN: never above a threshold,
+//     ignored by fmin) what is not a candidate -- the train items of rows whose train row intersects the tile (own cursors,
+//     lane r <-> row r) and the padding columns of the last tile -- and tracks the smallest candidate score of its rows
+//     (the full-order validity rule, hpp:555-562);
+//   * the counting warps meet (named barrier): all 128 rows of the tile are staged and masked;
+//   * counting: for every held-out entry of the CTA's rows, the candidates of the tile that rank before it -- scoring above
+//     it, or equal with a smaller item id (the tie order of the top-K selection).  Tiles wholly before the entry's own item
+//     count "s >= score" (as "s > next_below(score)"), tiles after it "s > score"; the item's own tile "s > score" plus the
+//     equal scores in the columns before the item.  The held-out entries of the 128 rows form ONE list (pref[r] = entries
+//     before row r), cut into work units of up to UN consecutive entries of one row; unit u belongs to counting thread
+//     u % 256 for the whole kernel (it alone updates the entries' counters in global memory: plain read-modify-write).
+//     A unit is one pass over its row's BN scores, every 16-byte load compared with the unit's thresholds.  The work of the
+//     CTA -- the sum of its rows' held-out counts, heavy-tailed per row -- is spread evenly over all 256 counting lanes:
+//     with per-warp lists the CTA ran at the pace of its heaviest warp;
+//   * every counting warp releases all eight blocks (blk_empty[w] counts eight arrivals).
 template <typename T>
-__device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowState<T>* rs, T* blk_all, int* pref_all, T* pthr_all, int* pitem_all,
+__device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowState<T>* rs, T* blk_all, int* pref, T* pthr, int* pitem,
                                             const unsigned bar_blkf, const unsigned bar_blke, const int cw, const int lane,
                                             const int tile_u0, const int NT)
 {
     constexpr int BN = NumTraits<T>::BN;
     constexpr int BNP = SmemLayout<T, true>::BNP;
+    constexpr int UN = sizeof(T) == 4 ? 4 : 2;                   // entries per work unit
+    constexpr int NCT = NCWARPS * 32;                            // counting threads
+    constexpr int PCAP = NCWARPS * AUC_PCAP;                     // entries staged in shared memory
     const int wrow0 = cw * 16;
+    const int tc = cw * 32 + lane;
     T* blk = blk_all + (size_t)cw * 16 * BNP;
-    int* pref = pref_all + cw * 20;
-    T* pthr = pthr_all + cw * AUC_PCAP;
-    int* pitem = pitem_all + cw * AUC_PCAP;
+    int* upref = pref + BM + 4;                                  // [BM + 1] units before row r (pref: [BM + 1] entries before row r)
+    auto count_sync = []() { asm volatile("bar.sync 1, %0;" ::"n"(NCWARPS * 32) : "memory"); };
 
-    // the list of held-out entries, the first AUC_PCAP of them staged in shared memory
-    {
-        int v = lane < 16 ? rs->npos[wrow0 + lane] : 0;
+    if (cw == 0) {                                               // prefix sums over the CTA's 128 rows (4 rows per lane)
+        int np[4], nu[4], sp = 0, su = 0;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const int w = __shfl_up_sync(FULL, v, o);
-            if (lane >= o) v += w;
-        }
-        if (lane < 16) pref[lane + 1] = v;
-        if (lane == 0) pref[0] = 0;
-        __syncwarp();
-        const int staged = pref[16] < AUC_PCAP ? pref[16] : AUC_PCAP;
-        int row_l = 0;
-        for (int q = lane; q < staged; q += 32) {
-            while (q >= pref[row_l + 1]) row_l++;
-            const size_t e = (size_t)rs->tp0[wrow0 + row_l] + (size_t)(q - pref[row_l]);
-            pthr[q] = P.pos_sorted[e];
-            pitem[q] = P.pos_item[e];
-        }
-        __syncwarp();
-    }
-    // Work units: up to UN (four; double: two) consecutive entries of ONE row (a row with npos entries makes ceil(npos / UN)
-    // units); unit u belongs to lane u % 32 for the whole kernel.  upref[r] = units before row r.
-    constexpr int UN = sizeof(T) == 4 ? 4 : 2;
-    int* upref = pref + 20 * NCWARPS;                            // (second half of the prefix area)
-    {
-        int v = lane < 16 ? (rs->npos[wrow0 + lane] + UN - 1) / UN : 0;
+        for (int i = 0; i < 4; i++) { np[i] = rs->npos[4 * lane + i]; nu[i] = (np[i] + UN - 1) / UN; sp += np[i]; su += nu[i]; }
+        int ip = sp, iu = su;
 #pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-            const int w = __shfl_up_sync(FULL, v, o);
-            if (lane >= o) v += w;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(FULL, ip, o), b = __shfl_up_sync(FULL, iu, o);
+            if (lane >= o) { ip += a; iu += b; }
         }
-        if (lane < 16) upref[lane + 1] = v;
-        if (lane == 0) upref[0] = 0;
-        __syncwarp();
+        int bp = ip - sp, bu = iu - su;                          // exclusive
+#pragma unroll
+        for (int i = 0; i < 4; i++) { pref[4 * lane + i] = bp; upref[4 * lane + i] = bu; bp += np[i]; bu += nu[i]; }
+        if (lane == 31) { pref[BM] = bp; upref[BM] = bu; }
     }
-    const int n_units = upref[16];
-    int unit_row[4];                                             // rows of the lane's first four units (further ones are looked up)
+    count_sync();
+    const int total_pos = pref[BM], n_units = upref[BM];
+    for (int q = tc; q < (total_pos < PCAP ? total_pos : PCAP); q += NCT) {      // the first PCAP entries: score and item id staged
+        int lo = 0, hi = BM - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pref[mid] <= q) lo = mid; else hi = mid - 1; }
+        const size_t e = (size_t)rs->tp0[lo] + (size_t)(q - pref[lo]);
+        pthr[q] = P.pos_sorted[e];
+        pitem[q] = P.pos_item[e];
+    }
+    int unit_row[4];                                             // rows of the thread's first four units (further ones are looked up)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int u = lane + 32 * j;
-        int r = 0;
-        while (r < 15 && u >= upref[r + 1]) r++;
-        unit_row[j] = r;
+        const int u = tc + NCT * j;
+        int lo = 0, hi = BM - 1;
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (upref[mid] <= u) lo = mid; else hi = mid - 1; }
+        unit_row[j] = lo;
     }
-    // own train cursor of row `lane` (lanes 0..15), minimum of half a row (row lane >> 1, columns (lane & 1) * BN / 2 ...)
+    // own train cursor of row `lane` of the warp's block (lanes 0..15), minimum of half a row (row lane >> 1, columns (lane & 1) * BN / 2 ...)
     int t_cur = 0, t_end = 0, t_nxt = INT_MAX;
     if (lane < 16 && tile_u0 + wrow0 + lane < P.mb && rs->npos[wrow0 + lane] > 0) {      // (ranked rows have held-out items)
         const int u = P.user0 + rs->urow[wrow0 + lane];
@@ -766,34 +753,29 @@ __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowSt
         if (t_cur < t_end) t_nxt = P.tri[t_cur];
     }
     T rmin = NumTraits<T>::inf();
+    // (pointers of the parameter block in registers: through the reference every use is a load from the parameter space)
+    unsigned int* const cnt_g = P.auc_cnt;
+    const unsigned int* const near_g = P.auc_near;
+    const T* const sorted_g = P.pos_sorted;
+    const int* const item_g = P.pos_item;
+    count_sync();                                                // (the staged entries are visible)
 
     if (P.dbg & 4) return;
-#if RMB_AUC_CLK      // developer build: cycles per phase of one counting warp (RMB200_AUC_DBG & 64)
-    long long ck[6] = {0, 0, 0, 0, 0, 0};
-    const bool clk_on = P.dbg_clk != nullptr;
-#define AUC_CLK(i) if (clk_on) { const long long t_ = clock64(); ck[i] += t_ - t_prev; t_prev = t_; }
-    long long t_prev = clk_on ? clock64() : 0;
-#else
-#define AUC_CLK(i)
-#endif
     for (int tile = 0; tile < NT; tile++) {
         const int item0 = tile * BN;
         mbar_wait(bar_blkf + 8 * cw, (unsigned)tile & 1u);
-        AUC_CLK(0)
-        if (P.dbg & 2) { __syncwarp(); if (lane == 0) mbar_arrive(bar_blke + 8 * cw); continue; }
-        if (lane < 16) {
-            T* dst = blk + (size_t)lane * BNP;
-            while (t_nxt < item0 + BN) {
-                dst[t_nxt - item0] = NumTraits<T>::nan();
-                t_cur++;
-                t_nxt = t_cur < t_end ? P.tri[t_cur] : INT_MAX;
+        if (!(P.dbg & 2)) {
+            if (lane < 16) {
+                T* dst = blk + (size_t)lane * BNP;
+                while (t_nxt < item0 + BN) {
+                    dst[t_nxt - item0] = NumTraits<T>::nan();
+                    t_cur++;
+                    t_nxt = t_cur < t_end ? P.tri[t_cur] : INT_MAX;
+                }
+                if (item0 + BN > P.n)
+                    for (int x = (P.n > item0 ? P.n - item0 : 0); x < BN; x++) dst[x] = NumTraits<T>::nan();
             }
-            if (item0 + BN > P.n)
-                for (int x = (P.n > item0 ? P.n - item0 : 0); x < BN; x++) dst[x] = NumTraits<T>::nan();
-        }
-        __syncwarp();
-        AUC_CLK(1)
-        {
+            __syncwarp();
             const T* src = blk + (size_t)(lane >> 1) * BNP + (lane & 1) * (BN / 2);
             constexpr int VEC = 16 / (int)sizeof(T);
             T m0 = NumTraits<T>::inf(), m1 = NumTraits<T>::inf();
@@ -807,60 +789,64 @@ __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowSt
             }
             rmin = fmin(rmin, fmin(m0, m1));
         }
-        AUC_CLK(2)
-        if (!(P.dbg & 1)) {
-            for (int j = 0, u = lane; u < n_units; j++, u += 32) {
-                int row_l;
-                if (j < 4) row_l = j == 0 ? unit_row[0] : (j == 1 ? unit_row[1] : (j == 2 ? unit_row[2] : unit_row[3]));
-                else { row_l = 0; while (row_l < 15 && u >= upref[row_l + 1]) row_l++; }
-                const int q = pref[row_l] + UN * (u - upref[row_l]);               // first entry of the unit
-                const int run = min(pref[row_l + 1] - q, UN);
-                const size_t e0 = (size_t)rs->tp0[wrow0 + row_l] + (size_t)(q - pref[row_l]);
-                const T* src = blk + (size_t)row_l * BNP;
+        count_sync();                                            // all 128 rows of the tile are staged and masked
+        if (!(P.dbg & 3)) {
+            for (int j = 0, u = tc; u < n_units; j++, u += NCT) {
+                int row;
+                if (j < 4) row = j == 0 ? unit_row[0] : (j == 1 ? unit_row[1] : (j == 2 ? unit_row[2] : unit_row[3]));
+                else {
+                    int lo = 0, hi = BM - 1;
+                    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (upref[mid] <= u) lo = mid; else hi = mid - 1; }
+                    row = lo;
+                }
+                const int q = pref[row] + UN * (u - upref[row]);                   // first entry of the unit
+                const int run = min(pref[row + 1] - q, UN);
+                const size_t e0 = (size_t)rs->tp0[row] + (size_t)(q - pref[row]);
+                const T* src = blk_all + (size_t)row * BNP;
+                // the unit's counters, scores and item ids: unconditional loads (entries past the unit's end re-read its first
+                // one), all in flight together -- the counters come from L2, a dependent load per entry cost more than the counting
+                unsigned before[UN];
                 T thr[UN], eff[UN];
                 int col[UN];
-                unsigned before[UN], c[UN];
+#pragma unroll
+                for (int t = 0; t < UN; t++) before[t] = cnt_g[e0 + (t < run ? t : 0)];
+                if (q + UN <= PCAP) {
+#pragma unroll
+                    for (int t = 0; t < UN; t++) { thr[t] = pthr[q + t]; col[t] = pitem[q + t] - item0; }
+                } else {
+#pragma unroll
+                    for (int t = 0; t < UN; t++) { thr[t] = sorted_g[e0 + (t < run ? t : 0)]; col[t] = item_g[e0 + (t < run ? t : 0)] - item0; }
+                }
                 unsigned banded = 0;                                          // entries within the noise's reach of other candidates: below
 #pragma unroll
                 for (int t = 0; t < UN; t++) {
                     bool on = t < run;
-                    thr[t] = !on ? NumTraits<T>::inf() : (q + t < AUC_PCAP ? pthr[q + t] : P.pos_sorted[e0 + t]);
-                    if (on && P.auc_near != nullptr && noise_reach(thr[t]) > (T)0) { banded |= 1u << t; on = false; }
-                    before[t] = on ? P.auc_cnt[e0 + t] : 0u;
-                    col[t] = !on ? 0 : (q + t < AUC_PCAP ? pitem[q + t] : P.pos_item[e0 + t]) - item0;
+                    if (on && near_g != nullptr && noise_reach(thr[t]) > (T)0) { banded |= 1u << t; on = false; }
+                    if (!on) col[t] = 0;
                     eff[t] = !on ? NumTraits<T>::inf() : (col[t] >= BN ? next_below<T>(thr[t]) : thr[t]);
                 }
-                if (sizeof(T) == 4 && (P.dbg & 16)) count_above_alu<UN>(src, eff, c);
-                else count_above<UN>(src, eff, c);
+                unsigned c[UN];
+                count_above<UN>(src, eff, c);
 #pragma unroll
                 for (int t = 0; t < UN; t++) {
                     if (t < run && !((banded >> t) & 1u)) {
                         unsigned ct = c[t];
                         if (col[t] > 0 && col[t] < BN)
                             for (int x = 0; x < col[t]; x++) ct += (src[x] == thr[t]);
-                        P.auc_cnt[e0 + t] = before[t] + ct;
+                        cnt_g[e0 + t] = before[t] + ct;
                     }
                 }
                 while (banded) {
                     const int t = __ffs(banded) - 1;
                     banded &= banded - 1;
                     auc_count_banded<T>(P, src, e0 + t, t == 0 ? thr[0] : (t == 1 ? thr[1] : (UN > 2 && t == 2 ? thr[UN > 2 ? 2 : 0] : thr[UN - 1])),
-                                        (q + t < AUC_PCAP ? pitem[q + t] : P.pos_item[e0 + t]) - item0);
+                                        (q + t < PCAP ? pitem[q + t] : item_g[e0 + t]) - item0);
                 }
             }
         }
         __syncwarp();
-        AUC_CLK(3)
-        if (lane == 0) mbar_arrive(bar_blke + 8 * cw);           // the FMA warp may stage its next block
+        if (lane < NCWARPS) mbar_arrive(bar_blke + 8 * lane);    // this warp is done with all eight blocks of the tile
     }
-#if RMB_AUC_CLK
-    if (clk_on && lane == 0 && cw == (P.dbg >> 8 & 7)) {
-        for (int i = 0; i < 4; i++) atomicAdd(P.dbg_clk + i, (unsigned long long)ck[i]);
-        atomicAdd(P.dbg_clk + 4, (unsigned long long)pref[16]);
-        atomicAdd(P.dbg_clk + 5, 1ull);
-    }
-#endif
-#undef AUC_CLK
     // smallest candidate score of every ranked row
     rmin = fmin(rmin, __shfl_xor_sync(FULL, rmin, 1));
     if ((lane & 1) == 0) {
@@ -921,7 +907,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
     if (tid == 0) {
         for (int s = 0; s < S; s++) { mbar_init(bar_full + 8 * s, 1); mbar_init(bar_empty + 8 * s, NW); }
         if (AUC)
-            for (int w = 0; w < NCWARPS; w++) { mbar_init(bar_blkf + 8 * w, 1); mbar_init(bar_blke + 8 * w, 1); }
+            for (int w = 0; w < NCWARPS; w++) { mbar_init(bar_blkf + 8 * w, 1); mbar_init(bar_blke + 8 * w, NCWARPS); }
         mbar_fence_init();
     }
     __syncthreads();   // the only CTA-wide barrier
@@ -981,7 +967,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
                 }
             }
 #else
-            for (int kk0 = 0; kk0 < kcount; kk0 += RMB_UNROLL) {
+            for (int kk0 = 0; kk0 < ((AUC && (P.dbg & 8) && kc > 0) ? 0 : kcount); kk0 += RMB_UNROLL) {     // (developer, dbg & 8: a quarter of the FMAs -- the counting warps set the pace)
                 if (RMB_EARLYTRY && kk0 + RMB_UNROLL >= kcount) {   // last block of the stage: probe the next stage now
                     const int nit = it + 1;
                     ready = (nit < total) ? mbar_try(bar_full + 8 * (nit % S), (nit / S) & 1) : 1u;
@@ -989,7 +975,6 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
 #pragma unroll
                 for (int kk = 0; kk < RMB_UNROLL; kk++) {
                     if (RMB_UNROLL > KPAD && kk0 + kk >= kcount) break;     // only the tail chunk of a k that is not a multiple of the unroll
-                    if (AUC && (P.dbg & 8) && kk > 0) continue;             // (developer: one k step per block -- the counting warps set the pace)
                     MicroTile<T>::load(frag[0], sA + (kk0 + kk) * UM, sB + (kk0 + kk) * BN, ly, lx);
                     mt.compute(frag[0]);
                 }
