@@ -68,6 +68,7 @@ def cpu_arm_callable():
     import oracle
     oracle.build()
     if oracle.have_ref():
+        oracle.use_best_ref_build_for_timing()      # the build closest to -march=native on this host
         return "reference", oracle
     return "port", oracle
 
@@ -96,13 +97,13 @@ def cpu_model():
     return "unknown"
 
 
-def sources_hash():
-    """Identifies the build the committed ncu traffic figure belongs to (profiles/roofline_traffic.json)."""
+def sources_hash(name=None):
+    """Identifies the kernel source the committed ncu traffic figure was captured on (profiles/roofline_traffic.json)."""
     h = hashlib.sha1()
     src = os.path.join(ROOT, "recometrics_b200", "csrc")
-    for name in sorted(os.listdir(src)):
-        if name.endswith((".cu", ".cuh")):
-            h.update(open(os.path.join(src, name), "rb").read())
+    for fn in sorted(os.listdir(src)):
+        if (name is None and fn.endswith((".cu", ".cuh"))) or fn == name:
+            h.update(open(os.path.join(src, fn), "rb").read())
     return h.hexdigest()[:12]
 
 
@@ -341,8 +342,10 @@ def product_arm(args, cfg, rank, world, local_rank):
             traffic = json.load(open(tpath)).get(str(cfg.cfg_id))
             if isinstance(traffic, dict):      # DRAM bytes of one launch of the dominant kernel, from the committed ncu capture
                 traffic_note = "%s; %s" % (traffic.get("per"), traffic.get("source"))
-                if traffic.get("sources_hash") not in (None, sources_hash()):
-                    traffic_note += "; NOTE: captured on build %s, this build is %s (kernel sources changed since the capture)" % (traffic.get("sources_hash"), sources_hash())
+                now = sources_hash(traffic.get("kernel_source"))
+                if traffic.get("sources_hash") not in (None, now):
+                    traffic_note += "; NOTE: captured on %s %s, this build has %s (the kernel source changed since the capture)" % (
+                        traffic.get("kernel_source", "sources"), traffic.get("sources_hash"), now)
                 traffic = int(traffic["dram_bytes_read"]) + int(traffic["dram_bytes_write"])
         except Exception:
             traffic = None
@@ -406,7 +409,34 @@ def product_arm(args, cfg, rank, world, local_rank):
             bad_users |= (diff > 1e-6).any(axis=1)
             worst = max(worst, float(diff.max()) if diff.size else 0.0)
             rows_cmp += cu
+        # the north-star's exception: two scores within a 1e-6 relative gap where their order matters (float64 re-scoring decides;
+        # "relative" to the user's score scale, tests/parity_utils.py).  Every mismatching user must be such a user.
+        unexplained, checked = 0, 0
+        bad_idx = np.nonzero(bad_users)[0][:400]
+        if bad_idx.size:
+            B64 = dd["B"].astype(np.float64)
+            b64 = None if dd["item_biases"] is None else dd["item_biases"].astype(np.float64)
+            for u in bad_idx:
+                sc = dd["A"][u].astype(np.float64) @ B64.T
+                if b64 is not None:
+                    sc = sc + b64
+                tr = dd["X_train"].indices[dd["X_train"].indptr[u]:dd["X_train"].indptr[u + 1]]
+                te = dd["X_test"].indices[dd["X_test"].indptr[u]:dd["X_test"].indptr[u + 1]]
+                sc[tr] = -np.inf
+                order = np.sort(sc[np.isfinite(sc)])[::-1]
+                tol = 1e-6 * max(abs(order[0]), abs(order[-1]))
+                near = bool(np.any(np.abs(np.diff(order[: K + 1])) <= tol))
+                if not near and ("roc" in cfg.metrics or "pr" in cfg.metrics):
+                    asc = order[::-1]
+                    for it in te:
+                        lo, hi = np.searchsorted(asc, sc[it] - tol, "left"), np.searchsorted(asc, sc[it] + tol, "right")
+                        if hi - lo > 1:
+                            near = True
+                            break
+                checked += 1
+                unexplained += 0 if near else 1
         parity = {"users": int(cu), "metric_rows": int(rows_cmp), "mismatched_users": int(bad_users.sum()), "tolerance": 1e-6,
+                  "mismatched_users_checked_in_float64": int(checked), "mismatched_users_without_a_1e-6_near_tie": int(unexplained),
                   "max_abs_diff": worst, "nan_rows_cpu": int(np.isnan(np.asarray(cpu_rows[cfg.metrics[0]]).reshape(cu, -1)[:, 0]).sum()),
                   "against": "cpu_baseline rows (%s) vs the rows of the timed e2e call, same users" % kind}
 

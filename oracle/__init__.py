@@ -38,6 +38,35 @@ def have_ref():
     return os.path.exists(REF_SO)
 
 
+REF_V4_SO = os.path.join(_HERE, "_ref", "librecometrics_ref_v4.so")
+_timing_so = None
+
+
+def _cpu_has_avx512():
+    try:
+        for ln in open("/proc/cpuinfo"):
+            if ln.startswith("flags"):
+                f = set(ln.split(":", 1)[1].split())
+                return {"avx512f", "avx512bw", "avx512vl", "avx512dq"} <= f
+    except OSError:
+        pass
+    return False
+
+
+def use_best_ref_build_for_timing():
+    """bench.py only: time the reference build closest to `-march=native` on THIS host (the x86-64-v4 build when the CPU has
+    AVX-512, else the portable x86-64-v3 one).  Parity tests never call this: they stay on the v3 build the goldens came from."""
+    global _timing_so
+    _timing_so = REF_V4_SO if (os.path.exists(REF_V4_SO) and _cpu_has_avx512()) else REF_SO
+    return ref_build_note()
+
+
+def ref_build_note():
+    so = _timing_so or REF_SO
+    return "oracle/_ref/%s (g++ -O3 -fopenmp %s; the reference's setup.py flags with a portable -march)" % (
+        os.path.basename(so), "-march=x86-64-v4 -mprefer-vector-width=256" if so == REF_V4_SO else "-march=x86-64-v3")
+
+
 _libs = {}
 
 
@@ -87,7 +116,7 @@ def ref_calc(A, B, Xtr, Xte, k, metrics=("p", "ap", "ndcg"), cumulative=False,
              consider_cold_start=True, min_items_pool=2, min_pos_test=1, nthreads=1,
              break_ties_with_noise=False, seed=1, dtype=np.float32):
     """Run the UNMODIFIED reference (calc_metrics_float/_double, recometrics_signatures.hpp:46-98)."""
-    lib = _lib(REF_SO)
+    lib = _lib(_timing_so or REF_SO)
     A, B, trp, tri, tep, tei, tev = _prep(A, B, Xtr, Xte, dtype)
     m, n, p = A.shape[0], B.shape[0], A.shape[1]
     outs = _alloc_outs(metrics, m, k, cumulative, dtype)
