@@ -156,6 +156,8 @@ class ClockSampler:
         self.path = None
 
     def start(self):
+        if os.environ.get("RMB200_BENCH_NO_SAMPLER") == "1":       # developer: is the sampler itself visible in the timing?
+            return
         try:
             fd, self.path = tempfile.mkstemp(prefix="rmb200_clocks_", suffix=".csv")
             os.close(fd)
@@ -275,9 +277,12 @@ def product_arm(args, cfg, rank, world, local_rank):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     kernel_ms, launches, path, fallbacks, retry_rows = 0.0, 0, 0, 0, 0
     phases = {}
+    wall_calls_ms = 0.0
     e0.record()
     for _ in range(args.steps):
+        t_w = time.perf_counter()
         call(True, tm)
+        wall_calls_ms += (time.perf_counter() - t_w) * 1e3
         kernel_ms += tm.dominant_kernel_ms
         launches += tm.kernel_launches
         for f in ("total_ms", "prep_ms", "score_select_ms", "metrics_ms"):
@@ -288,7 +293,13 @@ def product_arm(args, cfg, rank, world, local_rank):
     barrier()
     clocks = sampler.stop()
     dev_ms = e0.elapsed_time(e1)
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([dev_ms, phases.get("total_ms", 0.0), kernel_ms / args.steps, wall_calls_ms / args.steps], dtype=torch.float64, device=dev)
+        allr = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = {"ms_per_step": [round(float(x[0]) / args.steps, 2) for x in allr], "call_total_ms": [round(float(x[1]), 2) for x in allr],
+                    "kernel_ms": [round(float(x[2]), 2) for x in allr], "host_wall_ms_per_call": [round(float(x[3]), 2) for x in allr]}
         t = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms = float(t.item())
@@ -456,7 +467,7 @@ def product_arm(args, cfg, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
                     "ms_per_step": e2e_s * 1e3 / args.steps, "host_buffers": "pinned"},
             "e2e_pageable": e2e_pageable,
-            "gpu_launches": int(launches), "clocks": clocks,
+            "gpu_launches": int(launches) * world, "clocks": clocks, "per_rank": per_rank,
             "phases_ms_per_step": {k: round(v, 3) for k, v in phases.items()},
         }
         print(json.dumps(line), flush=True)

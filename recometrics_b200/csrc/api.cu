@@ -1069,8 +1069,31 @@ int run_call(const CallArgs<T>& a)
                 CK(cudaGetLastError());
                 tm.kernel_launches += 2;
                 { int rc2 = staged_rows_consumed(); if (rc2) return rc2; }      // (the gather read the staged rows once more)
-                rc = run_fma(d_At_fb.as<T>(), n_over, d_fb_list.as<int>(), false, false);
-                if (rc) return rc;
+                if (n_over <= 2048 && a.n >= 32768) {
+                    // a few users of a large catalogue: the full-order path (every candidate scored by item-parallel blocks, one
+                    // segmented sort) -- on the FMA tiles ONE CTA walked the whole catalogue for them (78 ms at 1M items for a
+                    // single user, profiles/r02v: two of four ranks of a strong-scaling run ran at half speed for it)
+                    int chunk = 0; size_t bytes = 0;
+                    full_order_plan(a.n, (int)sizeof(T), n_over, &chunk, &bytes);
+                    CK(d_fo.alloc(bytes));
+                    FullOrderArgs<T> fo;
+                    fo.At = d_At_fb.as<T>(); fo.Bt = d_Bt.as<T>(); fo.bias = bias_d; fo.p_pad = p_pad; fo.n = a.n; fo.K = K; fo.C = C;
+                    fo.user0 = b0; fo.nb = n_over; fo.umap = d_fb_list.as<int>();
+                    fo.trp = trp_d; fo.tri = tri_d; fo.tep = tep_d; fo.tei = tei_d; fo.ustatus = d_status.as<int>(); fo.uflags = d_flags.as<int>();
+                    fo.cand_score = d_cs.as<T>(); fo.cand_item = d_ci.as<int>(); fo.cand_count = d_cc.as<int>();
+                    fo.umin = count_ranks ? d_umin.as<unsigned long long>() : nullptr;
+                    fo.auc_cnt = count_ranks ? d_auc.as<unsigned int>() : nullptr;
+                    fo.pos_perm = count_ranks ? d_pos_perm.as<int>() : nullptr;
+                    fo.noise = a.noise; fo.seed_user0 = (unsigned long long)a.seed + (unsigned long long)(ub + b0);
+                    fo.scratch = d_fo.p; fo.scratch_bytes = bytes; fo.chunk_users = chunk;
+                    if (pf.test_rows_pending && count_ranks) { CK(cudaStreamWaitEvent(st, pf.test_rows, 0)); pf.test_rows_pending = false; }
+                    long long nl = 0;
+                    CK(full_order_run<T>(fo, st, &nl));
+                    tm.kernel_launches += nl;
+                } else {
+                    rc = run_fma(d_At_fb.as<T>(), n_over, d_fb_list.as<int>(), false, false);
+                    if (rc) return rc;
+                }
             }
         } else if (use_full) {
             // every candidate scored, (noise,) sorted: ranked top-K, smallest candidate score and held-out ranks off the sorted lists

@@ -123,18 +123,21 @@ def test_cfg2_full_catalogue_65_factors(rb, oracle_mod):
             assert rep["topk_rows_differing"] <= rep["topk_ambiguous"]
 
 
+@pytest.mark.parametrize("n_items", [20000, 40000])
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-def test_unscalable_factors_are_handed_to_the_fma_path_per_user(rb, dtype):
+def test_unscalable_factors_are_handed_to_the_fma_path_per_user(rb, dtype, n_items):
     """User rows whose norm lies outside what a power-of-two scaling can bring into fp16 range (1e-36, 1e33) and users with
-    near-constant scores: only THOSE users run on the FMA tiles; results equal the all-FMA path."""
-    d = synth.make(4, m=5000, n=20000, p=32)
+    near-constant scores: only THOSE users leave the tensor path -- re-run on the FMA tiles (small catalogues) or, a few users
+    of a large catalogue, on the full-order path (item-parallel scoring + one segmented sort instead of one CTA walking the
+    whole catalogue); results equal the all-FMA path."""
+    d = synth.make(4, m=5000, n=n_items, p=32)
     A = d["A"].astype(dtype).copy()
     tiny, huge = np.arange(5, 5000, 211), np.arange(9, 5000, 307)
     A[tiny] *= dtype(1e-36)
     A[huge] *= dtype(1e33)
     B = d["B"].astype(dtype).copy()
     const = np.arange(13, 5000, 401)                     # these users' scores = a_0 * b_0, and b_0 takes 3 values only: massive ties
-    B[:, 0] = np.random.default_rng(2).integers(0, 3, 20000).astype(dtype)
+    B[:, 0] = np.random.default_rng(2).integers(0, 3, n_items).astype(dtype)
     A[const, 1:] = 0
     a, b = _both_paths(rb, d, 20, A=A, B=B)
     n_special = len(set(tiny) | set(huge) | set(const))
