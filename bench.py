@@ -222,6 +222,11 @@ def product_arm(args, cfg, rank, world, local_rank):
     d = synth.make(cfg.cfg_id, m=users, n=args.items, seed_shift=rank, shared_items=True)
     A, B, bias = d["A"], d["B"], d["item_biases"]
     Xtr, Xte = d["X_train"], d["X_test"]
+    if args.zero_users > 0:
+        # users unseen in training have all-zero factors (every score equal -> NaN row): the tensor-core filter settles them
+        # without scoring and nobody else's batch pays for them (one such row used to send its whole batch to the FMA tiles)
+        zr = np.random.default_rng(99 + rank).random(A.shape[0]) < args.zero_users
+        A[zr] = 0
     m, n, p = A.shape[0], B.shape[0], A.shape[1]
     K = cfg.k
     flops = synth.algorithmic_flops(cfg, Xtr, Xte, has_ndcg="ndcg" in cfg.metrics)
@@ -461,7 +466,8 @@ def product_arm(args, cfg, rank, world, local_rank):
                        "k_metrics": K, "metrics": list(cfg.metrics), "cumulative": bool(cfg.cumulative),
                        "l2": "inputs (A+B+CSR = %.0f MB) larger than the 126 MB L2; no flush" % (
                            (A.nbytes + B.nbytes + Xtr.indices.nbytes + Xte.indices.nbytes) / 1e6),
-                       "scoring_path": {1: "fma", 2: "tensor filter + exact re-score"}.get(path, "?"),
+                       "scoring_path": {1: "fma", 2: "tensor filter + exact re-score", 3: "full order"}.get(path, "?"),
+                       **({"zero_factor_users": args.zero_users} if args.zero_users > 0 else {}),
                        "parallelism": "users block-partitioned, B replicated, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": int(d2h) * world,
@@ -487,6 +493,7 @@ def main():
                     help="N > 1: split the configuration's users over the GPUs (strong, default) or give every GPU that many (weak)")
     ap.add_argument("--items", type=int, default=0, help="items (default: the configuration's n)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--zero-users", type=float, default=0.0, help="fraction of users whose factors are set to zero (robustness line)")
     args = ap.parse_args()
 
     cfg = synth.CONFIGS[args.config]
