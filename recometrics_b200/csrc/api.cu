@@ -214,25 +214,25 @@ struct CallArgs {
 };
 
 template <typename T, int C, bool AUC>
-cudaError_t launch_score_select_inst(const rmb::ScoreSelectParams<T>& P, int n_rows, cudaStream_t st)
+cudaError_t launch_score_select_inst(const rmb::ScoreSelectParams<T>& P, int n_rows, int slices, cudaStream_t st)
 {
     auto kern = rmb::score_select_kernel<T, C, AUC>;
     const size_t smem = rmb::score_select_smem_bytes<T, AUC>();
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    kern<<<(n_rows + rmb::BM - 1) / rmb::BM, AUC ? rmb::AUC_THREADS : rmb::NTHREADS, smem, st>>>(P);
+    kern<<<dim3((n_rows + rmb::BM - 1) / rmb::BM, slices), AUC ? rmb::AUC_THREADS : rmb::NTHREADS, smem, st>>>(P);
     return cudaGetLastError();
 }
 
 template <typename T>
-cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool auc, int n_user_tiles, cudaStream_t st)
+cudaError_t launch_score_select(const rmb::ScoreSelectParams<T>& P, int C, bool auc, int n_rows, int slices, cudaStream_t st)
 {
-    if (C == 256) return auc ? launch_score_select_inst<T, 256, true>(P, n_user_tiles, st)
-                             : launch_score_select_inst<T, 256, false>(P, n_user_tiles, st);
-    if (C == 512) return auc ? launch_score_select_inst<T, 512, true>(P, n_user_tiles, st)
-                             : launch_score_select_inst<T, 512, false>(P, n_user_tiles, st);
-    return auc ? launch_score_select_inst<T, 1024, true>(P, n_user_tiles, st)
-               : launch_score_select_inst<T, 1024, false>(P, n_user_tiles, st);
+    if (C == 256) return auc ? launch_score_select_inst<T, 256, true>(P, n_rows, slices, st)
+                             : launch_score_select_inst<T, 256, false>(P, n_rows, slices, st);
+    if (C == 512) return auc ? launch_score_select_inst<T, 512, true>(P, n_rows, slices, st)
+                             : launch_score_select_inst<T, 512, false>(P, n_rows, slices, st);
+    return auc ? launch_score_select_inst<T, 1024, true>(P, n_rows, slices, st)
+               : launch_score_select_inst<T, 1024, false>(P, n_rows, slices, st);
 }
 
 template <int C>
@@ -886,9 +886,21 @@ int run_call(const CallArgs<T>& a)
         int rc = upload_users(0, 0);
         if (rc) return rc;
     }
-    CK(d_cs.alloc((size_t)UB * C * sizeof(T)));
-    CK(d_ci.alloc((size_t)UB * C * sizeof(int)));
-    CK(d_cc.alloc((size_t)UB * sizeof(int)));
+    // A call with fewer user tiles than SMs (small m) cuts the catalogue into item ranges on the FMA tiles: one CTA per (user tile,
+    // range), every range keeping its own best K, joined afterwards (merge_slices_kernel); rank counts are added atomically.
+    int fma_slices = 1;
+    if (!use_full) {
+        const int tiles = UB / BM, NT_all = (a.n + BN - 1) / BN;
+        int sl = tiles > 0 ? nsm / tiles : 1;
+        if (sl > NT_all / 8) sl = NT_all / 8;                       // (at least eight item tiles per range)
+        if (sl > C / K) sl = C / K;                                 // the joined heads fit one row ...
+        if (sl > 512 / K) sl = 512 / K;                             // ... and the final sort
+        if (const char* env = std::getenv("RMB200_SLICES")) { const int v = std::atoi(env); if (v >= 1 && v < sl) sl = v; }      // developer
+        if (sl > 1) fma_slices = sl;
+    }
+    CK(d_cs.alloc((size_t)UB * fma_slices * C * sizeof(T)));
+    CK(d_ci.alloc((size_t)UB * fma_slices * C * sizeof(int)));
+    CK(d_cc.alloc((size_t)UB * fma_slices * sizeof(int)));
     if (!on_dev) {
         for (int q = 0; q < 10; q++)
             if (a.out[q]) CK(d_out[q].alloc((size_t)UB * (q < 8 ? rs : 1) * sizeof(T)));
@@ -972,11 +984,18 @@ int run_call(const CallArgs<T>& a)
             sp.auc_near = (with_counts && noise_handback) ? d_near.as<unsigned>() : nullptr;
             sp.umin = with_counts ? d_umin.as<unsigned long long>() : nullptr;
             sp.umap = umap;
+            const int slices = (umap == nullptr && !use_tensor) ? fma_slices : 1;
+            sp.slice_rows = slices > 1 ? UB : 0;
             if (const char* env = std::getenv("RMB200_AUC_DBG")) sp.dbg = std::atoi(env);      // developer: timing experiments (wrong results)
             if (timed) cudaEventRecord(pk.a, st);
-            CK(launch_score_select<T>(sp, C, with_counts, n_rows, st));
+            CK(launch_score_select<T>(sp, C, with_counts, n_rows, slices, st));
             if (timed) { cudaEventRecord(pk.b, st); pk_pending = true; }
             tm.kernel_launches++;
+            if (slices > 1) {
+                merge_slices_kernel<T><<<(n_rows + 7) / 8, 256, 0, st>>>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, n_rows, slices, UB);
+                CK(cudaGetLastError());
+                tm.kernel_launches++;
+            }
             return RMB200_OK;
         };
         auto run_fma_batch = [&]() -> int {
@@ -1122,7 +1141,7 @@ int run_call(const CallArgs<T>& a)
             if (rc) return rc;
         }
         if (!use_full) {
-            CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, K, st));
+            CK(launch_rank_topk<T>(d_cs.as<T>(), d_ci.as<int>(), d_cc.as<int>(), C, nb, use_tensor ? K : K * fma_slices, st));
             tm.kernel_launches++;
         }
         if (noise_handback) {

@@ -203,6 +203,9 @@ struct ScoreSelectParams {
                                         // whose score lies within the reach of the tie-breaking noise of the held-out item's
                                         // (>= 2: the noise decides a rank of this user, api.cu hands the user to the full-order path)
     u64* umin;                          // [m] orderable(min candidate score), init ~0
+    int slice_rows;                     // item slices (gridDim.y > 1: a call with fewer user tiles than SMs cuts the catalogue into ranges, one CTA per
+                                        // (user tile, range)): rows of cand_score / cand_item / cand_count per slice -- slice y keeps the best K of its
+                                        // range in rows [y * slice_rows, ...), merge_slices_kernel joins them; rank counts are then added atomically
     int dbg;                            // developer (RMB200_AUC_DBG, timing experiments only -- results are wrong): 1 counting warps skip the
                                         // counting, 2 they skip masking / minima as well, 4 no hand-over of score blocks at all, 8 the FMA warps do a quarter of their FMAs
     const int* __restrict__ umap;       // optional [mb]: row r of this launch is batch-local user umap[r] (CSR rows, status, flags and
@@ -644,11 +647,11 @@ __device__ __forceinline__ T next_below(const T x)
 // Producer: one thread runs the TMA ring over (item tile, k chunk).
 template <typename T, int S, int BK>
 __device__ __forceinline__ void tma_producer_role(const ScoreSelectParams<T>& P, T* As, T* Bs, const unsigned bar_full, const unsigned bar_empty,
-                                                  const int KC, const int total)
+                                                  const int KC, const int total, const int tile0)
 {
     constexpr int BN = NumTraits<T>::BN;
     const T* gA = P.At + (size_t)blockIdx.x * P.p_pad * BM;
-    int tile = 0, kc = 0;
+    int tile = tile0, kc = 0;
     for (int it = 0; it < total; it++) {
         const int s = it % S;
         if (it >= S) mbar_wait(bar_empty + 8 * s, ((it / S) - 1) & 1);
@@ -677,6 +680,7 @@ __device__ __noinline__ void auc_count_banded(const ScoreSelectParams<T>& P, con
     unsigned ct = c3[0];
     if (colp > 0 && colp < BN)
         for (int x = 0; x < colp; x++) ct += (src[x] == p);
+    if (gridDim.y > 1) { atomicAdd(&P.auc_cnt[e], ct); atomicAdd(&P.auc_near[e], c3[1] - c3[2]); return; }
     P.auc_cnt[e] = before1 + ct;
     P.auc_near[e] = near0 + (c3[1] - c3[2]);
 }
@@ -700,11 +704,12 @@ __device__ __noinline__ void auc_count_banded(const ScoreSelectParams<T>& P, con
 template <typename T>
 __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowState<T>* rs, T* blk_all, int* pref, T* pthr, int* pitem,
                                             const unsigned bar_blkf, const unsigned bar_blke, const int cw, const int lane,
-                                            const int tile_u0, const int NT)
+                                            const int tile_u0, const int NT, const int t_begin)
 {
     constexpr int BN = NumTraits<T>::BN;
     constexpr int BNP = SmemLayout<T, true>::BNP;
     constexpr int UN = sizeof(T) == 4 ? 4 : 2;                   // entries per work unit
+    const bool sliced = gridDim.y > 1;                           // other CTAs count the same entries over other item ranges: atomic adds
     constexpr int NCT = NCWARPS * 32;                            // counting threads
     constexpr int PCAP = NCWARPS * AUC_PCAP;                     // entries staged in shared memory
     const int wrow0 = cw * 16;
@@ -750,6 +755,11 @@ __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowSt
     if (lane < 16 && tile_u0 + wrow0 + lane < P.mb && rs->npos[wrow0 + lane] > 0) {      // (ranked rows have held-out items)
         const int u = P.user0 + rs->urow[wrow0 + lane];
         t_cur = P.trp[u]; t_end = P.trp[u + 1];
+        if (t_begin > 0) {
+            int lo = t_cur, hi = t_end;
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tri[mid] < t_begin * BN) lo = mid + 1; else hi = mid; }
+            t_cur = lo;
+        }
         if (t_cur < t_end) t_nxt = P.tri[t_cur];
     }
     T rmin = NumTraits<T>::inf();
@@ -762,7 +772,7 @@ __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowSt
 
     if (P.dbg & 4) return;
     for (int tile = 0; tile < NT; tile++) {
-        const int item0 = tile * BN;
+        const int item0 = (t_begin + tile) * BN;
         mbar_wait(bar_blkf + 8 * cw, (unsigned)tile & 1u);
         if (!(P.dbg & 2)) {
             if (lane < 16) {
@@ -809,7 +819,7 @@ __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowSt
                 T thr[UN], eff[UN];
                 int col[UN];
 #pragma unroll
-                for (int t = 0; t < UN; t++) before[t] = cnt_g[e0 + (t < run ? t : 0)];
+                for (int t = 0; t < UN; t++) before[t] = sliced ? 0u : cnt_g[e0 + (t < run ? t : 0)];
                 if (q + UN <= PCAP) {
 #pragma unroll
                     for (int t = 0; t < UN; t++) { thr[t] = pthr[q + t]; col[t] = pitem[q + t] - item0; }
@@ -833,7 +843,8 @@ __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowSt
                         unsigned ct = c[t];
                         if (col[t] > 0 && col[t] < BN)
                             for (int x = 0; x < col[t]; x++) ct += (src[x] == thr[t]);
-                        cnt_g[e0 + t] = before[t] + ct;
+                        if (!sliced) cnt_g[e0 + t] = before[t] + ct;
+                        else if (ct) atomicAdd(&cnt_g[e0 + t], ct);
                     }
                 }
                 while (banded) {
@@ -880,8 +891,11 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
     const int warp = tid >> 5, lane = tid & 31;
     const int tile_u0 = blockIdx.x * UM;            // first user (batch-local) of this CTA
     const int KC = (P.p_pad + BK - 1) / BK;
-    const int NT = (P.n + BN - 1) / BN;
+    const int NT_all = (P.n + BN - 1) / BN;
+    const int t_begin = (int)((long long)NT_all * blockIdx.y / gridDim.y);          // this CTA's range of item tiles (the whole catalogue unless sliced)
+    const int NT = (int)((long long)NT_all * (blockIdx.y + 1) / gridDim.y) - t_begin;
     const int total = NT * KC;
+    const size_t slice_off = (size_t)blockIdx.y * (size_t)P.slice_rows;               // first row of this slice's candidate buffers
 
     // ---- one-time setup: per-row selection state, train cursors, barriers ----
     for (int r = tid; r < UM; r += NTHR) {
@@ -897,6 +911,11 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
             const int u = P.user0 + ul;
             cur = P.trp[u]; end = P.trp[u + 1];
             tp0 = P.tep[u]; npos = P.tep[u + 1] - tp0;
+            if (t_begin > 0) {                       // first train item inside this CTA's item range
+                int lo = cur, hi = end;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (P.tri[mid] < t_begin * BN) lo = mid + 1; else hi = mid; }
+                cur = lo;
+            }
         }
         rs->cur_train[r] = cur;
         rs->end_train[r] = end;
@@ -916,7 +935,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
         // registers to where they are needed (every warp of a group of four executes the same setmaxnreg)
         if (warp >= 2 * NCWARPS) {
             asm volatile("setmaxnreg.dec.sync.aligned.u32 32;");
-            if (warp == 2 * NCWARPS && lane == 0) tma_producer_role<T, S, BK>(P, As, Bs, bar_full, bar_empty, KC, total);
+            if (warp == 2 * NCWARPS && lane == 0) tma_producer_role<T, S, BK>(P, As, Bs, bar_full, bar_empty, KC, total, t_begin);
             return;
         }
         if (warp >= NCWARPS) {
@@ -924,13 +943,13 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
             else asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
             auc_count_role<T>(P, rs, reinterpret_cast<T*>(smem_raw + L::blk_off), reinterpret_cast<int*>(smem_raw + L::pref_off),
                               reinterpret_cast<T*>(smem_raw + L::pthr_off), reinterpret_cast<int*>(smem_raw + L::pitem_off),
-                              bar_blkf, bar_blke, warp - NCWARPS, lane, tile_u0, NT);
+                              bar_blkf, bar_blke, warp - NCWARPS, lane, tile_u0, NT, t_begin);
             return;
         }
         if (sizeof(T) == 4) asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
         else asm volatile("setmaxnreg.inc.sync.aligned.u32 160;");
     } else if (warp == NCWARPS) {
-        if (lane == 0) tma_producer_role<T, S, BK>(P, As, Bs, bar_full, bar_empty, KC, total);
+        if (lane == 0) tma_producer_role<T, S, BK>(P, As, Bs, bar_full, bar_empty, KC, total, t_begin);
         return;
     }
 
@@ -943,7 +962,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
     int it = 0;
     unsigned ready = mbar_try(bar_full, 0);         // probe of the stage about to be consumed
     for (int tile = 0; tile < NT; tile++) {
-        const int item0 = tile * BN;
+        const int item0 = (t_begin + tile) * BN;
         mt.zero();
         for (int kc = 0; kc < KC; kc++, it++) {
             const int s = it % S;
@@ -1007,8 +1026,8 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
             T m = max_nan(max_nan(s[0], s[1]), max_nan(s[2], s[3]));
             if (NC == 8) m = max_nan(m, max_nan(max_nan(s[NC - 4], s[NC - 3]), max_nan(s[NC - 2], s[NC - 1])));
             if (!(m < tau)) {
-                T* cs = P.cand_score + (size_t)rs->urow[row] * C;
-                int* ci = P.cand_item + (size_t)rs->urow[row] * C;
+                T* cs = P.cand_score + (slice_off + (size_t)rs->urow[row]) * C;
+                int* ci = P.cand_item + (slice_off + (size_t)rs->urow[row]) * C;
                 row_slow<T>(rs, cs, ci, P.tri, P.n, tau, row, item0 + lx * 4, item0 + BN, s[0], s[1], s[2], s[3]);
                 if (NC == 8)
                     row_slow<T>(rs, cs, ci, P.tri, P.n, tau, row, item0 + 64 + lx * 4, item0 + BN, s[NC - 4], s[NC - 3], s[NC - 2], s[NC - 1]);
@@ -1043,7 +1062,7 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
                 const int r = __ffs(need) - 1;
                 need &= need - 1;
                 const int row = wrow0 + r;
-                const size_t base = (size_t)rs->urow[row] * C;
+                const size_t base = (slice_off + (size_t)rs->urow[row]) * C;
                 compact_user<T, C>(P.cand_score + base, P.cand_item + base, rs->cnt[row], P.K, lane, &rs->tau[row], &rs->cnt[row]);
             }
         }
@@ -1055,10 +1074,10 @@ score_select_kernel(const __grid_constant__ ScoreSelectParams<T> P)
         const int row = wrow0 + r;
         if (tile_u0 + row < P.mb) {
             const int ul = rs->urow[row];
-            const size_t base = (size_t)ul * C;
+            const size_t base = (slice_off + (size_t)ul) * C;
             compact_user<T, C>(P.cand_score + base, P.cand_item + base, rs->cnt[row], P.K, lane, &rs->tau[row], &rs->cnt[row]);
             if (lane == 0) {
-                P.cand_count[ul] = rs->cnt[row];
+                P.cand_count[slice_off + ul] = rs->cnt[row];
                 if (rs->nan[row]) atomicOr(&P.uflags[P.user0 + ul], 1);
             }
         }
@@ -1092,6 +1111,29 @@ __global__ void rank_topk_kernel(T* __restrict__ cand_score, int* __restrict__ c
         const int idx = e * 32 + lane;
         if (idx < nv) { cs[idx] = s[e]; ci[idx] = it[e]; }
     }
+}
+
+// Item slices (ScoreSelectParams::slice_rows): join the heads the slices left for every user into slice 0's row -- the best K of the
+// catalogue are among the best K of every range.  One warp per user.
+template <typename T>
+__global__ void merge_slices_kernel(T* __restrict__ cand_score, int* __restrict__ cand_item, int* __restrict__ cand_count,
+                                    const int C, const int mb, const int slices, const int slice_rows)
+{
+    const int lane = threadIdx.x & 31;
+    const int ul = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (ul >= mb) return;
+    int total = cand_count[ul];
+    for (int y = 1; y < slices; y++) {
+        const size_t row = (size_t)y * slice_rows + ul;
+        const int c = cand_count[row];
+        for (int i = lane; i < c; i += 32) {
+            cand_score[(size_t)ul * C + total + i] = cand_score[row * C + i];
+            cand_item[(size_t)ul * C + total + i] = cand_item[row * C + i];
+        }
+        total += c;
+    }
+    __syncwarp();
+    if (lane == 0) cand_count[ul] = total;
 }
 
 }  // namespace rmb
