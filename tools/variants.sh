@@ -9,7 +9,7 @@ if [ "$1" = build ]; then
   shift
   i=0
   for v in "$@"; do
-    $NVCC $FLAGS $v -o build_variants/v$i.so recometrics_b200/csrc/api.cu & 
+    $NVCC $FLAGS $v -o build_variants/v$i.so recometrics_b200/csrc/api.cu recometrics_b200/csrc/full_order.cu & 
     echo "v$i: $v" >> build_variants/list.txt.tmp
     i=$((i+1))
   done
