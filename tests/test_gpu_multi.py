@@ -110,3 +110,21 @@ def test_pageable_item_factors_go_up_in_slices(rb, monkeypatch):
     a = _run(rb, d, 50, **TOPK4)
     b = _run(rb, d, 50, devices=[0, 1], **TOPK4)
     _same(a, b)
+
+
+def test_reference_cython_wrapper_spreads_its_call_over_the_gpus(rb, tmp_path, monkeypatch):
+    """The reference's UNMODIFIED Cython wrapper (oracle/build_ref_cython.py) with RMB200_DEVICES=all in the environment: its one
+    calc_metrics_float call runs on every GPU of the box and returns the one-GPU rows bit for bit (m = 300 is three 128-user
+    units: two devices get work)."""
+    _need(rb, 2)
+    import test_capi_host
+    monkeypatch.setenv("RMB200_DEVICES", "all")
+    stdout, path = test_capi_host.run_reference_cython_wrapper(tmp_path)
+    assert "HAS 1" in stdout and "COMPUTED" in stdout, stdout
+    rows = np.load(path)
+    monkeypatch.delenv("RMB200_DEVICES")
+    d = synth.make(1, m=300, n=500, p=8)
+    r = rb.calc_reco_metrics_ex(d["X_train"], d["X_test"], d["A"], d["B"], k=5, precision=True, average_precision=True, ndcg=True,
+                                break_ties_with_noise=False)
+    for i, key in enumerate(("P@K", "AP@K", "NDCG@K")):
+        assert np.array_equal(rows[i], r.metrics[key], equal_nan=True), key

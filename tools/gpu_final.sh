@@ -12,5 +12,6 @@ for cfg in 3 5 2 1; do
 done
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_bench_${TAG}.csv \
     python bench.py --users 151552 --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/launches_bench_${TAG}.log 2>&1
+( time timeout 300 python bench.py --zero-users 0.01 --no-cpu-baseline ) > gpurun_out/bench_cfg4_zero1pct_${TAG}.log 2>&1
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_${TAG}.txt 2>&1
 tail -3 gpurun_out/pytest_gpu_${TAG}.txt; for f in gpurun_out/bench_*_${TAG}.log; do grep '^{' $f | cut -c1-400; done; tail -3 gpurun_out/smoke_${TAG}.txt
