@@ -237,6 +237,8 @@ void full_order_plan(const int n, const int elem_bytes, const int max_users, int
     if (uc < 1) uc = 1;
     if (uc > max_users) uc = max_users;
     uc = (uc + FO_ROWS - 1) / FO_ROWS * FO_ROWS;
+    if (uc * (long long)n > 0x7fffffffLL) uc = 0x7fffffffLL / (n > 0 ? n : 1);      // (offsets and CUB's item counts are 32-bit)
+    if (uc < 1) uc = 1;
     const size_t elems = (size_t)uc * (size_t)n;
     const size_t key_bytes = elem_bytes == 4 ? 4 : 8;
     size_t temp = 0;
