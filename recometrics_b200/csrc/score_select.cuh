@@ -764,26 +764,28 @@ __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowSt
     }
     T rmin = NumTraits<T>::inf();
     // (pointers of the parameter block in registers: through the reference every use is a load from the parameter space)
+    const int dbg = P.dbg, n_items = P.n;
+    const int* const tri_g = P.tri;
     unsigned int* const cnt_g = P.auc_cnt;
     const unsigned int* const near_g = P.auc_near;
     const T* const sorted_g = P.pos_sorted;
     const int* const item_g = P.pos_item;
     count_sync();                                                // (the staged entries are visible)
 
-    if (P.dbg & 4) return;
+    if (dbg & 4) return;
     for (int tile = 0; tile < NT; tile++) {
         const int item0 = (t_begin + tile) * BN;
         mbar_wait(bar_blkf + 8 * cw, (unsigned)tile & 1u);
-        if (!(P.dbg & 2)) {
+        if (!(dbg & 2)) {
             if (lane < 16) {
                 T* dst = blk + (size_t)lane * BNP;
                 while (t_nxt < item0 + BN) {
                     dst[t_nxt - item0] = NumTraits<T>::nan();
                     t_cur++;
-                    t_nxt = t_cur < t_end ? P.tri[t_cur] : INT_MAX;
+                    t_nxt = t_cur < t_end ? tri_g[t_cur] : INT_MAX;
                 }
-                if (item0 + BN > P.n)
-                    for (int x = (P.n > item0 ? P.n - item0 : 0); x < BN; x++) dst[x] = NumTraits<T>::nan();
+                if (item0 + BN > n_items)
+                    for (int x = (n_items > item0 ? n_items - item0 : 0); x < BN; x++) dst[x] = NumTraits<T>::nan();
             }
             __syncwarp();
             const T* src = blk + (size_t)(lane >> 1) * BNP + (lane & 1) * (BN / 2);
@@ -800,7 +802,7 @@ __device__ __noinline__ void auc_count_role(const ScoreSelectParams<T>& P, RowSt
             rmin = fmin(rmin, fmin(m0, m1));
         }
         count_sync();                                            // all 128 rows of the tile are staged and masked
-        if (!(P.dbg & 3)) {
+        if (!(dbg & 3)) {
             for (int j = 0, u = tc; u < n_units; j++, u += NCT) {
                 int row;
                 if (j < 4) row = j == 0 ? unit_row[0] : (j == 1 ? unit_row[1] : (j == 2 ? unit_row[2] : unit_row[3]));
