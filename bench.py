@@ -365,7 +365,8 @@ def product_arm(args, cfg, rank, world, local_rank):
                 traffic = int(traffic["dram_bytes_read"]) + int(traffic["dram_bytes_write"])
         except Exception:
             traffic = None
-    batches = -(-m // (8 * 148 * 128))
+    big = path == 2 and (-(-n // 128) * 128) * (-(-(p + (1 if bias is not None else 0)) // 16) * 16) * 2 > (160 << 20)
+    batches = -(-m // ((4 if big else 8) * 148 * 128))      # (api.cu: a user batch is 8 waves of 148 CTAs x 128 users, 4 on very large catalogues)
     if path == 2:
         # tensor-core filter: every (user, item) score is an MMA on fp16 copies of the factors (tcgen05 kind::f16 runs
         # fp16 and bf16 operands at the same rate); the measured denominator is the driver's cuBLAS bf16 figure

@@ -808,7 +808,11 @@ int run_call(const CallArgs<T>& a)
     int nsm = 148;
     cudaDeviceGetAttribute(&nsm, cudaDevAttrMultiProcessorCount, dev);
     const int wave_users = nsm * BM;                       // one CTA (128 users) per SM
-    int UB = 8 * wave_users;                               // users per batch (8 full waves)
+    int UB = 8 * wave_users;                               // users per batch: 8 full waves ...
+    // ... 4 when the filter's item image is much larger than the L2 (256 MB at 1M items x 128 factors): the CTAs of a longer
+    // launch drift further apart and re-stream the item tiles from HBM (cfg4: 3.16 M users/s at 4 waves, 3.10 at 8, 2.96 at
+    // 16, 2.76 with all 1M users in one launch; smaller catalogues prefer 8; profiles/r02_batch_size.txt)
+    if (use_tensor && (size_t)round_up(a.n, 128) * KB * sizeof(__half) > (size_t)160 << 20) UB = 4 * wave_users;
     if (const char* env = std::getenv("RMB200_BATCH_USERS")) { const int v = std::atoi(env); if (v > 0) UB = round_up(v, BM); }
     int fo_chunk = 0; size_t fo_bytes = 0;
     if (use_full) {
