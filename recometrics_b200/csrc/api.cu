@@ -608,6 +608,7 @@ int run_call(const CallArgs<T>& a)
 #define RMB_F_CMID 512
 #endif
     if (use_tensor) C = (K <= 32) ? 256 : (K <= 128 ? RMB_F_CMID : 1024);
+    if (use_tensor) if (const char* env = std::getenv("RMB200_FILTER_C")) { const int v = std::atoi(env); if ((v == 256 || v == 512 || v == 1024) && v >= C) C = v; }   // developer
     if (use_full) C = round_up(K < a.n ? K : a.n, 32);              // row pitch of the ranked lists
 
     // ---- CSR slices of users [ub, ue), index pointers re-based to the slice ----
