@@ -481,6 +481,29 @@ struct PrefetchStream {
     }
 };
 
+// The metric rows of a user batch go back to the host on a stream of their own, out of two alternating sets of staging
+// buffers: the copy of batch b runs while batch b+1 is scored (cumulative rows are m x K values per metric: 400 MB at cfg5).
+// ready[s]: the kernels writing set s have run; copied[s]: its copies have landed (the set may be written again).
+struct ResultStream {
+    cudaStream_t s = nullptr;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    bool copied_valid[2] = {false, false};
+    cudaError_t init()
+    {
+        cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+        for (int i = 0; i < 2 && e == cudaSuccess; i++) {
+            e = cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[i], cudaEventDisableTiming);
+        }
+        return e;
+    }
+    ~ResultStream()
+    {
+        if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }       // nothing may still be reading the staging buffers
+        for (int i = 0; i < 2; i++) { if (ready[i]) cudaEventDestroy(ready[i]); if (copied[i]) cudaEventDestroy(copied[i]); }
+    }
+};
+
 template <typename T>
 int stage_rows(const T* src, size_t ld, int rows, int cols, bool on_dev, DevBuf& staging,
                const T** dev_src, size_t* dev_ld, cudaStream_t st, rmb200_timing_t& tm)
@@ -838,7 +861,9 @@ int run_call(const CallArgs<T>& a)
         CK(d_nz_cnt.alloc(16));
     }
 
-    DevBuf d_At, d_cs, d_ci, d_cc, d_out[10], d_tki, d_tks, d_stat_out, d_Ab, d_anorm;
+    DevBuf d_At, d_cs, d_ci, d_cc, d_out[2][10], d_tki[2], d_tks[2], d_stat_out[2], d_Ab, d_anorm;
+    ResultStream rsx;                                     // (declared after the buffers it reads: drained before they are freed)
+    if (!on_dev) CK(rsx.init());
     CK(d_At.alloc((size_t)p_pad * UB * sizeof(T)));
     DevBuf d_capx, d_overflow, d_fb_list, d_At_fb;
     // sampled threshold guess of the filter (filter_select.cuh, pass 0): every stride-th item tile, about 7/K of the
@@ -907,11 +932,13 @@ int run_call(const CallArgs<T>& a)
     CK(d_ci.alloc((size_t)UB * fma_slices * C * sizeof(int)));
     CK(d_cc.alloc((size_t)UB * fma_slices * sizeof(int)));
     if (!on_dev) {
-        for (int q = 0; q < 10; q++)
-            if (a.out[q]) CK(d_out[q].alloc((size_t)UB * (q < 8 ? rs : 1) * sizeof(T)));
-        if (ex && ex->topk_items) CK(d_tki.alloc((size_t)UB * K * sizeof(int)));
-        if (ex && ex->topk_scores) CK(d_tks.alloc((size_t)UB * K * sizeof(T)));
-        if (ex && ex->status) CK(d_stat_out.alloc((size_t)UB * sizeof(int)));
+        for (int set = 0; set < (UB < mr ? 2 : 1); set++) {
+            for (int q = 0; q < 10; q++)
+                if (a.out[q]) CK(d_out[set][q].alloc((size_t)UB * (q < 8 ? rs : 1) * sizeof(T)));
+            if (ex && ex->topk_items) CK(d_tki[set].alloc((size_t)UB * K * sizeof(int)));
+            if (ex && ex->topk_scores) CK(d_tks[set].alloc((size_t)UB * K * sizeof(T)));
+            if (ex && ex->status) CK(d_stat_out[set].alloc((size_t)UB * sizeof(int)));
+        }
     }
 
     // per-metric means over the users of the call (extension): partial sums per 256 users, added up in order at the end
@@ -929,6 +956,7 @@ int run_call(const CallArgs<T>& a)
         const int nb = (mr - b0) < UB ? (mr - b0) : UB;
         const int nb_pad = round_up(nb, BM);
         const int a_slot = (b0 / UB) & 1;                  // staging buffer holding this batch's user factors (host inputs)
+        const int r_set = (b0 / UB) & 1;                   // set of result staging buffers of this batch (host outputs)
         // the kernels reading the staged rows are queued: mark the buffer; once the scoring kernel is queued as well, the
         // next batch's rows go up into the other buffer (pageable sources keep this thread busy copying meanwhile)
         auto staged_rows_consumed = [&]() -> int {
@@ -1209,18 +1237,19 @@ int run_call(const CallArgs<T>& a)
             mp.pos_perm = d_pos_perm.as<int>(); mp.log2tab = d_log2.as<double>();
             mp.nan_value = nan_value;
             T* outs[10];
+            if (!on_dev && rsx.copied_valid[r_set]) CK(cudaStreamWaitEvent(st, rsx.copied[r_set], 0));      // the set's previous rows have left
             for (int q = 0; q < 10; q++) {
                 const size_t stride = q < 8 ? rs : 1;
                 if (!a.out[q]) outs[q] = nullptr;
                 else if (on_dev) outs[q] = a.out[q] + (size_t)(ub + b0) * stride;
-                else outs[q] = d_out[q].as<T>();
+                else outs[q] = d_out[r_set][q].as<T>();
             }
             mp.p = outs[0]; mp.tp = outs[1]; mp.r = outs[2]; mp.ap = outs[3]; mp.tap = outs[4];
             mp.ndcg = outs[5]; mp.hit = outs[6]; mp.rr = outs[7]; mp.roc = outs[8]; mp.pr = outs[9];
             mp.status_out = nullptr; mp.topk_items = nullptr; mp.topk_scores = nullptr;
-            if (ex && ex->status) mp.status_out = on_dev ? ex->status + ub + b0 : d_stat_out.as<int>();
-            if (ex && ex->topk_items) mp.topk_items = on_dev ? ex->topk_items + (size_t)(ub + b0) * K : d_tki.as<int>();
-            if (ex && ex->topk_scores) mp.topk_scores = on_dev ? reinterpret_cast<T*>(ex->topk_scores) + (size_t)(ub + b0) * K : d_tks.as<T>();
+            if (ex && ex->status) mp.status_out = on_dev ? ex->status + ub + b0 : d_stat_out[r_set].as<int>();
+            if (ex && ex->topk_items) mp.topk_items = on_dev ? ex->topk_items + (size_t)(ub + b0) * K : d_tki[r_set].as<int>();
+            if (ex && ex->topk_scores) mp.topk_scores = on_dev ? reinterpret_cast<T*>(ex->topk_scores) + (size_t)(ub + b0) * K : d_tks[r_set].as<T>();
             mp.pos_rank = pos_rank_d;
             if (pf.test_rows_pending) { CK(cudaStreamWaitEvent(st, pf.test_rows, 0)); pf.test_rows_pending = false; }
             user_metrics_kernel<T><<<(nb + METRICS_WARPS - 1) / METRICS_WARPS, METRICS_WARPS * 32, 0, st>>>(mp);
@@ -1242,19 +1271,26 @@ int run_call(const CallArgs<T>& a)
         // results of the batch -> caller's arrays at the shard's row offset (no gather collective:
         // every shard writes its own disjoint rows)
         if (!on_dev) {
-            pt.start();
+            CK(cudaEventRecord(rsx.ready[r_set], st));
+            CK(cudaStreamWaitEvent(rsx.s, rsx.ready[r_set], 0));
             for (int q = 0; q < 10; q++) {
                 if (!a.out[q] || (ex && ex->skip_row_copy)) continue;
                 const size_t stride = q < 8 ? rs : 1;
                 const size_t bytes = (size_t)nb * stride * sizeof(T);
-                CK(cudaMemcpyAsync(a.out[q] + (size_t)(ub + b0) * stride, d_out[q].p, bytes, cudaMemcpyDeviceToHost, st));
+                CK(cudaMemcpyAsync(a.out[q] + (size_t)(ub + b0) * stride, d_out[r_set][q].p, bytes, cudaMemcpyDeviceToHost, rsx.s));
                 tm.d2h_bytes += (int64_t)bytes;
             }
-            if (ex && ex->status) { CK(cudaMemcpyAsync(ex->status + ub + b0, d_stat_out.p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)nb * 4; }
-            if (ex && ex->topk_items) { CK(cudaMemcpyAsync(ex->topk_items + (size_t)(ub + b0) * K, d_tki.p, (size_t)nb * K * sizeof(int), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)nb * K * 4; }
-            if (ex && ex->topk_scores) { CK(cudaMemcpyAsync(reinterpret_cast<T*>(ex->topk_scores) + (size_t)(ub + b0) * K, d_tks.p, (size_t)nb * K * sizeof(T), cudaMemcpyDeviceToHost, st)); tm.d2h_bytes += (int64_t)nb * K * (int64_t)sizeof(T); }
-            pt.stop(tm.d2h_ms);
+            if (ex && ex->status) { CK(cudaMemcpyAsync(ex->status + ub + b0, d_stat_out[r_set].p, (size_t)nb * sizeof(int), cudaMemcpyDeviceToHost, rsx.s)); tm.d2h_bytes += (int64_t)nb * 4; }
+            if (ex && ex->topk_items) { CK(cudaMemcpyAsync(ex->topk_items + (size_t)(ub + b0) * K, d_tki[r_set].p, (size_t)nb * K * sizeof(int), cudaMemcpyDeviceToHost, rsx.s)); tm.d2h_bytes += (int64_t)nb * K * 4; }
+            if (ex && ex->topk_scores) { CK(cudaMemcpyAsync(reinterpret_cast<T*>(ex->topk_scores) + (size_t)(ub + b0) * K, d_tks[r_set].p, (size_t)nb * K * sizeof(T), cudaMemcpyDeviceToHost, rsx.s)); tm.d2h_bytes += (int64_t)nb * K * (int64_t)sizeof(T); }
+            CK(cudaEventRecord(rsx.copied[r_set], rsx.s));
+            rsx.copied_valid[r_set] = true;
         }
+    }
+    if (!on_dev) {                                        // what is still exposed of the result copies
+        const auto t_d = std::chrono::steady_clock::now();
+        CK(cudaStreamSynchronize(rsx.s));
+        tm.d2h_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_d).count();
     }
     if (!on_dev && ex && ex->pos_rank && !g_interrupt.load()) {
         pt.start();
