@@ -51,7 +51,9 @@ enum rmb200_status {
     RMB200_ERR_CUDA = 3,         /* a CUDA call failed; see rmb200_last_error()               */
     RMB200_ERR_OOM = 4,          /* device or host allocation failed (reference: bad_alloc)   */
     RMB200_ERR_INTERRUPTED = 5,  /* SIGINT arrived during the call (reference: runtime_error) */
-    RMB200_ERR_UNSUPPORTED = 6   /* valid request outside what this build implements          */
+    RMB200_ERR_UNSUPPORTED = 6,  /* valid request outside what this build implements          */
+    RMB200_ERR_RUNTIME = 7       /* the input is one the reference answers with std::runtime_error (splitters);   */
+                                 /* rmb200_last_error() holds the reference's message                              */
 };
 
 /* Largest k_metrics the fused top-K selection kernels handle.  Larger values (the reference's only bound is k_metrics <= n,
@@ -198,6 +200,81 @@ RMB200_API void rmb200_release_workspace(void);
 /* Measured FP32 / FP64 FMA throughput of `device` in TFLOP/s (register-resident FMA chains on all
  * SMs; the roofline denominator for the scoring kernel).  dtype_bytes = 4 or 8.  <0 on error. */
 RMB200_API double rmb200_measure_fma_peak(int device, int dtype_bytes, double *elapsed_ms);
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Train/test splitters -- the step BEFORE the evaluation path.
+ *
+ *   reference interface (replaced)                                                    this library
+ *   --------------------------------------------------------------------------------  --------------------------------
+ *   split_data_selected_users_float/_double  src/recometrics_signatures.hpp:100-130   rmb200_split_selected_users_f32/_f64
+ *     (template src/recometrics.hpp:1015-1106; declared recometrics/wrapper.pyx:64-77, :147-160; called :541, :580)
+ *   split_data_separate_users_float/_double  src/recometrics_signatures.hpp:132-178   rmb200_split_separate_users_f32/_f64
+ *     (template src/recometrics.hpp:1201-1322; wrapper.pyx:79-100, :162-183; called :647, :732)
+ *   split_data_joined_users_float/_double    src/recometrics_signatures.hpp:180-221   rmb200_split_joined_users_f32/_f64
+ *     (template src/recometrics.hpp:1439-1505; wrapper.pyx:102-120, :185-203; called :677, :762)
+ *
+ * Same arguments in the same order as the reference; the reference's std::vector outputs become one rmb200_split_t of
+ * library-owned host arrays, released with rmb200_split_free().  include/recometrics_b200_shim.hpp defines the reference's
+ * functions (and the templates Rwrapper.cpp instantiates) on top.  test_fraction is a double for both value types, as in the
+ * reference's templates; its *_float linkage functions declare it `const float` (src/recometrics_signatures.hpp:127, :174,
+ * :217), i.e. round it to float first -- a binding that mirrors them passes (double)(float)fraction, as the shim's do.
+ *
+ * Division of work.  WHICH entries of a user are held out is decided by ONE sequential std::mt19937 stream that the
+ * reference consumes user after user through std::shuffle (src/recometrics.hpp:1055-1060, :1223-1226): that replay is
+ * sequential by the definition of the output and runs on the host (while X is on its way to the GPU), producing one byte
+ * per entry.  Everything that touches the matrix itself -- ordering each row's entries by item id where the input is not
+ * sorted, the stable partition of every row into its training and held-out part, the gather of the selected / remaining
+ * users' rows and of the values -- runs on the GPU.  Results are entry-for-entry those of the reference built with the same
+ * libstdc++.  No CPU fallback: without a CUDA device the calls return RMB200_ERR_NO_DEVICE.
+ * Errors the reference throws as std::runtime_error come back as RMB200_ERR_RUNTIME with its message.
+ * ------------------------------------------------------------------------------------------------------------------- */
+typedef struct rmb200_csr_t {
+    int32_t rows, cols;
+    int64_t nnz;
+    int32_t *indptr;            /* [rows + 1]; NULL when the matrix is not part of this split (or the reference leaves it empty) */
+    int32_t *indices;           /* [nnz] */
+    void *values;               /* [nnz] float or double */
+} rmb200_csr_t;
+
+typedef struct rmb200_split_t {
+    rmb200_csr_t train, test, rem;   /* rem: separate users only */
+    int32_t *users_test;        /* [n_users_test] rows of X taken as test users, ascending (NULL for selected_users) */
+    int32_t n_users_test;
+    int32_t value_bytes;        /* 4 or 8 */
+    int32_t rows_sorted_on_device;   /* 1: some split row came with unsorted item ids and was ordered on the GPU */
+    int32_t device;
+    double total_ms, plan_ms, h2d_ms, kernel_ms, d2h_ms;   /* plan_ms: the sequential mt19937 replay on the host (overlaps h2d_ms) */
+    int64_t kernel_launches, h2d_bytes, d2h_bytes;
+    void *owner;                /* internal */
+} rmb200_split_t;
+
+RMB200_API int rmb200_split_selected_users_f32(const int32_t *X_csr_p, const int32_t *X_csr_i, const float *X_csr,
+    int32_t m, int32_t n, double test_fraction, uint64_t seed, int32_t device, rmb200_split_t *out);
+RMB200_API int rmb200_split_selected_users_f64(const int32_t *X_csr_p, const int32_t *X_csr_i, const double *X_csr,
+    int32_t m, int32_t n, double test_fraction, uint64_t seed, int32_t device, rmb200_split_t *out);
+RMB200_API int rmb200_split_separate_users_f32(const int32_t *X_csr_p, const int32_t *X_csr_i, const float *X_csr,
+    int32_t m, int32_t n, int32_t n_users_test, double test_fraction, int consider_cold_start,
+    int32_t min_items_pool, int32_t min_pos_test, uint64_t seed, int32_t device, rmb200_split_t *out);
+RMB200_API int rmb200_split_separate_users_f64(const int32_t *X_csr_p, const int32_t *X_csr_i, const double *X_csr,
+    int32_t m, int32_t n, int32_t n_users_test, double test_fraction, int consider_cold_start,
+    int32_t min_items_pool, int32_t min_pos_test, uint64_t seed, int32_t device, rmb200_split_t *out);
+RMB200_API int rmb200_split_joined_users_f32(const int32_t *X_csr_p, const int32_t *X_csr_i, const float *X_csr,
+    int32_t m, int32_t n, int32_t n_users_test, double test_fraction, int consider_cold_start,
+    int32_t min_items_pool, int32_t min_pos_test, uint64_t seed, int32_t device, rmb200_split_t *out);
+RMB200_API int rmb200_split_joined_users_f64(const int32_t *X_csr_p, const int32_t *X_csr_i, const double *X_csr,
+    int32_t m, int32_t n, int32_t n_users_test, double test_fraction, int consider_cold_start,
+    int32_t min_items_pool, int32_t min_pos_test, uint64_t seed, int32_t device, rmb200_split_t *out);
+/* The host half of the splitters on its own: the replay of the reference's mt19937 stream, with no matrix touched and no
+ * GPU needed -- NOT a CPU path to a split (it returns no matrices), but the part of the result that can be checked on any
+ * machine.  sample_users = 0: every row is split (selected_users); 1: the user sample of separate / joined users is drawn
+ * first and written to users_test[<= m] / *n_users_out.  held[<= nnz] receives one byte per entry of the split rows, in row
+ * order (1 = held out), *n_entries_out their number. */
+RMB200_API int rmb200_split_plan(const int32_t *X_csr_p, int32_t m, int32_t n, int32_t sample_users, int32_t n_users_test,
+    double test_fraction, int consider_cold_start, int32_t min_items_pool, int32_t min_pos_test, uint64_t seed,
+    int32_t *users_test, int32_t *n_users_out, uint8_t *held, int64_t *n_entries_out);
+/* Release the arrays of a split (safe on a zeroed or already released struct). */
+RMB200_API void rmb200_split_free(rmb200_split_t *split);
+RMB200_API int rmb200_sizeof_split(void);
 
 #ifdef __cplusplus
 }

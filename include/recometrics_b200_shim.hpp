@@ -9,6 +9,13 @@
  *   template <class real_t> calc_metrics(...)  (reference: src/recometrics.hpp:359-385,
  *                                               called by src/Rwrapper.cpp:250-274)
  *   get_has_openmp()                           (reference: src/recometrics_signatures.hpp:46)
+ *   split_data_{selected,separate,joined}_users_float / _double
+ *                                              (reference: src/recometrics_signatures.hpp:100-221,
+ *                                               defined in src/recometrics_instantiated.cpp:145-387,
+ *                                               called by recometrics/wrapper.pyx:541-762)
+ *   template <class real_t> split_data_{selected,separate,joined}_users(...)
+ *                                              (reference: src/recometrics.hpp:1015-1106, :1201-1322, :1439-1505,
+ *                                               called by src/Rwrapper.cpp:452, :529, :570)
  *
  * so that wrapper.pyx builds unmodified when this header replaces recometrics_signatures.hpp and
  * recometrics_instantiated.cpp is dropped from the sources, and Rwrapper.cpp swaps one #include.
@@ -28,6 +35,7 @@
 #include <new>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 #include "recometrics_b200.h"
 
@@ -51,6 +59,7 @@ inline void raise_for_status(const int rc)
         case RMB200_ERR_OOM: throw std::bad_alloc();
         case RMB200_ERR_BAD_ARG: throw std::invalid_argument(msg);
         case RMB200_ERR_INTERRUPTED: throw std::runtime_error("Error: procedure was interrupted.\n");
+        case RMB200_ERR_RUNTIME: throw std::runtime_error(rmb200_last_error());   /* the reference's own message */
         default: throw std::runtime_error(msg);
     }
 }
@@ -192,6 +201,173 @@ inline void calc_metrics_float
                         p_at_k, tp_at_k, r_at_k, ap_at_k, tap_at_k, ndcg_at_k, hit_at_k, rr_at_k, roc_auc, pr_auc,
                         consider_cold_start, min_items_pool, min_pos_test, nthreads, seed);
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Train/test splitters.  The reference fills std::vectors; the C-ABI hands out one rmb200_split_t of library-owned arrays
+ * that are copied into the caller's vectors and released (also when the copy throws).
+ * ------------------------------------------------------------------------------------------------------------------- */
+namespace rmb200_shim {
+
+struct split_guard {
+    rmb200_split_t s;
+    split_guard() : s() {}
+    ~split_guard() { rmb200_split_free(&s); }
+};
+
+template <class real_t>
+inline void take(const rmb200_csr_t &c, std::vector<int32_t> &p, std::vector<int32_t> &i, std::vector<real_t> &v)
+{
+    if (!c.indptr) return;                      /* (split_data_selected_users on m = 0 leaves its outputs untouched) */
+    p.assign(c.indptr, c.indptr + (size_t)c.rows + 1);
+    i.assign(c.indices, c.indices + (size_t)c.nnz);
+    v.assign((const real_t *)c.values, (const real_t *)c.values + (size_t)c.nnz);
+}
+
+inline int split_selected(const int32_t *p, const int32_t *i, const float *v, int32_t m, int32_t n, double f, uint64_t seed, rmb200_split_t *o)
+{ return rmb200_split_selected_users_f32(p, i, v, m, n, f, seed, -1, o); }
+inline int split_selected(const int32_t *p, const int32_t *i, const double *v, int32_t m, int32_t n, double f, uint64_t seed, rmb200_split_t *o)
+{ return rmb200_split_selected_users_f64(p, i, v, m, n, f, seed, -1, o); }
+inline int split_users(bool joined, const int32_t *p, const int32_t *i, const float *v, int32_t m, int32_t n, int32_t nu, double f,
+                       bool cold, int32_t pool, int32_t pos, uint64_t seed, rmb200_split_t *o)
+{
+    return joined ? rmb200_split_joined_users_f32(p, i, v, m, n, nu, f, cold, pool, pos, seed, -1, o)
+                  : rmb200_split_separate_users_f32(p, i, v, m, n, nu, f, cold, pool, pos, seed, -1, o);
+}
+inline int split_users(bool joined, const int32_t *p, const int32_t *i, const double *v, int32_t m, int32_t n, int32_t nu, double f,
+                       bool cold, int32_t pool, int32_t pos, uint64_t seed, rmb200_split_t *o)
+{
+    return joined ? rmb200_split_joined_users_f64(p, i, v, m, n, nu, f, cold, pool, pos, seed, -1, o)
+                  : rmb200_split_separate_users_f64(p, i, v, m, n, nu, f, cold, pool, pos, seed, -1, o);
+}
+
+}  /* namespace rmb200_shim */
+
+/* src/recometrics.hpp:1015-1030 */
+template <class real_t>
+void split_data_selected_users
+(
+    const int32_t *restrict X_csr_p,
+    const int32_t *restrict X_csr_i,
+    const real_t *restrict X_csr,
+    const int32_t m, const int32_t n,
+    std::vector<int32_t> &Xtrain_csr_p,
+    std::vector<int32_t> &Xtrain_csr_i,
+    std::vector<real_t> &Xtrain_csr,
+    std::vector<int32_t> &Xtest_csr_p,
+    std::vector<int32_t> &Xtest_csr_i,
+    std::vector<real_t> &Xtest_csr,
+    const double test_fraction,
+    uint64_t seed
+)
+{
+    rmb200_shim::split_guard g;
+    rmb200_shim::raise_for_status(rmb200_shim::split_selected(X_csr_p, X_csr_i, X_csr, m, n, test_fraction, seed, &g.s));
+    rmb200_shim::take<real_t>(g.s.train, Xtrain_csr_p, Xtrain_csr_i, Xtrain_csr);
+    rmb200_shim::take<real_t>(g.s.test, Xtest_csr_p, Xtest_csr_i, Xtest_csr);
+}
+
+/* src/recometrics.hpp:1201-1224 */
+template <class real_t>
+void split_data_separate_users
+(
+    const int32_t *restrict X_csr_p,
+    const int32_t *restrict X_csr_i,
+    const real_t *restrict X_csr,
+    int32_t m, int32_t n,
+    std::vector<int32_t> &users_test,
+    std::vector<int32_t> &Xrem_csr_p,
+    std::vector<int32_t> &Xrem_csr_i,
+    std::vector<real_t> &Xrem_csr,
+    std::vector<int32_t> &Xtrain_csr_p,
+    std::vector<int32_t> &Xtrain_csr_i,
+    std::vector<real_t> &Xtrain_csr,
+    std::vector<int32_t> &Xtest_csr_p,
+    std::vector<int32_t> &Xtest_csr_i,
+    std::vector<real_t> &Xtest_csr,
+    const int32_t n_users_test,
+    const double test_fraction,
+    const bool consider_cold_start,
+    const int32_t min_items_pool,
+    const int32_t min_pos_test,
+    uint64_t seed
+)
+{
+    rmb200_shim::split_guard g;
+    rmb200_shim::raise_for_status(rmb200_shim::split_users(false, X_csr_p, X_csr_i, X_csr, m, n, n_users_test, test_fraction,
+                                                           consider_cold_start, min_items_pool, min_pos_test, seed, &g.s));
+    users_test.assign(g.s.users_test, g.s.users_test + g.s.n_users_test);
+    rmb200_shim::take<real_t>(g.s.rem, Xrem_csr_p, Xrem_csr_i, Xrem_csr);
+    rmb200_shim::take<real_t>(g.s.train, Xtrain_csr_p, Xtrain_csr_i, Xtrain_csr);
+    rmb200_shim::take<real_t>(g.s.test, Xtest_csr_p, Xtest_csr_i, Xtest_csr);
+}
+
+/* src/recometrics.hpp:1439-1459 */
+template <class real_t>
+void split_data_joined_users
+(
+    const int32_t *restrict X_csr_p,
+    const int32_t *restrict X_csr_i,
+    const real_t *restrict X_csr,
+    int32_t m, int32_t n,
+    std::vector<int32_t> &users_test,
+    std::vector<int32_t> &Xtrain_csr_p,
+    std::vector<int32_t> &Xtrain_csr_i,
+    std::vector<real_t> &Xtrain_csr,
+    std::vector<int32_t> &Xtest_csr_p,
+    std::vector<int32_t> &Xtest_csr_i,
+    std::vector<real_t> &Xtest_csr,
+    const int32_t n_users_test,
+    const double test_fraction,
+    const bool consider_cold_start,
+    const int32_t min_items_pool,
+    const int32_t min_pos_test,
+    uint64_t seed
+)
+{
+    rmb200_shim::split_guard g;
+    rmb200_shim::raise_for_status(rmb200_shim::split_users(true, X_csr_p, X_csr_i, X_csr, m, n, n_users_test, test_fraction,
+                                                           consider_cold_start, min_items_pool, min_pos_test, seed, &g.s));
+    users_test.assign(g.s.users_test, g.s.users_test + g.s.n_users_test);
+    rmb200_shim::take<real_t>(g.s.train, Xtrain_csr_p, Xtrain_csr_i, Xtrain_csr);
+    rmb200_shim::take<real_t>(g.s.test, Xtest_csr_p, Xtest_csr_i, Xtest_csr);
+}
+
+/* src/recometrics_signatures.hpp:100-221 / src/recometrics_instantiated.cpp:145-387.  The float entry points declare the
+ * fraction `const float`: it is rounded to float on the way in, exactly as there. */
+#define RMB200_SHIM_SPLIT_LINKAGE(SUFFIX, REAL, FRAC)                                                                          \
+inline void split_data_selected_users_##SUFFIX(const int32_t *restrict X_csr_p, const int32_t *restrict X_csr_i,              \
+    const REAL *restrict X_csr, const int32_t m, const int32_t n, std::vector<int32_t> &Xtrain_csr_p,                          \
+    std::vector<int32_t> &Xtrain_csr_i, std::vector<REAL> &Xtrain_csr, std::vector<int32_t> &Xtest_csr_p,                      \
+    std::vector<int32_t> &Xtest_csr_i, std::vector<REAL> &Xtest_csr, const FRAC test_fraction, uint64_t seed)                  \
+{                                                                                                                              \
+    split_data_selected_users<REAL>(X_csr_p, X_csr_i, X_csr, m, n, Xtrain_csr_p, Xtrain_csr_i, Xtrain_csr, Xtest_csr_p,        \
+                                    Xtest_csr_i, Xtest_csr, test_fraction, seed);                                              \
+}                                                                                                                              \
+inline void split_data_separate_users_##SUFFIX(const int32_t *restrict X_csr_p, const int32_t *restrict X_csr_i,              \
+    const REAL *restrict X_csr, int32_t m, int32_t n, std::vector<int32_t> &users_test, std::vector<int32_t> &Xrem_csr_p,      \
+    std::vector<int32_t> &Xrem_csr_i, std::vector<REAL> &Xrem_csr, std::vector<int32_t> &Xtrain_csr_p,                         \
+    std::vector<int32_t> &Xtrain_csr_i, std::vector<REAL> &Xtrain_csr, std::vector<int32_t> &Xtest_csr_p,                      \
+    std::vector<int32_t> &Xtest_csr_i, std::vector<REAL> &Xtest_csr, const int32_t n_users_test, const FRAC test_fraction,     \
+    const bool consider_cold_start, const int32_t min_items_pool, const int32_t min_pos_test, uint64_t seed)                   \
+{                                                                                                                              \
+    split_data_separate_users<REAL>(X_csr_p, X_csr_i, X_csr, m, n, users_test, Xrem_csr_p, Xrem_csr_i, Xrem_csr, Xtrain_csr_p, \
+                                    Xtrain_csr_i, Xtrain_csr, Xtest_csr_p, Xtest_csr_i, Xtest_csr, n_users_test,               \
+                                    test_fraction, consider_cold_start, min_items_pool, min_pos_test, seed);                   \
+}                                                                                                                              \
+inline void split_data_joined_users_##SUFFIX(const int32_t *restrict X_csr_p, const int32_t *restrict X_csr_i,                \
+    const REAL *restrict X_csr, int32_t m, int32_t n, std::vector<int32_t> &users_test, std::vector<int32_t> &Xtrain_csr_p,    \
+    std::vector<int32_t> &Xtrain_csr_i, std::vector<REAL> &Xtrain_csr, std::vector<int32_t> &Xtest_csr_p,                      \
+    std::vector<int32_t> &Xtest_csr_i, std::vector<REAL> &Xtest_csr, const int32_t n_users_test, const FRAC test_fraction,     \
+    const bool consider_cold_start, const int32_t min_items_pool, const int32_t min_pos_test, uint64_t seed)                   \
+{                                                                                                                              \
+    split_data_joined_users<REAL>(X_csr_p, X_csr_i, X_csr, m, n, users_test, Xtrain_csr_p, Xtrain_csr_i, Xtrain_csr,           \
+                                  Xtest_csr_p, Xtest_csr_i, Xtest_csr, n_users_test, test_fraction, consider_cold_start,       \
+                                  min_items_pool, min_pos_test, seed);                                                         \
+}
+RMB200_SHIM_SPLIT_LINKAGE(double, double, double)
+RMB200_SHIM_SPLIT_LINKAGE(float, float, float)
+#undef RMB200_SHIM_SPLIT_LINKAGE
 
 #ifdef RMB200_SHIM_DEFINED_RESTRICT
 #   undef restrict

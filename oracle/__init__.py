@@ -30,8 +30,11 @@ _u64 = ctypes.c_uint64
 
 def build(force=False):
     """Compile the restatement (always possible) and, when /root/reference exists, oracle/_ref."""
-    if force or not os.path.exists(ORACLE_SO) or (os.path.isdir("/root/reference/src") and not os.path.exists(REF_SO)):
-        subprocess.run(["make", "-C", _HERE], check=True, capture_output=True)
+    srcs = [os.path.join(_HERE, f) for f in ("recometrics_oracle.c", "recometrics_oracle_impl.h", "split_oracle.c", "ref_shim.cpp")]
+    stale = os.path.exists(ORACLE_SO) and any(os.path.getmtime(f) > os.path.getmtime(ORACLE_SO) for f in srcs[:3])
+    ref_stale = os.path.isdir("/root/reference/src") and (not os.path.exists(REF_SO) or os.path.getmtime(srcs[3]) > os.path.getmtime(REF_SO))
+    if force or stale or ref_stale or not os.path.exists(ORACLE_SO):
+        subprocess.run(["make", "-B", "-C", _HERE], check=True, capture_output=True)
 
 
 def have_ref():
@@ -165,3 +168,95 @@ def oracle_calc(A, B, Xtr, Xte, k, metrics=("p", "ap", "ndcg"), cumulative=False
         res["pos_rank"] = pos_rank[: int(tep[-1])]
         res["tie_flags"] = tie_flags
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Train/test splitters (split_oracle.c; reference: src/recometrics.hpp:1015-1505).  Both doors take the CSR arrays of X
+# and return plain numpy arrays: {"users_test", "train": (p, i, v), "test": (p, i, v), "rem": (p, i, v) or None}.
+# ---------------------------------------------------------------------------------------------------------------------
+SPLIT_ERRORS = {1: "Target number of test users is larger than available users.\n",
+                2: "Selected minimum number of items is larger than total number of items.\n",
+                3: "No users satisfy criteria for test inclusion.\n"}
+
+
+def _split_bufs(m, nnz, dtype):
+    mk = lambda size, dt: np.full(max(size, 1), -7, dtype=dt)   # noqa: E731  (poison: "left untouched" is visible)
+    return dict(ut=mk(m, np.int32), rep=mk(m + 1, np.int32), rei=mk(nnz, np.int32), rev=mk(nnz, dtype),
+                trp=mk(m + 1, np.int32), tri=mk(nnz, np.int32), trv=mk(nnz, dtype),
+                tep=mk(m + 1, np.int32), tei=mk(nnz, np.int32), tev=mk(nnz, dtype))
+
+
+def _split_args(Xp, Xi, Xv):
+    Xv = np.ascontiguousarray(Xv)
+    assert Xv.dtype in (np.float32, np.float64)
+    return np.ascontiguousarray(Xp, dtype=np.int32), np.ascontiguousarray(Xi, dtype=np.int32), Xv
+
+
+def _csr3(p, i, v, rows, nnz=None):
+    p = p[: rows + 1].copy()
+    nnz = int(p[-1]) if nnz is None else nnz
+    return p, i[:nnz].copy(), v[:nnz].copy()
+
+
+def oracle_split(Xp, Xi, Xv, m, n, split_type="all", n_users_test=0, test_fraction=0.3, consider_cold_start=False,
+                 min_items_pool=2, min_pos_test=1, seed=1):
+    """The C restatement.  The float32 entry points of the reference take the fraction as a float
+    (src/recometrics_instantiated.cpp:192, :267, :337): the same rounding is applied here."""
+    lib = _lib(ORACLE_SO)
+    Xp, Xi, Xv = _split_args(Xp, Xi, Xv)
+    frac = float(np.float32(test_fraction)) if Xv.dtype == np.float32 else float(test_fraction)
+    b = _split_bufs(m, Xi.size, Xv.dtype)
+    vsz = Xv.dtype.itemsize
+    if split_type == "all":
+        lib.rmo_split_selected_users.restype = _int
+        rc = lib.rmo_split_selected_users(_ptr(Xp), _ptr(Xi), _ptr(Xv), _int(vsz), _i32(m), _i32(n), ctypes.c_double(frac),
+                                          _u64(seed), _ptr(b["trp"]), _ptr(b["tri"]), _ptr(b["trv"]),
+                                          _ptr(b["tep"]), _ptr(b["tei"]), _ptr(b["tev"]))
+        if rc:
+            raise RuntimeError("Passed negative dimensions.\n")
+        return {"users_test": None, "train": _csr3(b["trp"], b["tri"], b["trv"], m), "test": _csr3(b["tep"], b["tei"], b["tev"], m),
+                "rem": None}
+    joined = split_type == "joined"
+    sizes = np.zeros(2, dtype=np.int64)
+    lib.rmo_split_users.restype = _int
+    rc = lib.rmo_split_users(_ptr(Xp), _ptr(Xi), _ptr(Xv), _int(vsz), _i32(m), _i32(n), _i32(n_users_test), ctypes.c_double(frac),
+                             _int(int(consider_cold_start)), _i32(min_items_pool), _i32(min_pos_test), _u64(seed), _int(int(joined)),
+                             _ptr(b["ut"]), _ptr(b["rep"]), _ptr(b["rei"]), _ptr(b["rev"]),
+                             _ptr(b["trp"]), _ptr(b["tri"]), _ptr(b["trv"]), _ptr(b["tep"]), _ptr(b["tei"]), _ptr(b["tev"]), _ptr(sizes))
+    if rc:
+        raise RuntimeError(SPLIT_ERRORS.get(rc, "split oracle failed (%d)" % rc))
+    taken, others = int(sizes[0]), int(sizes[1])
+    return {"users_test": b["ut"][:taken].copy(),
+            "train": _csr3(b["trp"], b["tri"], b["trv"], taken + (others if joined else 0)),
+            "test": _csr3(b["tep"], b["tei"], b["tev"], taken),
+            "rem": None if joined else _csr3(b["rep"], b["rei"], b["rev"], others)}
+
+
+def ref_split(Xp, Xi, Xv, m, n, split_type="all", n_users_test=0, test_fraction=0.3, consider_cold_start=False,
+              min_items_pool=2, min_pos_test=1, seed=1):
+    """The UNMODIFIED reference (split_data_*_float/_double, src/recometrics_signatures.hpp:100-221)."""
+    lib = _lib(REF_SO)
+    Xp, Xi, Xv = _split_args(Xp, Xi, Xv)
+    sfx = "f32" if Xv.dtype == np.float32 else "f64"
+    b = _split_bufs(m, Xi.size, Xv.dtype)
+    sizes = np.zeros(7, dtype=np.int64)
+    err = ctypes.create_string_buffer(256)
+    if split_type == "all":
+        fn = getattr(lib, "rmref_split_selected_users_" + sfx)
+        fn.restype = _int
+        rc = fn(_ptr(Xp), _ptr(Xi), _ptr(Xv), _i32(m), _i32(n), ctypes.c_double(test_fraction), _u64(seed),
+                _ptr(b["trp"]), _ptr(b["tri"]), _ptr(b["trv"]), _ptr(b["tep"]), _ptr(b["tei"]), _ptr(b["tev"]), _ptr(sizes), err)
+    else:
+        fn = getattr(lib, "rmref_split_users_" + sfx)
+        fn.restype = _int
+        rc = fn(_ptr(Xp), _ptr(Xi), _ptr(Xv), _i32(m), _i32(n), _i32(n_users_test), ctypes.c_double(test_fraction),
+                _int(int(consider_cold_start)), _i32(min_items_pool), _i32(min_pos_test), _u64(seed), _int(int(split_type == "joined")),
+                _ptr(b["ut"]), _ptr(b["rep"]), _ptr(b["rei"]), _ptr(b["rev"]),
+                _ptr(b["trp"]), _ptr(b["tri"]), _ptr(b["trv"]), _ptr(b["tep"]), _ptr(b["tei"]), _ptr(b["tev"]), _ptr(sizes), err)
+    if rc:
+        raise RuntimeError(err.value.decode())
+    nut, nrp, nri, ntp, nti, nep, nei = (int(x) for x in sizes)
+    return {"users_test": b["ut"][:nut].copy() if split_type != "all" else None,
+            "train": _csr3(b["trp"], b["tri"], b["trv"], ntp - 1, nti),
+            "test": _csr3(b["tep"], b["tei"], b["tev"], nep - 1, nei),
+            "rem": _csr3(b["rep"], b["rei"], b["rev"], nrp - 1, nri) if split_type == "separated" else None}

@@ -3,11 +3,12 @@ librecometrics_b200.so -- the drop-in the north-star describes: "a thin C-ABI th
 
     python oracle/build_ref_cython.py [/root/reference]   ->  oracle/_ref/cy_b200/cpp_funs.<abi>.so
 
-wrapper.pyx is cythonized where it lies; its `recometrics_signatures.hpp` resolves to oracle/ref_cython_signatures/ (the
-three metric entry points come from include/recometrics_b200_shim.hpp, i.e. from the C-ABI; the splitter declarations from
-the reference's own header); the reference's recometrics_instantiated.cpp is compiled next to it for the splitters only
-(its three metric definitions renamed out of the way).  Everything generated goes to oracle/_ref/ (git-ignored, travels
-to the GPU box); no reference source is copied into the repository.
+wrapper.pyx is cythonized where it lies; its `recometrics_signatures.hpp` resolves to oracle/ref_cython_signatures/, which
+includes the reference's own header (declarations only) and then include/recometrics_b200_shim.hpp, whose definitions of
+calc_metrics_float/_double, get_has_openmp and the six split_data_* entry points all go to the C-ABI.  No reference source
+file is compiled into the module: every native call of the reference's Python package lands in librecometrics_b200.so.
+Everything generated goes to oracle/_ref/ (git-ignored, travels to the GPU box); no reference source is copied into the
+repository.
 """
 import os
 import subprocess
@@ -40,10 +41,7 @@ def build(reference="/root/reference", verbose=False):
                   "-DRMB200_REFERENCE_SIGNATURES_HPP=\"%s\"" % os.path.join(src, "recometrics_signatures.hpp"),
                   "-I", os.path.join(HERE, "ref_cython_signatures"), "-I", os.path.join(ROOT, "include")] + inc_py +
         [wrapper_cpp, "-o", os.path.join(tmp, "wrapper.o")])
-    run(common + ["-D_FOR_PYTHON", "-Dcalc_metrics_float=rmb200_unused_calc_metrics_float",
-                  "-Dcalc_metrics_double=rmb200_unused_calc_metrics_double", "-Dget_has_openmp=rmb200_unused_get_has_openmp",
-                  "-I", src, os.path.join(src, "recometrics_instantiated.cpp"), "-o", os.path.join(tmp, "splitters.o")])
-    run([cxx, "-shared", "-fopenmp", os.path.join(tmp, "wrapper.o"), os.path.join(tmp, "splitters.o"), "-o", target,
+    run([cxx, "-shared", "-fopenmp", os.path.join(tmp, "wrapper.o"), "-o", target,
          "-L", os.path.dirname(lib), "-lrecometrics_b200", "-Wl,-rpath,$ORIGIN/../../../recometrics_b200"])
     return target
 

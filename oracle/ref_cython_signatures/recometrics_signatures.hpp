@@ -3,20 +3,14 @@
  * librecometrics_b200.so instead of the reference's CPU code:
  *
  *   calc_metrics_float / calc_metrics_double / get_has_openmp   defined by include/recometrics_b200_shim.hpp (-> the C-ABI)
- *   split_data_*                                                 declared by the reference's own header (their definitions
- *                                                                come from the reference's recometrics_instantiated.cpp,
- *                                                                compiled next to it: the splitters are out of scope here)
+ *   split_data_{selected,separate,joined}_users_float/_double    likewise (-> rmb200_split_*)
  *
- * The reference header's declarations of the three metric entry points are renamed out of the way; nothing of it is copied.
+ * The reference header is still included -- FIRST, so that the shim's definitions are checked against its declarations by
+ * the compiler (a different parameter list would be an overload the wrapper's calls could not pick unambiguously) -- and
+ * nothing of it is copied.  No reference source file is compiled into the module.
  */
 #ifndef RMB200_REF_CYTHON_SIGNATURES_HPP
 #define RMB200_REF_CYTHON_SIGNATURES_HPP
-#include "recometrics_b200_shim.hpp"
-#define calc_metrics_float  rmb200_refdecl_calc_metrics_float
-#define calc_metrics_double rmb200_refdecl_calc_metrics_double
-#define get_has_openmp      rmb200_refdecl_get_has_openmp
 #include RMB200_REFERENCE_SIGNATURES_HPP   /* -DRMB200_REFERENCE_SIGNATURES_HPP="\"<reference>/src/recometrics_signatures.hpp\"" */
-#undef calc_metrics_float
-#undef calc_metrics_double
-#undef get_has_openmp
+#include "recometrics_b200_shim.hpp"
 #endif

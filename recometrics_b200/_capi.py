@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # RMB200_LIB: developer override used by tools/variants.sh to time alternative builds of the same library
 LIB_PATH = os.environ.get("RMB200_LIB") or os.path.join(_HERE, "librecometrics_b200.so")
 
-OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_INTERRUPTED, ERR_UNSUPPORTED = range(7)
+OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_OOM, ERR_INTERRUPTED, ERR_UNSUPPORTED, ERR_RUNTIME = range(8)
 MAX_K = 384     # largest k_metrics of the selection kernels; above it the call takes the full-order path
 
 # order of the ten outputs in the C signature (src/recometrics_signatures.hpp:56-65 of the reference)
@@ -25,6 +25,10 @@ EXPORTS = (
     "rmb200_device_count", "rmb200_version", "rmb200_last_error",
     "rmb200_request_interrupt", "rmb200_measure_fma_peak", "rmb200_release_workspace",
     "rmb200_sizeof_extra", "rmb200_sizeof_timing",
+    "rmb200_split_selected_users_f32", "rmb200_split_selected_users_f64",
+    "rmb200_split_separate_users_f32", "rmb200_split_separate_users_f64",
+    "rmb200_split_joined_users_f32", "rmb200_split_joined_users_f64",
+    "rmb200_split_plan", "rmb200_split_free", "rmb200_sizeof_split",
 )
 
 
@@ -58,6 +62,26 @@ class Extra(ctypes.Structure):
     ]
 
 
+class Csr(ctypes.Structure):
+    _fields_ = [("rows", ctypes.c_int32), ("cols", ctypes.c_int32), ("nnz", ctypes.c_int64),
+                ("indptr", ctypes.c_void_p), ("indices", ctypes.c_void_p), ("values", ctypes.c_void_p)]
+
+
+class Split(ctypes.Structure):
+    """rmb200_split_t (include/recometrics_b200.h)."""
+    _fields_ = [
+        ("train", Csr), ("test", Csr), ("rem", Csr),
+        ("users_test", ctypes.c_void_p), ("n_users_test", ctypes.c_int32), ("value_bytes", ctypes.c_int32),
+        ("rows_sorted_on_device", ctypes.c_int32), ("device", ctypes.c_int32),
+        ("total_ms", ctypes.c_double), ("plan_ms", ctypes.c_double), ("h2d_ms", ctypes.c_double),
+        ("kernel_ms", ctypes.c_double), ("d2h_ms", ctypes.c_double),
+        ("kernel_launches", ctypes.c_int64), ("h2d_bytes", ctypes.c_int64), ("d2h_bytes", ctypes.c_int64),
+        ("owner", ctypes.c_void_p),
+    ]
+    TIMING = ("total_ms", "plan_ms", "h2d_ms", "kernel_ms", "d2h_ms", "kernel_launches", "h2d_bytes", "d2h_bytes",
+              "rows_sorted_on_device", "device")
+
+
 class NativeLibraryError(RuntimeError):
     pass
 
@@ -82,7 +106,9 @@ def load():
     lib.rmb200_version.restype = ctypes.c_int
     lib.rmb200_sizeof_extra.restype = ctypes.c_int
     lib.rmb200_sizeof_timing.restype = ctypes.c_int
-    if lib.rmb200_sizeof_extra() != ctypes.sizeof(Extra) or lib.rmb200_sizeof_timing() != ctypes.sizeof(Timing):
+    lib.rmb200_sizeof_split.restype = ctypes.c_int
+    if (lib.rmb200_sizeof_extra() != ctypes.sizeof(Extra) or lib.rmb200_sizeof_timing() != ctypes.sizeof(Timing)
+            or lib.rmb200_sizeof_split() != ctypes.sizeof(Split)):
         raise NativeLibraryError("recometrics_b200: %s was built from a different include/recometrics_b200.h (struct sizes differ); rebuild it" % LIB_PATH)
     lib.rmb200_last_error.restype = ctypes.c_char_p
     lib.rmb200_request_interrupt.restype = None
@@ -91,6 +117,11 @@ def load():
     lib.rmb200_measure_fma_peak.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
     for name in EXPORTS[:4]:
         getattr(lib, name).restype = ctypes.c_int
+    for name in EXPORTS:
+        if name.startswith("rmb200_split_") and name != "rmb200_split_free":
+            getattr(lib, name).restype = ctypes.c_int
+    lib.rmb200_split_free.restype = None
+    lib.rmb200_split_free.argtypes = [ctypes.POINTER(Split)]
     _lib = lib
     return lib
 
@@ -132,6 +163,8 @@ def raise_for_status(rc):
         raise NotImplementedError(msg)
     if rc == ERR_NO_DEVICE:
         raise RuntimeError("recometrics_b200 needs a CUDA device (no CPU fallback): " + msg)
+    if rc == ERR_RUNTIME:          # the reference's own std::runtime_error, message included (Cython `except +` -> RuntimeError)
+        raise RuntimeError(msg)
     raise RuntimeError("recometrics_b200 CUDA failure: " + msg)
 
 
@@ -198,3 +231,60 @@ def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, stri
     if timing is not None:
         ex.timing = ctypes.pointer(timing)
     return ex
+
+
+def _take(addr, count, dtype):
+    """A numpy copy of `count` elements at host address `addr` (library-owned memory that is about to be released)."""
+    if not count:
+        return np.empty(0, dtype=dtype)
+    nbytes = int(count) * np.dtype(dtype).itemsize
+    return np.frombuffer((ctypes.c_uint8 * nbytes).from_address(addr), dtype=dtype).copy()
+
+
+def _take_csr(c, dtype):
+    if not c.indptr:
+        return None
+    return (_take(c.indptr, c.rows + 1, np.int32), _take(c.indices, c.nnz, np.int32), _take(c.values, c.nnz, dtype), (int(c.rows), int(c.cols)))
+
+
+def split(kind, indptr, indices, data, m, n, n_users_test=0, test_fraction=0.3, consider_cold_start=False,
+          min_items_pool=2, min_pos_test=1, seed=1, device=-1):
+    """rmb200_split_{selected,separate,joined}_users_f32/_f64.  kind: "all" | "separated" | "joined".
+    Returns {"train", "test", "rem": (indptr, indices, data, shape) or None, "users_test": int32 array or None, "timing": dict}."""
+    lib = load()
+    dtype = np.dtype(data.dtype)
+    assert dtype in (np.float32, np.float64) and indptr.dtype == np.int32 and indices.dtype == np.int32
+    sfx = "f32" if dtype == np.float32 else "f64"
+    # the reference's float entry points take the fraction as a float (src/recometrics_signatures.hpp:127, :174, :217)
+    frac = ctypes.c_double(float(np.float32(test_fraction)) if dtype == np.float32 else float(test_fraction))
+    out = Split()
+    common = (_vp(indptr), _vp(indices), _vp(data), ctypes.c_int32(m), ctypes.c_int32(n))
+    if kind == "all":
+        rc = getattr(lib, "rmb200_split_selected_users_" + sfx)(*common, frac, ctypes.c_uint64(seed), ctypes.c_int32(device), ctypes.byref(out))
+    else:
+        fn = getattr(lib, ("rmb200_split_separate_users_" if kind == "separated" else "rmb200_split_joined_users_") + sfx)
+        rc = fn(*common, ctypes.c_int32(n_users_test), frac, ctypes.c_int(int(consider_cold_start)), ctypes.c_int32(min_items_pool),
+                ctypes.c_int32(min_pos_test), ctypes.c_uint64(seed), ctypes.c_int32(device), ctypes.byref(out))
+    try:
+        raise_for_status(rc)
+        return {"train": _take_csr(out.train, dtype), "test": _take_csr(out.test, dtype), "rem": _take_csr(out.rem, dtype),
+                "users_test": _take(out.users_test, out.n_users_test, np.int32) if out.users_test else None,
+                "timing": {k: getattr(out, k) for k in Split.TIMING}}
+    finally:
+        lib.rmb200_split_free(ctypes.byref(out))
+
+
+def split_plan(indptr, m, n, sample_users, n_users_test=0, test_fraction=0.3, consider_cold_start=False, min_items_pool=2,
+               min_pos_test=1, seed=1):
+    """rmb200_split_plan: the host half of a split (needs no GPU).  Returns (users_test or None, held bytes)."""
+    lib = load()
+    indptr = np.ascontiguousarray(indptr, dtype=np.int32)
+    users = np.zeros(max(m, 1), dtype=np.int32)
+    held = np.zeros(max(int(indptr[m]), 1), dtype=np.uint8)
+    nu, ne = ctypes.c_int32(0), ctypes.c_int64(0)
+    rc = lib.rmb200_split_plan(_vp(indptr), ctypes.c_int32(m), ctypes.c_int32(n), ctypes.c_int32(int(sample_users)),
+                               ctypes.c_int32(n_users_test), ctypes.c_double(test_fraction), ctypes.c_int(int(consider_cold_start)),
+                               ctypes.c_int32(min_items_pool), ctypes.c_int32(min_pos_test), ctypes.c_uint64(seed),
+                               _vp(users), ctypes.byref(nu), _vp(held), ctypes.byref(ne))
+    raise_for_status(rc)
+    return (users[: nu.value].copy() if sample_users else None), held[: ne.value].copy()

@@ -41,6 +41,12 @@ void set_err(const char* what, const char* detail = nullptr)
     if (detail) { g_err += ": "; g_err += detail; }
 }
 
+}  // namespace
+namespace rmb {
+void set_last_error(const char* what, const char* detail) { set_err(what, detail); }   // for the library's other translation units (split.cu)
+}
+namespace {
+
 extern "C" void rmb200_sigint_handler(int) { g_interrupt.store(1); }
 
 // /root/reference/src/recometrics.hpp:126-174 (SignalSwitcher): swap the SIGINT handler for the

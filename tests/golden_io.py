@@ -1,4 +1,4 @@
-"""Load a tests/golden/*.npz case (inputs + the unmodified reference's outputs)."""
+"""Load a tests/golden/g_*.npz evaluation case (inputs + the unmodified reference's outputs)."""
 import glob
 import os
 
@@ -9,7 +9,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def case_names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "g_*.npz")))
 
 
 def load_case(name):

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstring>
 #include <stdexcept>
+#include <vector>
 #ifdef HAVE_REFERENCE_HEADER
 #include "recometrics_signatures.hpp"
 #endif
@@ -23,8 +24,65 @@ typedef void (*metrics_f64_t)(const double*, const size_t, const double*, const 
                               double*, double*, double*, double*, double*, double*, double*, double*, double*, double*,
                               const bool, int32_t, int32_t, int32_t, uint64_t);
 
+// the splitters' linkage functions (src/recometrics_signatures.hpp:100-221) and the templates src/Rwrapper.cpp:452-570 instantiates
+typedef std::vector<int32_t> ivec;
+typedef void (*split_all_f64_t)(const int32_t*, const int32_t*, const double*, const int32_t, const int32_t, ivec&, ivec&, std::vector<double>&,
+                                ivec&, ivec&, std::vector<double>&, const double, uint64_t);
+typedef void (*split_all_f32_t)(const int32_t*, const int32_t*, const float*, const int32_t, const int32_t, ivec&, ivec&, std::vector<float>&,
+                                ivec&, ivec&, std::vector<float>&, const float, uint64_t);
+typedef void (*split_sep_f64_t)(const int32_t*, const int32_t*, const double*, int32_t, int32_t, ivec&, ivec&, ivec&, std::vector<double>&,
+                                ivec&, ivec&, std::vector<double>&, ivec&, ivec&, std::vector<double>&, const int32_t, const double,
+                                const bool, const int32_t, const int32_t, uint64_t);
+typedef void (*split_sep_f32_t)(const int32_t*, const int32_t*, const float*, int32_t, int32_t, ivec&, ivec&, ivec&, std::vector<float>&,
+                                ivec&, ivec&, std::vector<float>&, ivec&, ivec&, std::vector<float>&, const int32_t, const float,
+                                const bool, const int32_t, const int32_t, uint64_t);
+typedef void (*split_join_f64_t)(const int32_t*, const int32_t*, const double*, int32_t, int32_t, ivec&, ivec&, ivec&, std::vector<double>&,
+                                 ivec&, ivec&, std::vector<double>&, const int32_t, const double, const bool, const int32_t, const int32_t, uint64_t);
+typedef void (*split_join_f32_t)(const int32_t*, const int32_t*, const float*, int32_t, int32_t, ivec&, ivec&, ivec&, std::vector<float>&,
+                                 ivec&, ivec&, std::vector<float>&, const int32_t, const float, const bool, const int32_t, const int32_t, uint64_t);
+
+static int check_splitters()
+{
+    split_all_f64_t a64 = &split_data_selected_users_double;
+    split_all_f32_t a32 = &split_data_selected_users_float;
+    split_sep_f64_t s64 = &split_data_separate_users_double;
+    split_sep_f32_t s32 = &split_data_separate_users_float;
+    split_join_f64_t j64 = &split_data_joined_users_double;
+    split_join_f32_t j32 = &split_data_joined_users_float;
+    (void)a32; (void)s32; (void)j32;
+    // 4 users x 6 items
+    const int32_t Xp[5] = {0, 3, 3, 7, 9}, Xi[9] = {0, 2, 5, 1, 2, 3, 4, 0, 5};
+    const double Xv[9] = {1., 2., 3., 4., 5., 6., 7., 8., 9.};
+    int threw = 0;
+    try {
+        ivec trp, tri, tep, tei, ut, rp, ri;
+        std::vector<double> trv, tev, rv;
+        a64(Xp, Xi, Xv, 4, 6, trp, tri, trv, tep, tei, tev, 0.5, 1);
+        if (trp.size() != 5 || tep.size() != 5 || tri.size() + tei.size() != 9 || tep[4] != 2 + 0 + 2 + 1) return 5;
+        s64(Xp, Xi, Xv, 4, 6, ut, rp, ri, rv, trp, tri, trv, tep, tei, tev, 2, 0.5, false, 2, 1, 1);
+        if (ut.size() != 2 || rp.size() != 3 || trp.size() != 3 || tep.size() != 3) return 6;
+        j64(Xp, Xi, Xv, 4, 6, ut, trp, tri, trv, tep, tei, tev, 2, 0.5, false, 2, 1, 1);
+        if (ut.size() != 2 || trp.size() != 5 || tep.size() != 3 || tri.size() + tei.size() != 9) return 7;
+        // the template form of the Rcpp wrapper, and the reference's refusal with its own message
+        split_data_selected_users<double>(Xp, Xi, Xv, 4, 6, trp, tri, trv, tep, tei, tev, 0.5, 1);
+        try {
+            split_data_separate_users<double>(Xp, Xi, Xv, 4, 6, ut, rp, ri, rv, trp, tri, trv, tep, tei, tev, 5, 0.5, false, 2, 1, 1);
+            return 8;
+        } catch (const std::runtime_error& e) {
+            if (std::strcmp(e.what(), "Target number of test users is larger than available users.\n") != 0) return 9;
+        }
+        std::printf("split ok users=%d,%d\n", ut[0], ut[1]);
+    } catch (const std::runtime_error& e) {
+        threw = 1;
+        std::printf("split threw runtime_error: %s\n", e.what());
+    }
+    if (!get_has_openmp() && !threw) return 10;    // no device and no exception: a CPU path would be a bug
+    return 0;
+}
+
 int main()
 {
+    if (const int rc = check_splitters()) return rc;
     metrics_f32_t f32 = &calc_metrics_float;
     metrics_f64_t f64 = &calc_metrics_double;
     // 3 users x 4 items, 2 factors; every user holds out one item
