@@ -233,24 +233,40 @@ def make_extra(device=-1, user_begin=0, user_end=0, inputs_on_device=False, stri
     return ex
 
 
-def _take(addr, count, dtype):
-    """A numpy copy of `count` elements at host address `addr` (library-owned memory that is about to be released)."""
+class _SplitOwner:
+    """Keeps one rmb200_split_t alive while numpy arrays look at its library-owned arrays; releases it afterwards."""
+
+    def __init__(self, lib, out):
+        self.lib, self.out = lib, out
+
+    def __del__(self):
+        try:
+            self.lib.rmb200_split_free(ctypes.byref(self.out))
+        except Exception:       # interpreter shutdown
+            pass
+
+
+def _view(owner, addr, count, dtype):
+    """numpy array over `count` elements at host address `addr` without a copy; the array (through its base) keeps `owner` alive."""
     if not count:
         return np.empty(0, dtype=dtype)
-    nbytes = int(count) * np.dtype(dtype).itemsize
-    return np.frombuffer((ctypes.c_uint8 * nbytes).from_address(addr), dtype=dtype).copy()
+    buf = (ctypes.c_uint8 * (int(count) * np.dtype(dtype).itemsize)).from_address(addr)
+    buf._rmb200_owner = owner
+    return np.frombuffer(buf, dtype=dtype)
 
 
-def _take_csr(c, dtype):
+def _view_csr(owner, c, dtype):
     if not c.indptr:
         return None
-    return (_take(c.indptr, c.rows + 1, np.int32), _take(c.indices, c.nnz, np.int32), _take(c.values, c.nnz, dtype), (int(c.rows), int(c.cols)))
+    return (_view(owner, c.indptr, c.rows + 1, np.int32), _view(owner, c.indices, c.nnz, np.int32), _view(owner, c.values, c.nnz, dtype),
+            (int(c.rows), int(c.cols)))
 
 
 def split(kind, indptr, indices, data, m, n, n_users_test=0, test_fraction=0.3, consider_cold_start=False,
           min_items_pool=2, min_pos_test=1, seed=1, device=-1):
     """rmb200_split_{selected,separate,joined}_users_f32/_f64.  kind: "all" | "separated" | "joined".
-    Returns {"train", "test", "rem": (indptr, indices, data, shape) or None, "users_test": int32 array or None, "timing": dict}."""
+    Returns {"train", "test", "rem": (indptr, indices, data, shape) or None, "users_test": int32 array or None, "timing": dict};
+    the arrays are views of the library's own result arrays (no copy), released with the last of them."""
     lib = load()
     dtype = np.dtype(data.dtype)
     assert dtype in (np.float32, np.float64) and indptr.dtype == np.int32 and indices.dtype == np.int32
@@ -265,13 +281,11 @@ def split(kind, indptr, indices, data, m, n, n_users_test=0, test_fraction=0.3, 
         fn = getattr(lib, ("rmb200_split_separate_users_" if kind == "separated" else "rmb200_split_joined_users_") + sfx)
         rc = fn(*common, ctypes.c_int32(n_users_test), frac, ctypes.c_int(int(consider_cold_start)), ctypes.c_int32(min_items_pool),
                 ctypes.c_int32(min_pos_test), ctypes.c_uint64(seed), ctypes.c_int32(device), ctypes.byref(out))
-    try:
-        raise_for_status(rc)
-        return {"train": _take_csr(out.train, dtype), "test": _take_csr(out.test, dtype), "rem": _take_csr(out.rem, dtype),
-                "users_test": _take(out.users_test, out.n_users_test, np.int32) if out.users_test else None,
-                "timing": {k: getattr(out, k) for k in Split.TIMING}}
-    finally:
-        lib.rmb200_split_free(ctypes.byref(out))
+    owner = _SplitOwner(lib, out)          # (releases the arrays when the last view goes away -- or right here if the call failed)
+    raise_for_status(rc)
+    return {"train": _view_csr(owner, out.train, dtype), "test": _view_csr(owner, out.test, dtype), "rem": _view_csr(owner, out.rem, dtype),
+            "users_test": _view(owner, out.users_test, out.n_users_test, np.int32) if out.users_test else None,
+            "timing": {k: getattr(out, k) for k in Split.TIMING}}
 
 
 def split_plan(indptr, m, n, sample_users, n_users_test=0, test_fraction=0.3, consider_cold_start=False, min_items_pool=2,

@@ -124,6 +124,13 @@ void pool_free(void* p)
     cudaFree(p);
 }
 
+}  // namespace
+namespace rmb {   // the same cache for the library's other translation units (split.cu)
+cudaError_t workspace_alloc(void** out, size_t bytes) { return pool_alloc(out, bytes); }
+void workspace_free(void* p) { pool_free(p); }
+}
+namespace {
+
 struct DevBuf {
     void* p = nullptr;
     DevBuf() = default;

@@ -35,6 +35,20 @@ def test_split_equals_reference_golden_and_oracle(rb, oracle_mod, name):
     assert t["rows_sorted_on_device"] == (1 if mk.get("unsorted") else 0)
 
 
+@pytest.mark.parametrize("knobs", [dict(RMB200_SPLIT_THREADS="0"), dict(RMB200_SPLIT_THREADS="3"),
+                                   dict(RMB200_SPLIT_THREADS="3", RMB200_SPLIT_SCOUT_FAULT="2")])
+def test_split_in_many_chunks_and_with_a_threaded_replay(rb, monkeypatch, knobs):
+    """Chunks of 150 entries: the device thread works through dozens of chunks behind the replay (which runs sequentially, on
+    several threads, and on several threads with its scout made to miscount once) -- same golden outputs."""
+    monkeypatch.setenv("RMB200_SPLIT_CHUNK", "150")
+    for k, val in knobs.items():
+        monkeypatch.setenv(k, val)
+    for name in ("split_all_f64", "split_all_unsorted_f64", "split_separated_f64", "split_joined_unsorted_f32", "split_all_long_rows_f32"):
+        mk, kw = split_cases.CASES[name]
+        p, i, v = split_cases.make_csr(**mk)
+        check_against_golden(name, split_cases.flatten(_product(rb, p, i, v, mk["m"], mk["n"], **kw)))
+
+
 @pytest.mark.parametrize("name", sorted(split_cases.REFUSALS))
 def test_split_refuses_with_the_reference_message(rb, name):
     mk, kw, message = split_cases.REFUSALS[name]

@@ -140,6 +140,29 @@ def test_host_plan_on_random_inputs(rb, oracle_mod):
     assert done > 80
 
 
+@pytest.mark.parametrize("knobs", [dict(RMB200_SPLIT_THREADS="0"), dict(RMB200_SPLIT_THREADS="3"),
+                                   dict(RMB200_SPLIT_THREADS="2", RMB200_SPLIT_SCOUT_FAULT="0"),
+                                   dict(RMB200_SPLIT_THREADS="3", RMB200_SPLIT_SCOUT_FAULT="3")])
+def test_host_plan_threaded_replay(rb, oracle_mod, monkeypatch, knobs):
+    """The replay of the random stream on several threads (recometrics_b200/csrc/split.cu, struct Replay): a scout runs ahead
+    counting the draws every std::shuffle will take, workers redo the chunks for real and publish them only if their generator
+    ends where the scout said.  Forced here on small inputs (chunks of 150 entries), with the scout made to MISCOUNT in one
+    chunk as well: the result must not change -- the disagreement is noticed and the rest replayed sequentially."""
+    from recometrics_b200 import _capi
+    monkeypatch.setenv("RMB200_SPLIT_CHUNK", "150")
+    for k, val in knobs.items():
+        monkeypatch.setenv(k, val)
+    for name in ("split_all_f64", "split_all_long_rows_f32", "split_separated_f32_strict", "split_joined_f64"):
+        mk, kw = split_cases.CASES[name]
+        kw = dict(kw)
+        p, i, v = split_cases.make_csr(**mk)
+        kind = kw.pop("split_type")
+        o = oracle_mod.oracle_split(p, i, v, mk["m"], mk["n"], split_type=kind, **kw)
+        frac = float(np.float32(kw["test_fraction"])) if v.dtype == np.float32 else kw["test_fraction"]
+        users, held = _capi.split_plan(p, mk["m"], mk["n"], kind != "all", **dict(kw, test_fraction=frac))
+        assert np.array_equal(held, _held_from_oracle(o, p, i, mk["m"], kind)), (name, knobs)
+
+
 @pytest.mark.parametrize("name", sorted(split_cases.REFUSALS))
 def test_host_plan_refuses_with_the_reference_message(rb, name):
     from recometrics_b200 import _capi
