@@ -457,6 +457,9 @@ def product_arm(args, cfg, rank, world, local_rank):
                   "max_abs_diff": worst, "nan_rows_cpu": int(np.isnan(np.asarray(cpu_rows[cfg.metrics[0]]).reshape(cu, -1)[:, 0]).sum()),
                   "against": "cpu_baseline rows (%s) vs the rows of the timed e2e call, same users" % kind}
 
+    split = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        split = split_block()
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -476,10 +479,39 @@ def product_arm(args, cfg, rank, world, local_rank):
             "e2e_pageable": e2e_pageable,
             "gpu_launches": int(launches) * world, "clocks": clocks, "per_rank": per_rank,
             "phases_ms_per_step": {k: round(v, 3) for k, v in phases.items()},
+            "split": split,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def split_block():
+    """A side measurement, NOT part of the headline: the step before the evaluation, one train/test
+    split of a MovieLens-20M-shaped matrix through the C-ABI (host buffers in, host arrays out) beside the reference's own
+    splitter on one host thread (it is sequential), outputs compared entry for entry.  Never fails the bench."""
+    try:
+        from recometrics_b200 import _capi
+        from tools.split_once import power_law_matrix
+        import oracle
+        m, n = 138493, 26744
+        p, i, v = power_law_matrix(m, n, 144.0)
+        best, res = None, None
+        for _ in range(4):
+            t0 = time.perf_counter()
+            res = _capi.split("all", p, i, v, m, n, test_fraction=0.3, seed=1)
+            ms = (time.perf_counter() - t0) * 1e3
+            best = ms if best is None else min(best, ms)
+        out = {"workload": "split_reco_train_test(split_type='all'): %d users x %d items, %d entries, f32" % (m, n, i.size),
+               "ms": round(best, 2), "entries_per_s": round(i.size / (best * 1e-3)), "library_timing": res["timing"]}
+        if oracle.have_ref():
+            t0 = time.perf_counter()
+            r = oracle.ref_split(p, i, v, m, n, split_type="all", test_fraction=0.3, seed=1)
+            out["reference_ms"] = round((time.perf_counter() - t0) * 1e3, 2)
+            out["identical_to_reference"] = bool(all(np.array_equal(x, y) for key in ("train", "test") for x, y in zip(r[key], res[key][:3])))
+        return out
+    except Exception as e:      # noqa: BLE001
+        return {"error": "%s: %s" % (type(e).__name__, e)}
 
 
 def main():
