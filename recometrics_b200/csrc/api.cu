@@ -468,6 +468,88 @@ cudaError_t upload_rows(void* dst, const void* src, size_t src_pitch, size_t row
     return cudaSuccess;
 }
 
+// The mirror image of upload_rows for one contiguous block: device memory to ordinary (pageable) host memory through the
+// lanes' pinned bounce buffers, every lane alternating between the DMA into one buffer and the memcpy out of the other.  The
+// driver's own path stages through one buffer and copies out on one thread (12 GB/s measured); this reaches what the host's
+// memory system gives several threads.  Work queued on `st` before the call is waited for; returns when the bytes are in dst.
+cudaError_t download_bytes(void* dst, const void* src, size_t total, cudaStream_t st)
+{
+    const int nt = upload_threads();
+    int dev = 0;
+    cudaGetDevice(&dev);
+    size_t min_bytes = 32u << 20;
+    if (const char* env = std::getenv("RMB200_UPLOAD_MIN_BYTES")) min_bytes = (size_t)std::atoll(env);      // developer / tests
+    if (total < min_bytes || nt == 0 || !host_pointer_is_pageable(dst) || !upload_pool_ready(dev, nt)) {
+        const cudaError_t e = cudaMemcpyAsync(dst, src, total, cudaMemcpyDeviceToHost, st);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+    }
+    UploadPool& g_up = g_ups[dev];
+    cudaEvent_t start = g_up.start;
+    cudaError_t e = cudaEventRecord(start, st);
+    if (e != cudaSuccess) return e;
+    const size_t nchunks = (total + UP_CHUNK - 1) / UP_CHUNK;
+    cudaError_t errs[UP_MAX_THREADS];
+    std::vector<std::thread> workers;
+    for (int t = 0; t < nt; t++) {
+        errs[t] = cudaSuccess;
+        workers.emplace_back([&, t]() {
+            cudaError_t er = cudaSetDevice(dev);
+            UploadLane& L = g_up.lane[t];
+            if (er == cudaSuccess) er = cudaStreamWaitEvent(L.st, start, 0);
+            // (an earlier UPLOAD may still be reading the bounce buffers: its events come first)
+            for (int b = 0; b < 2 && er == cudaSuccess; b++) if (L.recorded[b]) er = cudaEventSynchronize(L.ev[b]);
+            auto span = [&](size_t c, size_t* off) { *off = c * UP_CHUNK; return (total - *off) < UP_CHUNK ? (total - *off) : UP_CHUNK; };
+            auto fetch = [&](size_t c, int b) {
+                size_t off; const size_t nb = span(c, &off);
+                cudaError_t x = cudaMemcpyAsync(L.buf[b], static_cast<const unsigned char*>(src) + off, nb, cudaMemcpyDeviceToHost, L.st);
+                if (x == cudaSuccess) { x = cudaEventRecord(L.ev[b], L.st); L.recorded[b] = true; }
+                return x;
+            };
+            int b = 0;
+            if (er == cudaSuccess && (size_t)t < nchunks) er = fetch((size_t)t, 0);
+            for (size_t c = (size_t)t; c < nchunks && er == cudaSuccess; c += (size_t)nt, b ^= 1) {
+                if (c + (size_t)nt < nchunks) er = fetch(c + (size_t)nt, b ^ 1);       // the next chunk's DMA runs under this chunk's memcpy
+                if (er == cudaSuccess) er = cudaEventSynchronize(L.ev[b]);
+                if (er != cudaSuccess) break;
+                size_t off; const size_t nb = span(c, &off);
+                std::memcpy(static_cast<unsigned char*>(dst) + off, L.buf[b], nb);
+            }
+            errs[t] = er;
+        });
+    }
+    for (auto& w : workers) w.join();
+    for (int t = 0; t < nt; t++) if (errs[t] != cudaSuccess) return errs[t];
+    return cudaSuccess;
+}
+
+}  // namespace
+namespace rmb {   // the pageable-memory copy pipelines for the library's other translation units (split.cu).  The lanes belong
+                  // to whoever holds the call mutex: a split that runs beside an evaluation call takes the driver's plain path.
+cudaError_t upload_bytes_pageable(void* dst, const void* src, size_t bytes, cudaStream_t st, int share)
+{
+    std::unique_lock<std::mutex> lk(g_call_mutex, std::try_to_lock);
+    if (!lk.owns_lock()) return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+    g_upload_share = share > 1 ? share : 1;
+    const cudaError_t e = bytes ? upload_rows(dst, src, bytes, bytes, 1, st) : cudaSuccess;
+    g_upload_share = 1;
+    return e;
+}
+cudaError_t download_bytes_pageable(void* dst, const void* src, size_t bytes, cudaStream_t st, int share)
+{
+    if (!bytes) return cudaSuccess;
+    std::unique_lock<std::mutex> lk(g_call_mutex, std::try_to_lock);
+    if (!lk.owns_lock()) {
+        const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+        return e != cudaSuccess ? e : cudaStreamSynchronize(st);
+    }
+    g_upload_share = share > 1 ? share : 1;
+    const cudaError_t e = download_bytes(dst, src, bytes, st);
+    g_upload_share = 1;
+    return e;
+}
+}
+namespace {
+
 // The user factors are uploaded one user batch ahead, on a stream of their own, into two alternating staging buffers:
 // the upload of batch b+1 runs while the scoring kernel of batch b does.  ready[s]: the upload into buffer s has landed;
 // freed[s]: the kernels that read buffer s have run.

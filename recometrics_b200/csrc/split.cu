@@ -56,6 +56,10 @@ namespace rmb {   // api.cu
 void set_last_error(const char* what, const char* detail);
 cudaError_t workspace_alloc(void** out, size_t bytes);      // device blocks cached between calls (rmb200_release_workspace() frees them)
 void workspace_free(void* p);
+// pageable host memory <-> device through several copy threads and pinned bounce buffers (the evaluation path's upload pipeline
+// and its mirror image); `share`: divide the host's copy threads by this much.  The download returns when the bytes are there.
+cudaError_t upload_bytes_pageable(void* dst, const void* src, size_t bytes, cudaStream_t st, int share);
+cudaError_t download_bytes_pageable(void* dst, const void* src, size_t bytes, cudaStream_t st, int share);
 }
 
 namespace {
@@ -66,6 +70,26 @@ double ms_since(clk::time_point t0) { return std::chrono::duration<double, std::
 // ------------------------------------------------------------------------------------------------------------------
 // Host: the replay of the reference's random stream
 // ------------------------------------------------------------------------------------------------------------------
+// zero-filled bytes that cost nothing until they are written (calloc hands out untouched pages; a std::vector would fault
+// and fill all of them up front, on the call's critical path: 2-12 ms for 19 MB)
+struct ZeroedBytes {
+    uint8_t* p = nullptr;
+    size_t n = 0;
+    ZeroedBytes() = default;
+    ZeroedBytes(const ZeroedBytes&) = delete;
+    ZeroedBytes& operator=(const ZeroedBytes&) = delete;
+    ~ZeroedBytes() { std::free(p); }
+    void reset(size_t count)
+    {
+        std::free(p);
+        n = count;
+        p = (uint8_t*)std::calloc(count ? count : 1, 1);
+        if (!p) throw std::bad_alloc();
+    }
+    uint8_t* data() const { return p; }
+    size_t size() const { return n; }
+};
+
 struct SplitPlan {
     bool whole = true;                 // every row of X is split, in place (split_data_selected_users)
     std::vector<int32_t> sel_rows;     // rows of X that are split, ascending (empty when `whole`)
@@ -74,7 +98,7 @@ struct SplitPlan {
     std::vector<int32_t> test_p;       // [ns+1]
     std::vector<int32_t> train_p;      // [ns+1]
     std::vector<int32_t> rem_p;        // [nr+1]
-    std::vector<uint8_t> held;         // [nnz of the split rows] 1 = held out
+    ZeroedBytes held;                  // [nnz of the split rows] 1 = held out
     std::vector<int32_t> chunk_end;    // row after the last row of each chunk (ascending, last = ns)
     int32_t ns = 0, nr = 0, longest = 0;
 };
@@ -553,19 +577,25 @@ struct DeviceJob {
         JOB_CUDA(cudaEventCreate(&ev1.e));
         const cudaStream_t st = stream.s;
         dbg_setup = ms_since(t_setup);
+        const bool plain_copies = []() { const char* e = std::getenv("RMB200_SPLIT_PLAIN_COPIES"); return e && e[0] == '1'; }();
         auto up = [&](void* dst, const void* src, size_t bytes) {
             h2d_bytes += (int64_t)bytes;
-            return bytes ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : cudaSuccess;
+            if (!bytes) return cudaSuccess;
+            return plain_copies ? cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, st) : rmb::upload_bytes_pageable(dst, src, bytes, st, 2);
         };
         auto down = [&](void* dst, const void* src, size_t bytes) {     // (pageable destination: returns when the bytes are there)
             if (!bytes) return cudaSuccess;
             sig->wait([&]() { return touched->load(std::memory_order_acquire) != 0; });
             const auto t0 = clk::now();
-            const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
-            const cudaError_t e2 = cudaStreamSynchronize(st);
+            cudaError_t e;
+            if (plain_copies) {
+                e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+                const cudaError_t e2 = cudaStreamSynchronize(st);
+                if (e == cudaSuccess) e = e2;
+            } else e = rmb::download_bytes_pageable(dst, src, bytes, st, 2);
             d2h_ms += ms_since(t0);
             d2h_bytes += (int64_t)bytes;
-            return e != cudaSuccess ? e : e2;
+            return e;
         };
         float span = 0.f;
         auto kernels_begin = [&]() { return cudaEventRecord(ev0.e, st); };
@@ -764,7 +794,7 @@ int run_split_impl(SplitKind kind, const int32_t* Xp, const int32_t* Xi, const T
     const int32_t ns = P.ns, nr = P.nr;
     const int64_t sel_nnz = P.sel_p[ns], test_nnz = P.test_p[ns], rem_nnz = nr ? P.rem_p[nr] : 0;
     const int64_t train_nnz = sel_nnz - test_nnz + (kind == SPLIT_JOINED ? rem_nnz : 0);
-    P.held.assign((size_t)sel_nnz, 0);
+    P.held.reset((size_t)sel_nnz);
 
     // ---- the result (host side): pointer arrays come straight from the plan ----
     SplitOwner* own = new (std::nothrow) SplitOwner();
@@ -909,7 +939,7 @@ int rmb200_split_plan(const int32_t* Xp, int32_t m, int32_t n, int32_t sample_us
                 return fail(RMB200_ERR_RUNTIME, refusal);
         }
         count_rows(Xp, P.whole ? nullptr : P.sel_rows.data(), P.whole ? m : (int32_t)P.sel_rows.size(), test_fraction, P);
-        P.held.assign((size_t)P.sel_p[P.ns], 0);
+        P.held.reset((size_t)P.sel_p[P.ns]);
         std::unique_ptr<std::atomic<int>[]> chunk_done(new std::atomic<int>[P.chunk_end.size()]);
         for (size_t c = 0; c < P.chunk_end.size(); c++) chunk_done[c].store(0);
         std::atomic<int> stop{0};
