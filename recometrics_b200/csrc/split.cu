@@ -34,6 +34,7 @@
 #include <cmath>
 #include <cstdio>
 #include <condition_variable>
+#include <deque>
 #include <memory>
 #include <mutex>
 #include <exception>
@@ -514,6 +515,66 @@ int fail(int code, const char* what, const char* detail = nullptr)
 
 enum SplitKind { SPLIT_WHOLE = 0, SPLIT_SEPARATE = 1, SPLIT_JOINED = 2 };
 
+// Result pieces on their way back to the host: a few threads, each with a stream of its own, copy finished pieces into the
+// (pageable, already touched) result arrays while the device thread goes on with the next chunk.  Two copies in flight also
+// means two host threads doing the driver's staging memcpy: ~2x the 12 GB/s of one blocking copy after the other.
+struct Downloads {
+    struct Piece { void* dst; const void* src; size_t bytes; };
+    std::mutex mu;
+    std::condition_variable cv;
+    std::deque<Piece> queue;
+    bool closing = false;
+    cudaError_t err = cudaSuccess;
+    double copy_ms = 0.0;              // summed over the threads
+    std::vector<std::thread> threads;
+
+    void start(int device, int n, Signal* sig, std::atomic<int>* touched)
+    {
+        for (int t = 0; t < n; t++)
+            threads.emplace_back([this, device, sig, touched]() {
+                cudaStream_t st = nullptr;
+                cudaError_t e = cudaSetDevice(device);
+                if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+                sig->wait([&]() { return touched->load(std::memory_order_acquire) != 0; });
+                double ms = 0.0;
+                for (;;) {
+                    Piece p;
+                    {
+                        std::unique_lock<std::mutex> lk(mu);
+                        cv.wait(lk, [&]() { return closing || !queue.empty(); });
+                        if (queue.empty()) break;
+                        p = queue.front();
+                        queue.pop_front();
+                    }
+                    if (e != cudaSuccess) continue;            // (drain the queue; the error is reported at finish())
+                    const auto t0 = clk::now();
+                    e = cudaMemcpyAsync(p.dst, p.src, p.bytes, cudaMemcpyDeviceToHost, st);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+                    ms += ms_since(t0);
+                }
+                if (st) cudaStreamDestroy(st);
+                std::lock_guard<std::mutex> lk(mu);
+                copy_ms += ms;
+                if (e != cudaSuccess && err == cudaSuccess) err = e;
+            });
+    }
+    void push(void* dst, const void* src, size_t bytes)
+    {
+        if (!bytes) return;
+        { std::lock_guard<std::mutex> lk(mu); queue.push_back(Piece{dst, src, bytes}); }
+        cv.notify_one();
+    }
+    cudaError_t finish()
+    {
+        { std::lock_guard<std::mutex> lk(mu); closing = true; }
+        cv.notify_all();
+        for (auto& t : threads) if (t.joinable()) t.join();
+        threads.clear();
+        return err;
+    }
+    ~Downloads() { finish(); }
+};
+
 // The device side of one call, run on its own host thread.
 template <typename T>
 struct DeviceJob {
@@ -711,6 +772,14 @@ struct DeviceJob {
         }
 
         // ---- the split rows, chunk by chunk behind the replay ----
+        Downloads downloads;
+        if (!plain_copies) downloads.start(device, 2, sig, touched);
+        auto down_later = [&](void* dst, const void* src, size_t bytes) {
+            if (plain_copies) return down(dst, src, bytes);
+            d2h_bytes += (int64_t)bytes;
+            downloads.push(dst, src, bytes);
+            return cudaSuccess;
+        };
         int32_t r0 = 0;
         for (size_t c = 0; c < Q.chunk_end.size(); c++) {
             const int32_t r1 = Q.chunk_end[c];
@@ -738,13 +807,16 @@ struct DeviceJob {
                 JOB_CUDA(cudaGetLastError());
                 JOB_CUDA(kernels_end());
                 const int k0 = j0 - t0, k1 = j1 - t1;      // the chunk's training entries
-                JOB_CUDA(down(out->train.indices + k0, d_tri.as<int>() + k0, sizeof(int32_t) * (size_t)(k1 - k0)));
-                JOB_CUDA(down((T*)out->train.values + k0, d_trv.as<T>() + k0, sizeof(T) * (size_t)(k1 - k0)));
-                JOB_CUDA(down(out->test.indices + t0, d_tei.as<int>() + t0, sizeof(int32_t) * (size_t)(t1 - t0)));
-                JOB_CUDA(down((T*)out->test.values + t0, d_tev.as<T>() + t0, sizeof(T) * (size_t)(t1 - t0)));
+                // (kernels_end() has waited for the chunk's kernels: its pieces may leave on the copy threads' own streams)
+                JOB_CUDA(down_later(out->train.indices + k0, d_tri.as<int>() + k0, sizeof(int32_t) * (size_t)(k1 - k0)));
+                JOB_CUDA(down_later((T*)out->train.values + k0, d_trv.as<T>() + k0, sizeof(T) * (size_t)(k1 - k0)));
+                JOB_CUDA(down_later(out->test.indices + t0, d_tei.as<int>() + t0, sizeof(int32_t) * (size_t)(t1 - t0)));
+                JOB_CUDA(down_later((T*)out->test.values + t0, d_tev.as<T>() + t0, sizeof(T) * (size_t)(t1 - t0)));
             }
             r0 = r1;
         }
+        JOB_CUDA(downloads.finish());
+        d2h_ms += downloads.copy_ms;          // (thread time: two copies run side by side)
         dbg_end = clk::now();
 #undef JOB_CUDA
     }
