@@ -49,6 +49,36 @@ def test_split_in_many_chunks_and_with_a_threaded_replay(rb, monkeypatch, knobs)
         check_against_golden(name, split_cases.flatten(_product(rb, p, i, v, mk["m"], mk["n"], **kw)))
 
 
+def test_split_through_the_pageable_copy_pipelines(rb, oracle_mod, monkeypatch):
+    """X goes up and the untouched users' rows come down through the library's copy pipelines for pageable memory (several
+    copy threads + pinned bounce buffers, recometrics_b200/csrc/api.cu upload_rows / download_bytes) once a block reaches
+    32 MB.  Forced here on small blocks (RMB200_UPLOAD_MIN_BYTES=1), and run on blocks of several bounce buffers each
+    (2 M entries: 8 MB per index array and per lane buffer), against the oracle."""
+    monkeypatch.setenv("RMB200_UPLOAD_MIN_BYTES", "1")
+    for name in ("split_separated_f64", "split_joined_f64", "split_all_f32_half"):
+        mk, kw = split_cases.CASES[name]
+        p, i, v = split_cases.make_csr(**mk)
+        check_against_golden(name, split_cases.flatten(_product(rb, p, i, v, mk["m"], mk["n"], **kw)))
+    m, n = 60000, 30000
+    rs = np.random.RandomState(8)
+    lens = np.minimum(n - 2, (rs.pareto(1.4, m) * 40 + 1).astype(np.int64))
+    indptr = np.zeros(m + 1, np.int32)
+    indptr[1:] = np.cumsum(lens)
+    nnz = int(indptr[-1])
+    row_of = np.repeat(np.arange(m), lens)
+    step = np.maximum(1, (n - 1) // np.maximum(lens[row_of], 1))
+    indices = ((np.arange(nnz) - indptr[row_of]) * step + rs.randint(0, 1 << 30, size=m)[row_of] % step).astype(np.int32)
+    data = ((np.arange(nnz) % 89) + 1).astype(np.float64)
+    assert nnz > 5_000_000
+    for kind in ("separated", "joined"):
+        kw = dict(split_type=kind, n_users_test=3000, test_fraction=0.3, consider_cold_start=False, min_items_pool=2, min_pos_test=1, seed=6)
+        got = split_cases.flatten(_product(rb, indptr, indices, data, m, n, **kw))
+        want = split_cases.flatten(oracle_mod.oracle_split(indptr, indices, data, m, n, **kw))
+        assert set(got) == set(want)
+        for k in want:
+            assert np.array_equal(got[k], want[k]), (kind, k)
+
+
 @pytest.mark.parametrize("name", sorted(split_cases.REFUSALS))
 def test_split_refuses_with_the_reference_message(rb, name):
     mk, kw, message = split_cases.REFUSALS[name]
