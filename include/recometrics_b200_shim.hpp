@@ -203,6 +203,7 @@ inline void calc_metrics_float
 }
 
 
+#ifndef RMB200_SHIM_NO_SPLITTERS   /* define it to keep the reference's CPU splitters (src/recometrics_instantiated.cpp) */
 /* ---------------------------------------------------------------------------------------------------------------------
  * Train/test splitters.  The reference fills std::vectors; the C-ABI hands out one rmb200_split_t of library-owned arrays
  * that are copied into the caller's vectors and released (also when the copy throws).
@@ -368,6 +369,7 @@ inline void split_data_joined_users_##SUFFIX(const int32_t *restrict X_csr_p, co
 RMB200_SHIM_SPLIT_LINKAGE(double, double, double)
 RMB200_SHIM_SPLIT_LINKAGE(float, float, float)
 #undef RMB200_SHIM_SPLIT_LINKAGE
+#endif /* RMB200_SHIM_NO_SPLITTERS */
 
 #ifdef RMB200_SHIM_DEFINED_RESTRICT
 #   undef restrict
