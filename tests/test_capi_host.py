@@ -22,7 +22,10 @@ def _declared_symbols():
 def test_header_declares_the_boundary():
     names = _declared_symbols()
     for want in ("rmb200_calc_metrics_f32", "rmb200_calc_metrics_f64", "rmb200_calc_metrics_ex_f32",
-                 "rmb200_calc_metrics_ex_f64", "rmb200_last_error", "rmb200_device_count"):
+                 "rmb200_calc_metrics_ex_f64", "rmb200_last_error", "rmb200_device_count",
+                 "rmb200_split_selected_users_f32", "rmb200_split_selected_users_f64", "rmb200_split_separate_users_f32",
+                 "rmb200_split_separate_users_f64", "rmb200_split_joined_users_f32", "rmb200_split_joined_users_f64",
+                 "rmb200_split_free"):
         assert want in names
 
 
@@ -47,6 +50,30 @@ def test_extra_struct_layout_matches_header(rb):
     lib = _capi.load()          # the sizes the library itself was compiled with
     assert lib.rmb200_sizeof_extra() == ctypes.sizeof(_capi.Extra)
     assert lib.rmb200_sizeof_timing() == ctypes.sizeof(_capi.Timing)
+
+
+def test_split_struct_layout_matches_header(rb):
+    """ctypes mirror of rmb200_csr_t / rmb200_split_t (LP64)."""
+    from recometrics_b200 import _capi
+    assert ctypes.sizeof(_capi.Csr) == 2 * 4 + 8 + 3 * 8
+    assert ctypes.sizeof(_capi.Split) == 3 * 40 + 8 + 4 * 4 + 5 * 8 + 3 * 8 + 8
+    assert _capi.Split.users_test.offset == 120 and _capi.Split.total_ms.offset == 144 and _capi.Split.owner.offset == 208
+    assert _capi.load().rmb200_sizeof_split() == ctypes.sizeof(_capi.Split)
+
+
+def test_no_device_means_no_split_either(rb):
+    """The splitters need the GPU for every matrix they return: without one the call fails (RMB200_ERR_NO_DEVICE) after the
+    reference's own argument checks -- which still answer first, with the reference's messages."""
+    from recometrics_b200 import _capi
+    if _capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    from tools import split_cases
+    p, i, v = split_cases.make_csr(m=50, n=80, seed=21)
+    for kind in ("all", "separated", "joined"):
+        with pytest.raises(RuntimeError, match="no CPU"):
+            _capi.split(kind, p, i, v, 50, 80, n_users_test=5)
+    with pytest.raises(RuntimeError, match="Target number of test users is larger"):
+        _capi.split("separated", p, i, v, 50, 80, n_users_test=51)
 
 
 def test_no_device_means_error_not_fallback(rb):
