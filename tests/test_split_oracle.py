@@ -163,6 +163,32 @@ def test_host_plan_threaded_replay(rb, oracle_mod, monkeypatch, knobs):
         assert np.array_equal(held, _held_from_oracle(o, p, i, mk["m"], kind)), (name, knobs)
 
 
+def test_host_plan_threaded_replay_randomised(rb, monkeypatch):
+    """A few hundred calls with random worker counts, both forms of the scout, random injected miscounts and seeds beyond 32 bits,
+    on rows that reach the shuffle's second regime (65,536 entries and more): always the bytes of the sequential replay."""
+    from recometrics_b200 import _capi
+    rs = np.random.RandomState(11)
+    p, i, v = split_cases.make_csr(m=1500, n=70001, seed=31, mean_len=12.0, heavy_rows=(66000, 65535, 2, 3, 4, 5))
+    for seed in (9, 2 ** 32 + 5, 2 ** 63 + 12345):
+        monkeypatch.setenv("RMB200_SPLIT_THREADS", "0")
+        monkeypatch.delenv("RMB200_SPLIT_SCOUT_FAULT", raising=False)
+        _, ref = _capi.split_plan(p, 1500, 70001, False, test_fraction=0.35, seed=seed)
+        monkeypatch.setenv("RMB200_SPLIT_CHUNK", "9000")
+        for _ in range(60):
+            monkeypatch.setenv("RMB200_SPLIT_THREADS", str(rs.randint(1, 7)))
+            if rs.rand() < 0.5:
+                monkeypatch.setenv("RMB200_SPLIT_PLAIN_SCOUT", "1")
+            else:
+                monkeypatch.delenv("RMB200_SPLIT_PLAIN_SCOUT", raising=False)
+            fault = int(rs.randint(-1, 20))
+            if fault >= 0:
+                monkeypatch.setenv("RMB200_SPLIT_SCOUT_FAULT", str(fault))
+            else:
+                monkeypatch.delenv("RMB200_SPLIT_SCOUT_FAULT", raising=False)
+            _, held = _capi.split_plan(p, 1500, 70001, False, test_fraction=0.35, seed=seed)
+            assert np.array_equal(held, ref), (seed, fault)
+
+
 @pytest.mark.parametrize("name", sorted(split_cases.REFUSALS))
 def test_host_plan_refuses_with_the_reference_message(rb, name):
     from recometrics_b200 import _capi
