@@ -35,6 +35,7 @@
 #include <cstdio>
 #include <condition_variable>
 #include <deque>
+#include <locale>
 #include <memory>
 #include <mutex>
 #include <exception>
@@ -261,6 +262,7 @@ public:
         for (int k = 0; k < 624; k++) { text += std::to_string(x[k]); text += ' '; }
         text += std::to_string(p);
         std::istringstream is(text);
+        is.imbue(std::locale::classic());     // (whatever the host application did to the global locale)
         std::mt19937 g;
         is >> g;
         return g;
