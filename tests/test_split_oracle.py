@@ -49,6 +49,42 @@ def test_oracle_refuses_what_the_reference_refuses(oracle_mod, name):
             oracle_mod.ref_split(p, i, v, mk["m"], mk["n"], **kw)
 
 
+def test_oracle_satisfies_the_invariants_of_the_reference_r_tests(oracle_mod):
+    """tests/testthat/test-split.R:7-93 of the reference, on the oracle: X_train + X_test == X[users_test, ], shapes, a fixed
+    number of users, the error when no user can meet the criteria."""
+    import scipy.sparse as sp
+
+    def rsparse(m, n, density, seed):
+        X = sp.random(m, n, density=density, format="csr", random_state=seed, dtype=np.float64)
+        X.data = np.round(X.data * 10 + 1)
+        X.sort_indices()
+        return sp.csr_array(X)
+
+    def mat(parts, n):
+        p, i, v = parts
+        return sp.csr_array((v, i, p), shape=(len(p) - 1, n))
+
+    for n in (10000, 3):
+        X = rsparse(1000, n, 0.01, 123)
+        o = oracle_mod.oracle_split(X.indptr, X.indices, X.data, 1000, n, split_type="all", test_fraction=0.3)
+        assert abs((mat(o["train"], n) + mat(o["test"], n)) - X).sum() == 0
+    X = rsparse(1000, 10000, 0.01, 123)
+    o = oracle_mod.oracle_split(X.indptr, X.indices, X.data, 1000, 10000, split_type="separated", n_users_test=100, test_fraction=0.3)
+    ut = o["users_test"]
+    assert len(ut) == 100 and abs((mat(o["train"], 10000) + mat(o["test"], 10000)) - X[ut, :]).sum() == 0
+    assert mat(o["rem"], 10000).shape[0] == 900
+    o = oracle_mod.oracle_split(X.indptr, X.indices, X.data, 1000, 10000, split_type="joined", n_users_test=100, test_fraction=0.3)
+    tr, te = mat(o["train"], 10000), mat(o["test"], 10000)
+    assert tr.shape[0] == 1000 and te.shape[0] == 100
+    assert abs((tr[:100, :] + te) - X[o["users_test"], :]).sum() == 0
+    X = rsparse(10, 9, 0.5, 123)
+    o = oracle_mod.oracle_split(X.indptr, X.indices, X.data, 10, 9, split_type="separated", n_users_test=2, test_fraction=0.3)
+    assert len(o["users_test"]) == 2 and len(o["rem"][0]) - 1 == 8
+    X = rsparse(1000, 3, 0.01, 1)
+    with pytest.raises(RuntimeError, match="No users satisfy criteria"):
+        oracle_mod.oracle_split(X.indptr, X.indices, X.data, 1000, 3, split_type="separated", n_users_test=100, test_fraction=0.3, min_pos_test=2)
+
+
 def _random_case(rs):
     m, n = int(rs.randint(2, 300)), int(rs.randint(3, 2000))
     dtype = np.float32 if rs.rand() < 0.5 else np.float64
