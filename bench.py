@@ -351,7 +351,7 @@ def product_arm(args, cfg, rank, world, local_rank):
 
     # ---- roofline of the dominant kernel (score_select): algorithmic flops / CUDA-event kernel time
     ach = flops * args.steps / (kernel_ms * 1e-3) / 1e12
-    traffic, traffic_note = None, None
+    traffic, traffic_note, captured_users = None, None, None
     tpath = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tpath):
         try:
@@ -362,11 +362,21 @@ def product_arm(args, cfg, rank, world, local_rank):
                 if traffic.get("sources_hash") not in (None, now):
                     traffic_note += "; NOTE: captured on %s %s, this build has %s (the kernel source changed since the capture)" % (
                         traffic.get("kernel_source", "sources"), traffic.get("sources_hash"), now)
+                captured_users = traffic.get("users_per_launch")
                 traffic = int(traffic["dram_bytes_read"]) + int(traffic["dram_bytes_write"])
         except Exception:
             traffic = None
     big = path == 2 and (-(-n // 128) * 128) * (-(-(p + (1 if bias is not None else 0)) // 16) * 16) * 2 > (160 << 20)
     batches = -(-m // ((4 if big else 8) * 148 * 128))      # (api.cu: a user batch is 8 waves of 148 CTAs x 128 users, 4 on very large catalogues)
+    users_per_launch = min(m, (4 if big else 8) * 148 * 128)
+    try:
+        if traffic is not None and captured_users and int(captured_users) != users_per_launch:
+            # every wave of 148 CTAs streams the item image once: DRAM bytes of a launch go with its number of waves
+            traffic = int(round(traffic * users_per_launch / int(captured_users)))
+            traffic_note = (traffic_note or "") + "; scaled by %d/%d: the capture was a launch of %d users, a launch of this run has %d" % (
+                users_per_launch, int(captured_users), int(captured_users), users_per_launch)
+    except Exception:       # noqa: BLE001  (bookkeeping must never fail the bench)
+        pass
     if path == 2:
         # tensor-core filter: every (user, item) score is an MMA on fp16 copies of the factors (tcgen05 kind::f16 runs
         # fp16 and bf16 operands at the same rate); the measured denominator is the driver's cuBLAS bf16 figure
