@@ -48,49 +48,46 @@ def split_reco_train_test(X, split_type="separated", users_test_fraction=0.1, ma
 
     Extensions: ``device`` (CUDA ordinal, -1 = current) and ``return_timing`` (appends the call's timing dict to the tuple).
     """
-    if (max_test_users is None) or (max_test_users == 0):
-        max_test_users = X.shape[0]
+    # The reference's argument handling (recometrics/__init__.py:764-808), check for check and in its order.  It uses bare
+    # `assert`s: the same AssertionError is raised here explicitly, so that `python -O` does not switch the checks off.
+    def require(condition):
+        if not condition:
+            raise AssertionError()
 
-    assert max_test_users > 0
-    assert seed >= 0
-    assert min_pos_test >= 0
-    assert min_items_pool >= 0
-
-    max_test_users = int(max_test_users)
-    seed = int(seed)
-    min_pos_test = int(min_pos_test)
-    min_items_pool = int(min_items_pool)
-
+    n_rows, n_cols = X.shape[0], X.shape[1]
+    if not max_test_users:                       # None or 0: "as many as there are"
+        max_test_users = n_rows
+    require(max_test_users > 0)
+    for lower_bounded in (seed, min_pos_test, min_items_pool):
+        require(lower_bounded >= 0)
+    max_test_users, seed = int(max_test_users), int(seed)
+    min_pos_test, min_items_pool = int(min_pos_test), int(min_items_pool)
     if users_test_fraction is not None:
-        assert (users_test_fraction > 0) and (users_test_fraction < 1)
+        require(0 < users_test_fraction < 1)
         users_test_fraction = float(users_test_fraction)
-
-    assert (items_test_fraction > 0) and (items_test_fraction < 1)
+    require(0 < items_test_fraction < 1)
     items_test_fraction = float(items_test_fraction)
-
-    assert split_type in ("all", "separated", "joined")
+    require(split_type in ("all", "separated", "joined"))
     consider_cold_start = bool(consider_cold_start)
 
-    if min_pos_test >= X.shape[1]:
-        raise ValueError("'min_pos_test' must be smaller than the number of columns in 'X'.")
-    if min_items_pool >= X.shape[1]:
-        raise ValueError("'min_items_pool' must be smaller than the number of columns in 'X'.")
+    for name, value in (("min_pos_test", min_pos_test), ("min_items_pool", min_items_pool)):
+        if value >= n_cols:
+            raise ValueError("'%s' must be smaller than the number of columns in 'X'." % name)
 
     n_users_take = 0
     if split_type != "all":
-        if X.shape[0] < 2:
+        if n_rows < 2:
             raise ValueError("'X' has less than 2 rows.")
-        if users_test_fraction is not None:
-            n_users_take = X.shape[0] * users_test_fraction
-            if n_users_take < 1:
-                warn("Desired fraction of test users implies <1, will select 1 user.")
-                n_users_take = 1
-            n_users_take = round(n_users_take)
-            n_users_take = min(n_users_take, max_test_users)
-        else:
-            if max_test_users > X.shape[0]:
+        if users_test_fraction is None:
+            if max_test_users > n_rows:
                 warn("'max_test_users' is larger than number of users. Will take all.")
-            n_users_take = min(max_test_users, X.shape[0])
+            n_users_take = min(max_test_users, n_rows)
+        else:
+            wanted = n_rows * users_test_fraction
+            if wanted < 1:
+                warn("Desired fraction of test users implies <1, will select 1 user.")
+                wanted = 1
+            n_users_take = min(round(wanted), max_test_users)
 
     X = _as_csr(X)
     if (not X.shape[0]) or (not X.shape[1]):
